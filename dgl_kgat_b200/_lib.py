@@ -1,0 +1,97 @@
+"""ctypes binding of libkgat_b200.so (the C ABI declared in include/kgat_b200.h).
+
+There is no CPU fallback: if the shared library is missing or the current device
+is not an sm_100 GPU every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libkgat_b200.so")
+
+c_i32p = C.c_void_p     # device pointers travel as plain addresses
+c_f32p = C.c_void_p
+
+
+class KgatGraph(C.Structure):
+    """Mirror of ``kgat_graph_t``."""
+    _fields_ = [("n_nodes", C.c_int64), ("n_edges", C.c_int64), ("n_rel", C.c_int64)] + [
+        (name, C.c_void_p) for name in (
+            "csr_ptr", "csr_src", "csr_dst", "csr_rel", "csr_eid",
+            "csc_ptr", "csc_dst", "csc_pos", "csc_eid",
+            "rel_ptr", "bk_pos", "bk_head", "bk_tail")]
+
+
+GRAPH_ARRAYS = [name for name, _ in KgatGraph._fields_[3:]]
+
+# name -> (restype, argtypes); must list every KGAT_API symbol of the header
+_GP = C.POINTER(KgatGraph)
+SIGNATURES = {
+    "kgat_version": (C.c_int, []),
+    "kgat_error_string": (C.c_char_p, [C.c_int]),
+    "kgat_last_cuda_error": (C.c_int, []),
+    "kgat_device_check": (C.c_int, []),
+    "kgat_graph_build_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
+    "kgat_graph_build": (C.c_int, [_GP, c_i32p, c_i32p, c_i32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kgat_attention_logits": (C.c_int, [_GP, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, C.c_void_p]),
+    "kgat_segment_softmax": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "kgat_edge_weights_from_eid": (C.c_int, [_GP, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "kgat_layer_fwd": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int,
+                                 C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int64,
+                                 C.c_void_p]),
+    "kgat_layer_bwd_partials": (C.c_int, []),
+    "kgat_layer_bwd": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p,
+                                 c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_float,
+                                 c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "kgat_input_bwd": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p,
+                                 C.c_int, c_f32p, C.c_void_p]),
+    "kgat_score_topk": (C.c_int, [c_f32p, C.c_int64, C.c_int, c_i32p, C.c_int64, c_i32p, C.c_int64, c_i32p, c_i32p,
+                                  C.c_int, c_i32p, c_f32p, C.c_void_p]),
+}
+
+
+class KgatError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KgatError(
+            "libkgat_b200.so is missing (%s).  Build it with `python -m dgl_kgat_b200.build`; "
+            "there is no CPU or PyTorch fallback for the KGAT hot path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        lib = load()
+        msg = lib.kgat_error_string(status).decode()
+        extra = ""
+        if status == -4:
+            extra = " (cudaError %d)" % lib.kgat_last_cuda_error()
+        raise KgatError("%s failed: %s%s" % (what or "kgat call", msg, extra))
+
+
+def ptr(t):
+    """Device address of a tensor, or None for a null argument."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

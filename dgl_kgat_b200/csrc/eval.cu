@@ -1,0 +1,160 @@
+// (5) Full-rank user x item scoring with a fused per-row top-K.
+//
+// Replaces the per-user Python loop of the reference (metric.py:44-51): gather the item matrix,
+// emb_u @ emb_items^T, score[train items] = 0.0, full descending sort.  Here one CTA owns BM eval
+// users and walks the item axis in BN-wide tiles: an fp32 register-tiled GEMM produces a BM x BN
+// score tile in shared memory, then one thread per user applies the mask-to-0.0 quirk
+// (metric.py:50) and merges the tile into that user's running top-K list.  The U x I score matrix
+// (7 GB at Amazon-book shape) never exists.  Ties -> lower item position first: items are visited in
+// ascending order and a candidate only displaces an entry it beats strictly.
+#include "common.cuh"
+
+#include <limits.h>
+
+namespace kgat {
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, EV_THREADS = 256;
+constexpr int LDT = BM + 4;      // padded leading dimension of the transposed operand tiles
+constexpr int MAX_K = 64;
+
+__global__ void __launch_bounds__(EV_THREADS)
+score_topk_kernel(const float* __restrict__ emb, int64_t stride, int dim,
+                  const int32_t* __restrict__ user_ids, int n_users,
+                  const int32_t* __restrict__ item_ids, int n_items,
+                  const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items,
+                  int K, int32_t* __restrict__ topk_idx, float* __restrict__ topk_score) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sU = reinterpret_cast<float*>(smem_raw);       // [BK][LDT]  sU[k][m]
+    float* sI = sU + BK * LDT;                            // [BK][LDT]  sI[k][n]
+    float* sS = sI + BK * LDT;                            // [BM][BN+1]
+    float* sLs = sS + BM * (BN + 1);                      // [BM][K] scores, descending
+    int* sLi = reinterpret_cast<int*>(sLs + BM * K);      // [BM][K] item positions
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;               // 16 x 16 threads, 4 x 4 scores each
+    const int lm = tid >> 2, lq = tid & 3;                // loader: row lm, float4 lq of the BK chunk
+    const int u0 = blockIdx.x * BM;
+
+    const bool urow_ok = u0 + lm < n_users;
+    const float* uptr = urow_ok ? emb + static_cast<size_t>(user_ids[u0 + lm]) * stride : emb;
+
+    // per-user selection state (threads 0 .. BM-1)
+    const bool sel = tid < BM && u0 + tid < n_users;
+    int cnt = 0, mp = 0, mend = 0, next_mask = INT_MAX;
+    float thr = -INFINITY;
+    if (sel && mask_ptr) {
+        mp = mask_ptr[u0 + tid];
+        mend = mask_ptr[u0 + tid + 1];
+        next_mask = mp < mend ? mask_items[mp] : INT_MAX;
+    }
+    float* myLs = sLs + tid * K;
+    int* myLi = sLi + tid * K;
+
+    for (int n0 = 0; n0 < n_items; n0 += BN) {
+        const bool irow_ok = n0 + lm < n_items;
+        const float* iptr = irow_ok ? emb + static_cast<size_t>(item_ids[n0 + lm]) * stride : emb;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+        for (int k0 = 0; k0 < dim; k0 += BK) {
+            const int kk = k0 + lq * 4;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (kk < dim) {
+                if (urow_ok) a = ldg4(uptr + kk);
+                if (irow_ok) b = ldg4(iptr + kk);
+            }
+            __syncthreads();        // previous chunk fully consumed
+            sU[(lq * 4 + 0) * LDT + lm] = a.x; sU[(lq * 4 + 1) * LDT + lm] = a.y;
+            sU[(lq * 4 + 2) * LDT + lm] = a.z; sU[(lq * 4 + 3) * LDT + lm] = a.w;
+            sI[(lq * 4 + 0) * LDT + lm] = b.x; sI[(lq * 4 + 1) * LDT + lm] = b.y;
+            sI[(lq * 4 + 2) * LDT + lm] = b.z; sI[(lq * 4 + 3) * LDT + lm] = b.w;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BK; ++k) {
+                const float4 av = *reinterpret_cast<const float4*>(sU + k * LDT + ty * 4);
+                const float4 bv = *reinterpret_cast<const float4*>(sI + k * LDT + tx * 4);
+                const float a4[4] = {av.x, av.y, av.z, av.w};
+                const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sS[(ty * 4 + i) * (BN + 1) + tx * 4 + j] = acc[i][j];
+        __syncthreads();
+
+        if (sel) {
+            const int jmax = min(BN, n_items - n0);
+            for (int j = 0; j < jmax; ++j) {
+                const int item = n0 + j;
+                float s = sS[tid * (BN + 1) + j];
+                if (item == next_mask) {                    // train item: score forced to 0.0 (metric.py:50)
+                    s = 0.0f;
+                    do {
+                        ++mp;
+                        next_mask = mp < mend ? mask_items[mp] : INT_MAX;
+                    } while (next_mask == item);
+                }
+                if (cnt < K || s > thr) {
+                    int p = cnt < K ? cnt : K - 1;
+                    while (p > 0 && myLs[p - 1] < s) {
+                        myLs[p] = myLs[p - 1];
+                        myLi[p] = myLi[p - 1];
+                        --p;
+                    }
+                    myLs[p] = s;
+                    myLi[p] = item;
+                    if (cnt < K) ++cnt;
+                    if (cnt == K) thr = myLs[K - 1];
+                }
+            }
+        }
+        // the next tile's first __syncthreads orders these sS reads before sS is rewritten
+    }
+
+    if (sel) {
+        for (int p = 0; p < K; ++p) {
+            const bool ok = p < cnt;
+            topk_idx[static_cast<size_t>(u0 + tid) * K + p] = ok ? myLi[p] : -1;
+            if (topk_score) topk_score[static_cast<size_t>(u0 + tid) * K + p] = ok ? myLs[p] : -INFINITY;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace kgat
+
+using namespace kgat;
+
+extern "C" int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
+                               const int32_t* user_ids, int64_t n_users,
+                               const int32_t* item_ids, int64_t n_items,
+                               const int32_t* mask_ptr, const int32_t* mask_items,
+                               int K, int32_t* topk_idx, float* topk_score, kgat_stream_t stream) {
+    KGAT_REQUIRE(emb && user_ids && item_ids && topk_idx);
+    KGAT_REQUIRE(n_users >= 0 && n_items >= 0 && n_users < INT_MAX && n_items < INT_MAX);
+    KGAT_REQUIRE((mask_ptr == nullptr) == (mask_items == nullptr) || (mask_ptr && !mask_items));
+    KGAT_REQUIRE(aligned16(emb) && emb_stride % 4 == 0);
+    if (dim <= 0 || dim % 4 != 0 || K <= 0 || K > MAX_K) return KGAT_ERR_UNSUPPORTED_DIM;
+    if (n_users == 0) return KGAT_OK;
+    const size_t smem = sizeof(float) * (2 * BK * LDT + BM * (BN + 1)) + (sizeof(float) + sizeof(int)) * BM * K + 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+        KGAT_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const unsigned grid = static_cast<unsigned>((n_users + BM - 1) / BM);
+    score_topk_kernel<<<grid, EV_THREADS, smem, as_stream(stream)>>>(
+        emb, emb_stride, dim, user_ids, static_cast<int>(n_users), item_ids, static_cast<int>(n_items),
+        mask_ptr, mask_items, K, topk_idx, topk_score);
+    KGAT_LAUNCH_CHECK();
+    return KGAT_OK;
+}

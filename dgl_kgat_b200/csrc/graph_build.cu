@@ -1,0 +1,228 @@
+// (1) Graph construction: triplets -> destination-sorted CSR, source-sorted CSC and
+// relation buckets, all on the device.  Replaces DGLGraph()/add_edges/readonly
+// (reference dataset.py:112-130) and the per-relation filter_edges scans
+// (reference models.py:150).  Bit-exact against oracle/graph_ref.py: every order is a
+// stable LSD radix sort (cub::DeviceRadixSort is stable) of an explicit key, so the
+// result does not depend on scheduling.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace kgat {
+
+thread_local int g_last_cuda_error = 0;
+
+namespace {
+
+constexpr int TPB = 256;
+
+inline int blocks_for(int64_t n) { return static_cast<int>((n + TPB - 1) / TPB); }
+
+inline int bits_for(uint64_t max_key) {
+    int b = 1;
+    while (b < 64 && (max_key >> b) != 0) ++b;
+    return b;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+template <typename KeyT>
+__global__ void make_edge_keys(const int32_t* __restrict__ head, const int32_t* __restrict__ rel,
+                               int64_t n_rel, int64_t n_edges, KeyT* __restrict__ keys,
+                               int32_t* __restrict__ vals) {
+    int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n_edges) {
+        keys[i] = static_cast<KeyT>(static_cast<uint64_t>(head[i]) * static_cast<uint64_t>(n_rel) +
+                                    static_cast<uint64_t>(rel[i]));
+        vals[i] = static_cast<int32_t>(i);
+    }
+}
+
+__global__ void gather_csr(const int32_t* __restrict__ head, const int32_t* __restrict__ rel,
+                           const int32_t* __restrict__ tail, const int32_t* __restrict__ csr_eid,
+                           int64_t n_edges, int32_t* __restrict__ csr_src, int32_t* __restrict__ csr_dst,
+                           int32_t* __restrict__ csr_rel) {
+    int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (c < n_edges) {
+        int32_t e = csr_eid[c];
+        csr_src[c] = tail[e];
+        csr_dst[c] = head[e];
+        csr_rel[c] = rel[e];
+    }
+}
+
+__global__ void copy_keys_iota(const int32_t* __restrict__ src, int64_t n, uint32_t* __restrict__ keys,
+                               int32_t* __restrict__ vals) {
+    int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        keys[i] = static_cast<uint32_t>(src[i]);
+        vals[i] = static_cast<int32_t>(i);
+    }
+}
+
+// ptr[v] = number of sorted keys < v, v = 0..n_bins  (segment offsets of a sorted key array)
+template <typename KeyT>
+__global__ void segment_offsets(const KeyT* __restrict__ sorted, int64_t n, int64_t n_bins,
+                                int32_t* __restrict__ ptr) {
+    int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (v > n_bins) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (static_cast<int64_t>(sorted[mid]) < v) lo = mid + 1; else hi = mid;
+    }
+    ptr[v] = static_cast<int32_t>(lo);
+}
+
+__global__ void gather2(const int32_t* __restrict__ pos, int64_t n, const int32_t* __restrict__ a,
+                        const int32_t* __restrict__ b, int32_t* __restrict__ out_a,
+                        int32_t* __restrict__ out_b) {
+    int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        int32_t p = pos[i];
+        out_a[i] = a[p];
+        out_b[i] = b[p];
+    }
+}
+
+struct Workspace {
+    size_t keys_a, keys_b, vals_a, cub_temp, cub_bytes, total;
+};
+
+template <typename KeyT>
+size_t cub_temp_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const KeyT*>(nullptr),
+                                    static_cast<KeyT*>(nullptr), static_cast<const int32_t*>(nullptr),
+                                    static_cast<int32_t*>(nullptr), static_cast<int>(n), 0,
+                                    static_cast<int>(sizeof(KeyT) * 8));
+    return bytes;
+}
+
+Workspace plan(int64_t n_edges) {
+    Workspace w{};
+    size_t e = static_cast<size_t>(n_edges > 0 ? n_edges : 1);
+    size_t off = 0;
+    w.keys_a = off; off += align_up(e * sizeof(uint64_t));
+    w.keys_b = off; off += align_up(e * sizeof(uint64_t));
+    w.vals_a = off; off += align_up(e * sizeof(int32_t));
+    size_t t64 = cub_temp_bytes<uint64_t>(n_edges), t32 = cub_temp_bytes<uint32_t>(n_edges);
+    w.cub_bytes = t64 > t32 ? t64 : t32;
+    w.cub_temp = off; off += align_up(w.cub_bytes);
+    w.total = off;
+    return w;
+}
+
+template <typename KeyT>
+int sort_edges_by_head_rel(const kgat_graph_t* g, const int32_t* head, const int32_t* rel, char* ws,
+                           const Workspace& w, cudaStream_t st) {
+    const int64_t E = g->n_edges;
+    KeyT* ka = reinterpret_cast<KeyT*>(ws + w.keys_a);
+    KeyT* kb = reinterpret_cast<KeyT*>(ws + w.keys_b);
+    int32_t* va = reinterpret_cast<int32_t*>(ws + w.vals_a);
+    make_edge_keys<KeyT><<<blocks_for(E), TPB, 0, st>>>(head, rel, g->n_rel, E, ka, va);
+    KGAT_LAUNCH_CHECK();
+    size_t bytes = w.cub_bytes;
+    uint64_t max_key = static_cast<uint64_t>(g->n_nodes) * static_cast<uint64_t>(g->n_rel);
+    KGAT_CUDA(cub::DeviceRadixSort::SortPairs(ws + w.cub_temp, bytes, ka, kb, va, g->csr_eid,
+                                              static_cast<int>(E), 0, bits_for(max_key), st));
+    return KGAT_OK;
+}
+
+}  // namespace
+}  // namespace kgat
+
+using namespace kgat;
+
+extern "C" size_t kgat_graph_build_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t n_rel) {
+    (void)n_nodes; (void)n_rel;
+    if (n_edges < 0) return 0;
+    return plan(n_edges).total;
+}
+
+extern "C" int kgat_graph_build(const kgat_graph_t* g, const int32_t* head, const int32_t* rel,
+                                const int32_t* tail, void* workspace, size_t workspace_bytes,
+                                kgat_stream_t stream) {
+    KGAT_REQUIRE(g != nullptr);
+    KGAT_REQUIRE(g->n_nodes > 0 && g->n_rel > 0 && g->n_edges >= 0);
+    KGAT_REQUIRE(g->n_edges < (int64_t(1) << 31) && g->n_nodes < (int64_t(1) << 31));
+    KGAT_REQUIRE(g->csr_ptr && g->csc_ptr && g->rel_ptr);
+    cudaStream_t st = as_stream(stream);
+    const int64_t N = g->n_nodes, E = g->n_edges, R = g->n_rel;
+    if (E == 0) {
+        KGAT_CUDA(cudaMemsetAsync(g->csr_ptr, 0, sizeof(int32_t) * (N + 1), st));
+        KGAT_CUDA(cudaMemsetAsync(g->csc_ptr, 0, sizeof(int32_t) * (N + 1), st));
+        KGAT_CUDA(cudaMemsetAsync(g->rel_ptr, 0, sizeof(int32_t) * (R + 1), st));
+        return KGAT_OK;
+    }
+    KGAT_REQUIRE(head && rel && tail && workspace);
+    KGAT_REQUIRE(g->csr_src && g->csr_dst && g->csr_rel && g->csr_eid && g->csc_dst && g->csc_pos &&
+                 g->csc_eid && g->bk_pos && g->bk_head && g->bk_tail);
+    Workspace w = plan(E);
+    if (workspace_bytes < w.total) return KGAT_ERR_WORKSPACE;
+    char* ws = static_cast<char*>(workspace);
+
+    // CSR: stable sort of edge ids by key head * R + rel
+    int rc;
+    if (static_cast<uint64_t>(N) * static_cast<uint64_t>(R) < (uint64_t(1) << 32))
+        rc = sort_edges_by_head_rel<uint32_t>(g, head, rel, ws, w, st);
+    else
+        rc = sort_edges_by_head_rel<uint64_t>(g, head, rel, ws, w, st);
+    if (rc != KGAT_OK) return rc;
+    gather_csr<<<blocks_for(E), TPB, 0, st>>>(head, rel, tail, g->csr_eid, E, g->csr_src, g->csr_dst, g->csr_rel);
+    KGAT_LAUNCH_CHECK();
+    segment_offsets<int32_t><<<blocks_for(N + 1), TPB, 0, st>>>(g->csr_dst, E, N, g->csr_ptr);
+    KGAT_LAUNCH_CHECK();
+
+    uint32_t* ka = reinterpret_cast<uint32_t*>(ws + w.keys_a);
+    uint32_t* kb = reinterpret_cast<uint32_t*>(ws + w.keys_b);
+    int32_t* va = reinterpret_cast<int32_t*>(ws + w.vals_a);
+    size_t bytes = w.cub_bytes;
+
+    // CSC: stable sort of CSR positions by tail
+    copy_keys_iota<<<blocks_for(E), TPB, 0, st>>>(g->csr_src, E, ka, va);
+    KGAT_LAUNCH_CHECK();
+    KGAT_CUDA(cub::DeviceRadixSort::SortPairs(ws + w.cub_temp, bytes, ka, kb, va, g->csc_pos,
+                                              static_cast<int>(E), 0, bits_for(static_cast<uint64_t>(N)), st));
+    segment_offsets<uint32_t><<<blocks_for(N + 1), TPB, 0, st>>>(kb, E, N, g->csc_ptr);
+    KGAT_LAUNCH_CHECK();
+    gather2<<<blocks_for(E), TPB, 0, st>>>(g->csc_pos, E, g->csr_dst, g->csr_eid, g->csc_dst, g->csc_eid);
+    KGAT_LAUNCH_CHECK();
+
+    // relation buckets: stable sort of CSR positions by relation
+    copy_keys_iota<<<blocks_for(E), TPB, 0, st>>>(g->csr_rel, E, ka, va);
+    KGAT_LAUNCH_CHECK();
+    KGAT_CUDA(cub::DeviceRadixSort::SortPairs(ws + w.cub_temp, bytes, ka, kb, va, g->bk_pos,
+                                              static_cast<int>(E), 0, bits_for(static_cast<uint64_t>(R)), st));
+    segment_offsets<uint32_t><<<blocks_for(R + 1), TPB, 0, st>>>(kb, E, R, g->rel_ptr);
+    KGAT_LAUNCH_CHECK();
+    gather2<<<blocks_for(E), TPB, 0, st>>>(g->bk_pos, E, g->csr_dst, g->csr_src, g->bk_head, g->bk_tail);
+    KGAT_LAUNCH_CHECK();
+    return KGAT_OK;
+}
+
+extern "C" int kgat_version(void) { return 1; }
+
+extern "C" int kgat_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" const char* kgat_error_string(int status) {
+    switch (status) {
+        case KGAT_OK: return "ok";
+        case KGAT_ERR_INVALID_ARG: return "invalid argument (null pointer, bad size or misaligned buffer)";
+        case KGAT_ERR_UNSUPPORTED_DIM: return "unsupported feature width (must be a multiple of 4, at most 256)";
+        case KGAT_ERR_WORKSPACE: return "workspace too small";
+        case KGAT_ERR_CUDA: return "CUDA runtime error (see kgat_last_cuda_error)";
+        case KGAT_ERR_NO_DEVICE: return "no sm_100 CUDA device is current";
+        default: return "unknown kgat status";
+    }
+}
+
+extern "C" int kgat_device_check(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return KGAT_ERR_NO_DEVICE; }
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return KGAT_ERR_NO_DEVICE;
+    }
+    return major == 10 ? KGAT_OK : KGAT_ERR_NO_DEVICE;
+}

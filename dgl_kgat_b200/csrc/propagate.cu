@@ -1,0 +1,520 @@
+// (3c)+(4) KGATConv forward / backward and the entity-table gradient.
+//
+// Forward (reference models.py:60-70 + :163-167), one CTA per tile of TM destination rows:
+//   phase 1  warp-per-row CSR aggregation  h_nb[v] = sum_c w[c] * h_in[src[c]]  with 128-bit row
+//            loads (DIN/4 lanes per edge, 32/(DIN/4) edges per warp instruction, 4x unrolled),
+//            fp32 accumulation in registers, fixed summation order (no atomics);
+//            z = h_in[v] (.) h_nb[v] goes to shared memory, h_nb to HBM for the backward;
+//   phase 2  tile GEMM  pre = z W2^T  from shared memory, LeakyReLU, dropout mask;
+//   phase 3  row L2 norm by warp shuffle, un-normalised row -> h_out, normalised row -> its slice of
+//            the (N, sum d) concat buffer.
+// Backward, persistent CTAs over row tiles:
+//   phase 1  gradient of the layer output assembled per row: normalize-backward of the concat slice
+//            + next layer's direct term + transposed aggregation over the CSC (again gather-only,
+//            deterministic), then dropout / LeakyReLU backward -> dpre tile in shared memory;
+//   phase 2  dW2 += dpre^T z in registers (4xBJ blocks per thread, one partial per CTA, reduced by a
+//            second kernel in fixed order), dz = dpre W2, dx_direct = dz (.) h_nb, dh_nb = dz (.) h_in.
+#include "common.cuh"
+
+namespace kgat {
+namespace {
+
+constexpr int TM = 32;          // destination rows per tile
+constexpr int THREADS = 256;    // 8 warps
+constexpr int WARPS = THREADS / 32;
+
+// sum_c w[c] * feat[idx[c]] over c in [beg,end) for one row; W-wide rows, every lane group ends
+// with the full sum (lane l holds elements 4*(l % (W/4)) .. +3)
+template <int W>
+__device__ __forceinline__ float4 gather_row(const int32_t* __restrict__ idx, const float* __restrict__ wgt,
+                                             int beg, int end, const float* __restrict__ feat, int lane) {
+    constexpr int LPE = W / 4;          // lanes per edge
+    constexpr int EPW = 32 / LPE;       // edges per warp instruction
+    const int sub = lane / LPE, li = lane % LPE;
+    const float* base = feat + li * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int e = beg + sub;
+    for (; e + 3 * EPW < end; e += 4 * EPW) {
+        const int s0 = __ldg(idx + e), s1 = __ldg(idx + e + EPW), s2 = __ldg(idx + e + 2 * EPW),
+                  s3 = __ldg(idx + e + 3 * EPW);
+        const float w0 = __ldg(wgt + e), w1 = __ldg(wgt + e + EPW), w2 = __ldg(wgt + e + 2 * EPW),
+                    w3 = __ldg(wgt + e + 3 * EPW);
+        const float4 v0 = ldg4(base + static_cast<size_t>(s0) * W);
+        const float4 v1 = ldg4(base + static_cast<size_t>(s1) * W);
+        const float4 v2 = ldg4(base + static_cast<size_t>(s2) * W);
+        const float4 v3 = ldg4(base + static_cast<size_t>(s3) * W);
+        fma4(acc, w0, v0);
+        fma4(acc, w1, v1);
+        fma4(acc, w2, v2);
+        fma4(acc, w3, v3);
+    }
+    for (; e < end; e += EPW) {
+        const int s0 = __ldg(idx + e);
+        const float w0 = __ldg(wgt + e);
+        fma4(acc, w0, ldg4(base + static_cast<size_t>(s0) * W));
+    }
+    return across_groups_sum<LPE>(acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int DIN, int DOUT>
+struct FwdSmem {
+    static constexpr int LDW = DOUT + 1;
+    static constexpr size_t bytes = sizeof(float) * (DIN * LDW + TM * DIN + TM * DOUT) + 16;
+};
+
+template <int DIN, int DOUT>
+__global__ void __launch_bounds__(THREADS)
+layer_fwd_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict__ csr_src,
+                 const float* __restrict__ w_csr, int row_begin, int row_end,
+                 const float* __restrict__ h_in, const float* __restrict__ W2,
+                 const float* __restrict__ drop_mask, float slope, float* __restrict__ h_nb,
+                 float* __restrict__ act, float* __restrict__ h_out, float* __restrict__ concat,
+                 int64_t cstride, int64_t out_off, int64_t in_off) {
+    constexpr int LDW = DOUT + 1;
+    constexpr int LPI = DIN / 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sZ = reinterpret_cast<float*>(smem_raw);          // [TM][DIN]   (16B aligned)
+    float* sY = sZ + TM * DIN;                               // [TM][DOUT]
+    float* sW = sY + TM * DOUT;                              // [DIN][LDW], sW[i][j] = W2[j][i]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = row_begin + blockIdx.x * TM;
+
+    for (int idx = tid; idx < DOUT * DIN; idx += THREADS) {
+        const int j = idx / DIN, i = idx % DIN;
+        sW[i * LDW + j] = __ldg(W2 + idx);
+    }
+
+    // phase 1: aggregation, z tile
+    for (int rl = warp; rl < TM; rl += WARPS) {
+        const int row = row0 + rl;
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < row_end) {
+            const int beg = __ldg(csr_ptr + row), end = __ldg(csr_ptr + row + 1);
+            const float4 hn = gather_row<DIN>(csr_src, w_csr, beg, end, h_in, lane);
+            if (lane < LPI) {
+                const size_t o = static_cast<size_t>(row) * DIN + lane * 4;
+                const float4 x = ldg4(h_in + o);
+                *reinterpret_cast<float4*>(h_nb + o) = hn;
+                if (in_off >= 0)
+                    *reinterpret_cast<float4*>(concat + static_cast<size_t>(row) * cstride + in_off + lane * 4) = x;
+                z = make_float4(x.x * hn.x, x.y * hn.y, x.z * hn.z, x.w * hn.w);
+            }
+        }
+        if (lane < LPI) *reinterpret_cast<float4*>(sZ + rl * DIN + lane * 4) = z;
+    }
+    __syncthreads();
+
+    // phase 2: pre = z W2^T, LeakyReLU, dropout
+    {
+        constexpr int RG = THREADS / DOUT;      // row groups
+        constexpr int RPT = TM / RG;            // rows per thread
+        static_assert(RG >= 1 && RG <= TM && TM % RG == 0, "unsupported DOUT");
+        const int j = tid % DOUT, rg = tid / DOUT;
+        float acc[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) acc[k] = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < DIN; i += 4) {
+            const float w0 = sW[(i + 0) * LDW + j], w1 = sW[(i + 1) * LDW + j], w2 = sW[(i + 2) * LDW + j],
+                        w3 = sW[(i + 3) * LDW + j];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const float4 zv = *reinterpret_cast<const float4*>(sZ + (rg + k * RG) * DIN + i);
+                acc[k] = fmaf(zv.x, w0, acc[k]);
+                acc[k] = fmaf(zv.y, w1, acc[k]);
+                acc[k] = fmaf(zv.z, w2, acc[k]);
+                acc[k] = fmaf(zv.w, w3, acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int rl = rg + k * RG, row = row0 + rl;
+            float y = 0.f;
+            if (row < row_end) {
+                const float a = acc[k] > 0.f ? acc[k] : acc[k] * slope;
+                const size_t o = static_cast<size_t>(row) * DOUT + j;
+                if (act) act[o] = a;
+                y = drop_mask ? a * __ldg(drop_mask + o) : a;
+            }
+            sY[rl * DOUT + j] = y;
+        }
+    }
+    __syncthreads();
+
+    // phase 3: row norm, write un-normalised output and the normalised concat slice
+    for (int rl = warp; rl < TM; rl += WARPS) {
+        const int row = row0 + rl;
+        if (row >= row_end) continue;
+        float ss = 0.f;
+        for (int j = lane; j < DOUT; j += 32) {
+            const float v = sY[rl * DOUT + j];
+            ss = fmaf(v, v, ss);
+        }
+        ss = warp_sum(ss);
+        const float denom = fmaxf(sqrtf(ss), NORM_EPS);
+        for (int j = lane; j < DOUT; j += 32) {
+            const float v = sY[rl * DOUT + j];
+            h_out[static_cast<size_t>(row) * DOUT + j] = v;
+            if (concat) concat[static_cast<size_t>(row) * cstride + out_off + j] = v / denom;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <int DIN, int DOUT>
+struct BwdCfg {
+    static constexpr int BJ = (DOUT * DIN >= 4096) ? 4 : ((DOUT * DIN >= 2048) ? 2 : 1);
+    static constexpr int NBLOCKS = DOUT * DIN / (4 * BJ);
+    static constexpr int NB = (NBLOCKS + THREADS - 1) / THREADS;
+    static constexpr size_t bytes = sizeof(float) * (DOUT * DIN + TM * DOUT + TM * DIN) + 16;
+};
+
+template <int DIN, int DOUT>
+__global__ void __launch_bounds__(THREADS)
+layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
+                 const float* __restrict__ w_csc, int row_begin, int row_end, int n_tiles,
+                 const float* __restrict__ d_concat, int64_t cstride, int64_t out_off,
+                 const float* __restrict__ nxt_dx_direct, const float* __restrict__ nxt_dh_nb,
+                 const float* __restrict__ h_in, const float* __restrict__ h_nb,
+                 const float* __restrict__ act, const float* __restrict__ h_out,
+                 const float* __restrict__ drop_mask, const float* __restrict__ W2, float slope,
+                 float* __restrict__ dx_direct, float* __restrict__ dh_nb, float* __restrict__ partials) {
+    using C = BwdCfg<DIN, DOUT>;
+    constexpr int BJ = C::BJ, NBLOCKS = C::NBLOCKS, NB = C::NB;
+    constexpr int LPI = DIN / 4, LPO = DOUT / 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sDP = reinterpret_cast<float*>(smem_raw);     // [TM][DOUT]
+    float* sZ = sDP + TM * DOUT;                         // [TM][DIN]
+    float* sW = sZ + TM * DIN;                           // [DOUT][DIN] as given
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int idx = tid; idx < DOUT * DIN / 4; idx += THREADS)
+        reinterpret_cast<float4*>(sW)[idx] = __ldg(reinterpret_cast<const float4*>(W2) + idx);
+
+    float acc[NB][BJ][4];
+#pragma unroll
+    for (int n = 0; n < NB; ++n)
+#pragma unroll
+        for (int a = 0; a < BJ; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[n][a][b] = 0.f;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = row_begin + tile * TM;
+        __syncthreads();      // previous tile's readers are done with sDP / sZ (also orders the sW fill)
+
+        // phase 1: dpre and z for every row of the tile
+        for (int rl = warp; rl < TM; rl += WARPS) {
+            const int row = row0 + rl;
+            float4 dp = make_float4(0.f, 0.f, 0.f, 0.f), z = dp;
+            if (row < row_end) {
+                const int lo = lane % LPO;
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (nxt_dh_nb) {
+                    const int beg = __ldg(csc_ptr + row), end = __ldg(csc_ptr + row + 1);
+                    g = gather_row<DOUT>(csc_dst, w_csc, beg, end, nxt_dh_nb, lane);
+                }
+                const size_t oo = static_cast<size_t>(row) * DOUT + lo * 4;
+                if (nxt_dx_direct) {
+                    const float4 t = ldg4(nxt_dx_direct + oo);
+                    g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+                }
+                const float4 y = ldg4(h_out + oo);
+                if (d_concat) {
+                    const float4 dc = ldg4(d_concat + static_cast<size_t>(row) * cstride + out_off + lo * 4);
+                    float ss = y.x * y.x;
+                    ss = fmaf(y.y, y.y, ss); ss = fmaf(y.z, y.z, ss); ss = fmaf(y.w, y.w, ss);
+                    ss = group_sum<LPO>(ss);
+                    const float n = sqrtf(ss);
+                    if (n >= NORM_EPS) {          // clamp_min passes the gradient to the norm
+                        const float4 c = make_float4(y.x / n, y.y / n, y.z / n, y.w / n);
+                        float dot = c.x * dc.x;
+                        dot = fmaf(c.y, dc.y, dot); dot = fmaf(c.z, dc.z, dot); dot = fmaf(c.w, dc.w, dot);
+                        dot = group_sum<LPO>(dot);
+                        g.x += (dc.x - c.x * dot) / n;
+                        g.y += (dc.y - c.y * dot) / n;
+                        g.z += (dc.z - c.z * dot) / n;
+                        g.w += (dc.w - c.w * dot) / n;
+                    } else {                      // row clamped to eps: y / eps, constant denominator
+                        g.x += dc.x / NORM_EPS; g.y += dc.y / NORM_EPS;
+                        g.z += dc.z / NORM_EPS; g.w += dc.w / NORM_EPS;
+                    }
+                }
+                if (drop_mask) {
+                    const float4 m = ldg4(drop_mask + oo);
+                    g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+                }
+                const float4 a = act ? ldg4(act + oo) : y;
+                dp.x = a.x > 0.f ? g.x : g.x * slope;
+                dp.y = a.y > 0.f ? g.y : g.y * slope;
+                dp.z = a.z > 0.f ? g.z : g.z * slope;
+                dp.w = a.w > 0.f ? g.w : g.w * slope;
+                const size_t oi = static_cast<size_t>(row) * DIN + (lane % LPI) * 4;
+                const float4 x = ldg4(h_in + oi), hn = ldg4(h_nb + oi);
+                z = make_float4(x.x * hn.x, x.y * hn.y, x.z * hn.z, x.w * hn.w);
+            }
+            if (lane < LPO) *reinterpret_cast<float4*>(sDP + rl * DOUT + lane * 4) = dp;
+            if (lane < LPI) *reinterpret_cast<float4*>(sZ + rl * DIN + lane * 4) = z;
+        }
+        __syncthreads();
+
+        // phase 2a: dW2 += dpre^T z
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int b = tid + n * THREADS;
+            if (b < NBLOCKS) {
+                const int i0 = (b % LPI) * 4, j0 = (b / LPI) * BJ;
+#pragma unroll 4
+                for (int r = 0; r < TM; ++r) {
+                    const float4 zv = *reinterpret_cast<const float4*>(sZ + r * DIN + i0);
+#pragma unroll
+                    for (int a = 0; a < BJ; ++a) {
+                        const float d = sDP[r * DOUT + j0 + a];
+                        acc[n][a][0] = fmaf(d, zv.x, acc[n][a][0]);
+                        acc[n][a][1] = fmaf(d, zv.y, acc[n][a][1]);
+                        acc[n][a][2] = fmaf(d, zv.z, acc[n][a][2]);
+                        acc[n][a][3] = fmaf(d, zv.w, acc[n][a][3]);
+                    }
+                }
+            }
+        }
+
+        // phase 2b: dz = dpre W2; dx_direct = dz (.) h_nb; dh_nb = dz (.) h_in
+        {
+            constexpr int RG = THREADS / DIN;
+            constexpr int RPT = TM / RG;
+            static_assert(RG >= 1 && RG <= TM && TM % RG == 0, "unsupported DIN");
+            const int i = tid % DIN, rg = tid / DIN;
+            float dz[RPT];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) dz[k] = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < DOUT; j += 4) {
+                const float w0 = sW[(j + 0) * DIN + i], w1 = sW[(j + 1) * DIN + i], w2 = sW[(j + 2) * DIN + i],
+                            w3 = sW[(j + 3) * DIN + i];
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    const float4 d = *reinterpret_cast<const float4*>(sDP + (rg + k * RG) * DOUT + j);
+                    dz[k] = fmaf(d.x, w0, dz[k]);
+                    dz[k] = fmaf(d.y, w1, dz[k]);
+                    dz[k] = fmaf(d.z, w2, dz[k]);
+                    dz[k] = fmaf(d.w, w3, dz[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int row = row0 + rg + k * RG;
+                if (row < row_end) {
+                    const size_t o = static_cast<size_t>(row) * DIN + i;
+                    dx_direct[o] = dz[k] * __ldg(h_nb + o);
+                    dh_nb[o] = dz[k] * __ldg(h_in + o);
+                }
+            }
+        }
+    }
+
+    // one dW2 partial per CTA
+    float* my = partials + static_cast<size_t>(blockIdx.x) * DOUT * DIN;
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        const int b = tid + n * THREADS;
+        if (b < NBLOCKS) {
+            const int i0 = (b % LPI) * 4, j0 = (b / LPI) * BJ;
+#pragma unroll
+            for (int a = 0; a < BJ; ++a)
+                *reinterpret_cast<float4*>(my + (j0 + a) * DIN + i0) =
+                    make_float4(acc[n][a][0], acc[n][a][1], acc[n][a][2], acc[n][a][3]);
+        }
+    }
+}
+
+// dW2[idx] = sum_p partials[p][idx], fixed order; 8 threads per element, combined by shuffle
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int n_elem, float* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = t >> 3, part = t & 7;
+    float s = 0.f;
+    if (idx < n_elem)
+        for (int p = part; p < n_partials; p += 8) s += __ldg(partials + static_cast<size_t>(p) * n_elem + idx);
+    s = group_sum<8>(s);
+    if (idx < n_elem && part == 0) out[idx] = s;
+}
+
+// d_entity[v] = d_concat[v, in_off:+D] + dx_direct[v] + sum_{k in CSC row v} w[k] * dh_nb[dst[k]]
+template <int D>
+__global__ void __launch_bounds__(THREADS)
+input_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
+                 const float* __restrict__ w_csc, int row_begin, int row_end,
+                 const float* __restrict__ d_concat, int64_t cstride, int64_t in_off,
+                 const float* __restrict__ dx_direct, const float* __restrict__ dh_nb,
+                 float* __restrict__ d_entity) {
+    constexpr int LP = D / 4;
+    const int lane = threadIdx.x & 31;
+    const int row = row_begin + blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row >= row_end) return;
+    const int beg = __ldg(csc_ptr + row), end = __ldg(csc_ptr + row + 1);
+    float4 g = gather_row<D>(csc_dst, w_csc, beg, end, dh_nb, lane);
+    if (lane < LP) {
+        const size_t o = static_cast<size_t>(row) * D + lane * 4;
+        const float4 t = ldg4(dx_direct + o);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        if (d_concat) {
+            const float4 c = ldg4(d_concat + static_cast<size_t>(row) * cstride + in_off + lane * 4);
+            g.x += c.x; g.y += c.y; g.z += c.z; g.w += c.w;
+        }
+        *reinterpret_cast<float4*>(d_entity + o) = g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+struct FwdArgs {
+    const kgat_graph_t* g; int row_begin, row_end;
+    const float *h_in, *w_csr, *W2, *drop_mask; float slope;
+    float *h_nb, *act, *h_out, *concat; int64_t cstride, out_off, in_off; cudaStream_t st;
+};
+
+template <int DIN, int DOUT>
+int launch_fwd(const FwdArgs& a) {
+    constexpr size_t smem = FwdSmem<DIN, DOUT>::bytes;
+    static bool configured = false;
+    if (!configured) {
+        KGAT_CUDA(cudaFuncSetAttribute(layer_fwd_kernel<DIN, DOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        configured = true;
+    }
+    const int rows = a.row_end - a.row_begin;
+    const unsigned grid = (rows + TM - 1) / TM;
+    layer_fwd_kernel<DIN, DOUT><<<grid, THREADS, smem, a.st>>>(
+        a.g->csr_ptr, a.g->csr_src, a.w_csr, a.row_begin, a.row_end, a.h_in, a.W2, a.drop_mask, a.slope,
+        a.h_nb, a.act, a.h_out, a.concat, a.cstride, a.out_off, a.in_off);
+    KGAT_LAUNCH_CHECK();
+    return KGAT_OK;
+}
+
+struct BwdArgs {
+    const kgat_graph_t* g; int row_begin, row_end;
+    const float* d_concat; int64_t cstride, out_off;
+    const float *nxt_dx_direct, *nxt_dh_nb, *w_csc, *h_in, *h_nb, *act, *h_out, *drop_mask, *W2; float slope;
+    float *dx_direct, *dh_nb, *dW2, *partials; cudaStream_t st;
+};
+
+inline int bwd_max_ctas() { return 4 * num_sms(); }
+
+template <int DIN, int DOUT>
+int launch_bwd(const BwdArgs& a) {
+    constexpr size_t smem = BwdCfg<DIN, DOUT>::bytes;
+    static bool configured = false;
+    if (!configured) {
+        KGAT_CUDA(cudaFuncSetAttribute(layer_bwd_kernel<DIN, DOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        configured = true;
+    }
+    const int rows = a.row_end - a.row_begin;
+    const int n_tiles = (rows + TM - 1) / TM;
+    const int grid = n_tiles < bwd_max_ctas() ? n_tiles : bwd_max_ctas();
+    layer_bwd_kernel<DIN, DOUT><<<grid, THREADS, smem, a.st>>>(
+        a.g->csc_ptr, a.g->csc_dst, a.w_csc, a.row_begin, a.row_end, n_tiles, a.d_concat, a.cstride, a.out_off,
+        a.nxt_dx_direct, a.nxt_dh_nb, a.h_in, a.h_nb, a.act, a.h_out, a.drop_mask, a.W2, a.slope, a.dx_direct,
+        a.dh_nb, a.partials);
+    KGAT_LAUNCH_CHECK();
+    const int n_elem = DIN * DOUT;
+    reduce_partials_kernel<<<(n_elem * 8 + 255) / 256, 256, 0, a.st>>>(a.partials, grid, n_elem, a.dW2);
+    KGAT_LAUNCH_CHECK();
+    return KGAT_OK;
+}
+
+#define KGAT_DIM_PAIRS(X) \
+    X(128, 128) X(128, 64) X(64, 64) X(64, 32) X(32, 32) X(32, 16) X(16, 16) X(16, 8)
+
+}  // namespace
+}  // namespace kgat
+
+using namespace kgat;
+
+extern "C" int kgat_layer_fwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                              const float* h_in, const float* w_csr, const float* W2,
+                              const float* drop_mask, int d_in, int d_out, float slope,
+                              float* h_nb, float* act, float* h_out, float* concat,
+                              int64_t concat_stride, int64_t out_off, int64_t in_off,
+                              kgat_stream_t stream) {
+    KGAT_REQUIRE(g && h_in && W2 && h_nb && h_out);
+    KGAT_REQUIRE(g->n_edges == 0 || w_csr);
+    KGAT_REQUIRE(row_begin >= 0 && row_end <= g->n_nodes && row_begin <= row_end);
+    KGAT_REQUIRE(aligned16(h_in) && aligned16(h_nb) && aligned16(h_out) && aligned16(W2));
+    KGAT_REQUIRE(!drop_mask || act);        // with dropout the pre-mask activation must be kept
+    if (concat) {
+        KGAT_REQUIRE(aligned16(concat) && concat_stride % 4 == 0 && out_off % 4 == 0 && out_off >= 0);
+        KGAT_REQUIRE(in_off < 0 || in_off % 4 == 0);
+    } else {
+        in_off = -1;
+    }
+    if (row_begin == row_end) return KGAT_OK;
+    FwdArgs a{g, (int)row_begin, (int)row_end, h_in, w_csr, W2, drop_mask, slope, h_nb, act, h_out, concat,
+              concat_stride, out_off, in_off, as_stream(stream)};
+#define X(DI, DO) if (d_in == DI && d_out == DO) return launch_fwd<DI, DO>(a);
+    KGAT_DIM_PAIRS(X)
+#undef X
+    return KGAT_ERR_UNSUPPORTED_DIM;
+}
+
+extern "C" int kgat_layer_bwd_partials(void) { return bwd_max_ctas(); }
+
+extern "C" int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                              const float* d_concat, int64_t concat_stride, int64_t out_off,
+                              const float* nxt_dx_direct, const float* nxt_dh_nb, const float* w_csc,
+                              const float* h_in, const float* h_nb, const float* act, const float* h_out,
+                              const float* drop_mask, const float* W2, int d_in, int d_out, float slope,
+                              float* dx_direct, float* dh_nb, float* dW2, float* dW2_partials,
+                              kgat_stream_t stream) {
+    KGAT_REQUIRE(g && h_in && h_nb && h_out && W2 && dx_direct && dh_nb && dW2 && dW2_partials);
+    KGAT_REQUIRE(row_begin >= 0 && row_end <= g->n_nodes && row_begin <= row_end);
+    KGAT_REQUIRE(!nxt_dh_nb || g->n_edges == 0 || w_csc);
+    KGAT_REQUIRE(!drop_mask || act);
+    KGAT_REQUIRE(aligned16(h_in) && aligned16(h_nb) && aligned16(h_out) && aligned16(W2) && aligned16(dx_direct) &&
+                 aligned16(dh_nb) && aligned16(dW2_partials));
+    if (d_concat) KGAT_REQUIRE(aligned16(d_concat) && concat_stride % 4 == 0 && out_off % 4 == 0 && out_off >= 0);
+    cudaStream_t st = as_stream(stream);
+    if (row_begin == row_end) {
+        KGAT_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * d_in * d_out, st));
+        return KGAT_OK;
+    }
+    BwdArgs a{g, (int)row_begin, (int)row_end, d_concat, concat_stride, out_off, nxt_dx_direct, nxt_dh_nb, w_csc,
+              h_in, h_nb, act, h_out, drop_mask, W2, slope, dx_direct, dh_nb, dW2, dW2_partials, st};
+#define X(DI, DO) if (d_in == DI && d_out == DO) return launch_bwd<DI, DO>(a);
+    KGAT_DIM_PAIRS(X)
+#undef X
+    return KGAT_ERR_UNSUPPORTED_DIM;
+}
+
+extern "C" int kgat_input_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                              const float* d_concat, int64_t concat_stride, int64_t in_off,
+                              const float* dx_direct, const float* dh_nb, const float* w_csc, int d,
+                              float* d_entity, kgat_stream_t stream) {
+    KGAT_REQUIRE(g && dx_direct && dh_nb && d_entity);
+    KGAT_REQUIRE(g->n_edges == 0 || w_csc);
+    KGAT_REQUIRE(row_begin >= 0 && row_end <= g->n_nodes && row_begin <= row_end);
+    KGAT_REQUIRE(aligned16(dx_direct) && aligned16(dh_nb) && aligned16(d_entity));
+    if (d_concat) KGAT_REQUIRE(aligned16(d_concat) && concat_stride % 4 == 0 && in_off % 4 == 0 && in_off >= 0);
+    if (row_begin == row_end) return KGAT_OK;
+    const int rows = static_cast<int>(row_end - row_begin);
+    const unsigned grid = (rows + WARPS - 1) / WARPS;
+    cudaStream_t st = as_stream(stream);
+#define LAUNCH(D)                                                                                          \
+    if (d == D) {                                                                                          \
+        input_bwd_kernel<D><<<grid, THREADS, 0, st>>>(g->csc_ptr, g->csc_dst, w_csc, (int)row_begin,       \
+                                                      (int)row_end, d_concat, concat_stride, in_off,       \
+                                                      dx_direct, dh_nb, d_entity);                         \
+        KGAT_LAUNCH_CHECK();                                                                               \
+        return KGAT_OK;                                                                                    \
+    }
+    LAUNCH(128) LAUNCH(64) LAUNCH(32) LAUNCH(16) LAUNCH(8)
+#undef LAUNCH
+    return KGAT_ERR_UNSUPPORTED_DIM;
+}

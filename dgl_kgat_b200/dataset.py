@@ -1,0 +1,214 @@
+"""Graph inputs with the reference's ``DataLoader`` surface (reference ``dataset.py``), DGL-free.
+
+What is kept (consumers: kgat.py:74-80, :95-117, :147, :173, :185):
+``n_users, n_items, n_train, n_valid, n_test, n_KG_entity, n_KG_relation,
+n_train_KG_triplet, n_test_KG_triplet, train_KG_triplet, test_KG_triplet, item_id_range,
+train_user_dict, valid_user_dict, test_user_dict, train_valid_user_dict, train_pairs,
+valid_pairs, test_pairs, train_g, test_g, KG_sampler(), CF_pair_sampler()``.
+
+Id layout (dataset.py:60-73): users ``[0, U)``, then items, then the other KG entities,
+i.e. item and entity ids are offset by ``n_users``; the user->items dicts keep RAW item
+ids (they are built before the offset, dataset.py:45-50) so their values index the
+``(n_items,)`` score vector directly.  Triplets: ``[KG ; (u, R_kg, v) ; (v, R_kg+1, u)]``
+(dataset.py:84-93, :165-185).  ``train_g`` / ``test_g`` are :class:`CKGraph` objects built
+once and cached (the reference rebuilds a DGLGraph per access, dataset.py:112-130; the
+observable content is the same).
+
+On-disk format (dataset.py:14-18, :150-152; datasets/README.md): tab-separated files with
+a header row, ``datasets/<name>/data/{uv_train,uv_val,uv_test}.pd`` (columns u, v) and
+``kg_item.pd`` (columns h, r, t), ids consecutive from 0.  ``DataLoader.from_synthetic``
+builds the same object from :mod:`synth` without touching the disk.
+"""
+from __future__ import annotations
+
+import os
+import random as rd
+
+import numpy as np
+import pandas as pd
+
+from . import synth
+from .graph import CKGraph
+
+_UV_FILES = ["uv_train.pd", "uv_val.pd", "uv_test.pd"]
+_KG_FILE = "kg_item.pd"
+_SEP = "\t"
+
+
+def _read_table(path):
+    if not os.path.isfile(path):
+        raise FileNotFoundError("%s does not exist" % path)
+    return pd.read_csv(path, sep=_SEP, header=0, dtype=np.int32)
+
+
+def _pairs_to_dict(u, v):
+    """{user: array of item ids}, users ascending, items in stable input order
+    (dataset.py:187-196 groups a frame that was stably sorted by u)."""
+    u = np.asarray(u)
+    v = np.asarray(v)
+    order = np.argsort(u, kind="stable")
+    us, vs = u[order], v[order]
+    uniq, start = np.unique(us, return_index=True)
+    bounds = np.append(start, len(us))
+    return {uniq[i]: vs[bounds[i]: bounds[i + 1]] for i in range(len(uniq))}
+
+
+class EdgeBatchSampler:
+    """One shuffled pass over the edges of a (src -> dst) graph in batches, each positive
+    edge paired with one uniformly corrupted copy.  Stands in for
+    ``dgl.contrib.sampling.EdgeSampler(..., neg_sample_size=1, shuffle=True,
+    return_false_neg=True)`` as used at dataset.py:223-233: ``negative_mode='head'``
+    replaces the source node, ``'tail'`` the destination node, the replacement is uniform
+    over all nodes, and ``false_neg`` flags corrupted edges that exist in the graph with
+    the same relation."""
+
+    def __init__(self, src, dst, etype, n_nodes, batch_size, negative_mode, rng):
+        self.src, self.dst, self.n_nodes = np.asarray(src, np.int64), np.asarray(dst, np.int64), int(n_nodes)
+        self.etype = None if etype is None else np.asarray(etype, np.int64)
+        self.batch_size, self.mode, self.rng = int(batch_size), negative_mode, rng
+        self._n_rel = 1 if self.etype is None else int(self.etype.max()) + 1
+        self._keys = np.unique(self._edge_key(self.src, self.dst, self.etype))
+
+    def _edge_key(self, s, d, r):
+        k = s * self.n_nodes + d
+        return k if r is None else k * self._n_rel + r
+
+    def __iter__(self):
+        E = self.src.shape[0]
+        perm = self.rng.permutation(E)
+        for b in range(0, E, self.batch_size):
+            eid = perm[b: b + self.batch_size]
+            s, d = self.src[eid], self.dst[eid]
+            r = None if self.etype is None else self.etype[eid]
+            corrupt = self.rng.integers(0, self.n_nodes, size=eid.shape[0])
+            ns, nd = (corrupt, d) if self.mode == "head" else (s, corrupt)
+            false_neg = np.isin(self._edge_key(ns, nd, r), self._keys).astype(np.int64)
+            yield s, d, r, ns, nd, false_neg
+
+
+class DataLoader(object):
+    def __init__(self, data_name, symmetric=True, as_continuous_ids=True, add_uv2KG=True, seed=1234,
+                 data_dir=None, _frames=None):
+        self._data_name = data_name
+        rd.seed(seed)
+        self._rng = np.random.default_rng(seed)
+        if _frames is None:
+            if data_dir is None:
+                root = os.environ.get("KGAT_DATA_ROOT", os.path.join(os.getcwd(), "datasets"))
+                data_dir = os.path.join(root, data_name, "data")
+            train_pd, valid_pd, test_pd = (_read_table(os.path.join(data_dir, f)) for f in _UV_FILES)
+            kg_pd = _read_table(os.path.join(data_dir, _KG_FILE))
+        else:
+            train_pd, valid_pd, test_pd, kg_pd = _frames
+        if len(train_pd.columns) != 2:
+            raise NotImplementedError("only implicit feedback (columns u, v) is supported, "
+                                      "as in the reference's published pipelines")
+        train_pd, valid_pd, test_pd = (f.sort_values(by=["u"], kind="stable").reset_index(drop=True)
+                                       for f in (train_pd, valid_pd, test_pd))
+        self.n_users = int(train_pd["u"].nunique())             # dataset.py:29
+        self.n_items = int(train_pd["v"].nunique())             # dataset.py:30
+        self.n_train, self.n_valid, self.n_test = train_pd.shape[0], valid_pd.shape[0], test_pd.shape[0]
+
+        tu, tv = train_pd["u"].values, train_pd["v"].values
+        vu, vv = valid_pd["u"].values, valid_pd["v"].values
+        # dicts hold RAW item ids: built before the offset (dataset.py:45-50)
+        self.train_user_dict = _pairs_to_dict(tu, tv)
+        self.valid_user_dict = _pairs_to_dict(vu, vv)
+        self.test_user_dict = _pairs_to_dict(test_pd["u"].values, test_pd["v"].values)
+        self.train_valid_user_dict = _pairs_to_dict(np.concatenate([tu, vu]), np.concatenate([tv, vv]))
+
+        off = self.n_users if as_continuous_ids else 0          # dataset.py:60-73
+        self.item_id_range = np.arange(off, off + self.n_items)
+        self.train_pairs = np.stack([tu, tv + off], 1).astype(np.int32)
+        self.valid_pairs = np.stack([vu, vv + off], 1).astype(np.int32)
+        self.test_pairs = np.stack([test_pd["u"].values, test_pd["v"].values + off], 1).astype(np.int32)
+        kg = kg_pd[["h", "r", "t"]].values.astype(np.int32).copy()
+        kg[:, 0] += off
+        kg[:, 2] += off
+
+        n_kg_rel = int(np.unique(kg[:, 1]).size)                # dataset.py:77
+        self._train_uv_triplet = self._uv2triplet(self.train_pairs, n_kg_rel, symmetric)
+        train_valid_uv = self._uv2triplet(np.vstack([self.train_pairs, self.valid_pairs]), n_kg_rel, symmetric)
+        if add_uv2KG:                                            # dataset.py:84-93
+            self.train_KG_triplet = np.vstack((kg, self._train_uv_triplet))
+            self.test_KG_triplet = np.vstack((kg, train_valid_uv))
+        else:
+            self.train_KG_triplet = kg
+            self.test_KG_triplet = kg
+        self.n_KG_relation = int(np.unique(self.train_KG_triplet[:, 1]).size)      # dataset.py:95
+        self.n_KG_entity = int(np.unique(np.concatenate(
+            (self.train_KG_triplet[:, 0], self.train_KG_triplet[:, 2]))).size)     # dataset.py:96
+        self.n_train_KG_triplet = self.train_KG_triplet.shape[0]
+        self.n_test_KG_triplet = self.test_KG_triplet.shape[0]
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_synthetic(cls, config="tiny", seed=1234, skew=False):
+        """Same object from a synthetic CKG of a BASELINE.json shape; the held-out pairs
+        serve as both the validation and the test split."""
+        ck = synth.synth_ckg(config, seed=seed, skew=skew)
+        U = ck.cfg.n_users
+        frame = lambda p: pd.DataFrame({"u": p[:, 0].astype(np.int32), "v": (p[:, 1] - U).astype(np.int32)})
+        kg = pd.DataFrame({"h": ck.kg[:, 0] - U, "r": ck.kg[:, 1], "t": ck.kg[:, 2] - U}, dtype=np.int32)
+        return cls("synthetic-" + ck.cfg.name, seed=seed,
+                   _frames=(frame(ck.train_pairs), frame(ck.valid_pairs), frame(ck.valid_pairs), kg))
+
+    @staticmethod
+    def _uv2triplet(pairs, offset_rel, symmetric=True):
+        trip = synth.uv_triplets(pairs, offset_rel)              # dataset.py:165-185
+        return trip if symmetric else trip[: pairs.shape[0]]
+
+    def _graph(self, name, triplets):
+        if name not in self._graphs:
+            self._graphs[name] = CKGraph(self.n_KG_entity, triplets, n_rel=self.n_KG_relation)
+        return self._graphs[name]
+
+    @property
+    def train_g(self):
+        return self._graph("train", self.train_KG_triplet)
+
+    @property
+    def test_g(self):
+        return self._graph("test", self.test_KG_triplet)
+
+    def __repr__(self):
+        info = "{}:\n".format(self._data_name)
+        info += "\t#user {}, #item {}\n".format(self.n_users, self.n_items)
+        info += "\t#train {}, #valid {}, #test {}\n".format(self.n_train, self.n_valid, self.n_test)
+        info += "In the knowledge graph:\n"
+        info += "\tKG: #entity {}, #relation {}, #train triplet {}, #test triplet {}\n".format(
+            self.n_KG_entity, self.n_KG_relation, self.n_train_KG_triplet, self.n_test_KG_triplet)
+        return info
+
+    # ------------------------------------------------------------------ samplers (host side)
+    @staticmethod
+    def _n_batch(batch_size, n):
+        if batch_size < 0 or batch_size > n:
+            return n
+        return batch_size
+
+    def KG_sampler(self, batch_size, pos_mode="uniform", neg_mode="tail", num_workers=8, exclude_positive=False):
+        """Yields ``(h, r, pos_t, neg_t, false_neg)`` batches (dataset.py:234-282).  As in the
+        reference the names refer to the t->h graph: "h" is the edge SOURCE (= KG tail), "pos_t"
+        the edge destination (= KG head), and the corrupted node is the destination."""
+        if not (pos_mode == "uniform" and neg_mode == "tail"):
+            raise NotImplementedError("only pos_mode='uniform', neg_mode='tail' (the mode kgat.py uses)")
+        t = self.train_KG_triplet
+        sampler = EdgeBatchSampler(t[:, 2], t[:, 0], t[:, 1], self.n_KG_entity,
+                                   self._n_batch(batch_size, self.n_train_KG_triplet), "tail", self._rng)
+        for s, d, r, _, nd, false_neg in sampler:
+            yield s, r, d, nd, false_neg
+
+    def CF_pair_sampler(self, batch_size, pos_mode="uniform", neg_mode="random", num_workers=8,
+                        exclude_positive=False):
+        """Yields ``(users, pos_items, neg_items, false_neg)`` batches over the symmetric
+        user-item graph (dataset.py:283-325): users = edge destinations, pos_items = edge sources,
+        neg_items = uniformly corrupted sources."""
+        if not (pos_mode == "uniform" and neg_mode == "random"):
+            raise NotImplementedError("only pos_mode='uniform', neg_mode='random' (the mode kgat.py uses)")
+        t = self._train_uv_triplet
+        sampler = EdgeBatchSampler(t[:, 2], t[:, 0], None, self.n_users + self.n_items,
+                                   self._n_batch(batch_size, t.shape[0]), "head", self._rng)
+        for s, d, _, ns, _, false_neg in sampler:
+            yield d, s, ns, false_neg

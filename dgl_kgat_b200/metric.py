@@ -1,0 +1,133 @@
+"""Full-rank Recall@K / NDCG@K with the reference's signature (reference ``metric.py``).
+
+``calc_recall_ndcg(embedding, train_user_dict, test_user_dict, all_item_id_range, K)``
+keeps the reference semantics, quirks included:
+
+* train items are masked to **0.0**, not -inf (metric.py:50) and therefore still rank;
+* NDCG's ideal DCG is the DCG of the *sorted retrieved hit vector* (metric.py:31-34);
+* averages run over ``len(test_user_dict)`` (metric.py:66-67);
+* ties rank the lower item index first (``th.sort`` at metric.py:51 is unstable; this is
+  the contract north_star fixes).
+
+The per-user Python loop, the 17.5 MB item-matrix re-gather per user, the full sort and
+the per-user device->host sync are replaced by ONE launch of the fused scoring + top-K
+kernel (``kgat_score_topk``) and one (n_users, K) read-back; the metric arithmetic is
+done in float64 numpy like the reference's helpers.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch as th
+
+from . import ops
+
+
+def one_recall_at_k(r, k, all_pos_num):
+    r = np.asarray(r, dtype=np.float64)[:k]
+    return np.sum(r) / all_pos_num
+
+
+def one_dcg_at_k(r, k, method=1):
+    r = np.asarray(r, dtype=np.float64)[:k]
+    if r.size:
+        if method == 0:
+            return r[0] + np.sum(r[1:] / np.log2(np.arange(2, r.size + 1)))
+        elif method == 1:
+            return np.sum(r / np.log2(np.arange(2, r.size + 2)))
+        raise ValueError('method must be 0 or 1.')
+    return 0.
+
+
+def one_ndcg_at_k(r, k, method=1):
+    dcg_max = one_dcg_at_k(sorted(r, reverse=True), k, method)
+    if not dcg_max:
+        return 0.
+    return one_dcg_at_k(r, k, method) / dcg_max
+
+
+class EvalPlan:
+    """The two user dicts flattened once: eval user list, train-item mask in CSR form
+    (positions into the item range, ascending per user) and sorted positive keys."""
+
+    def __init__(self, train_user_dict, test_user_dict, n_items):
+        users = list(test_user_dict.keys())
+        self.n_users = len(users)
+        self.n_items = int(n_items)
+        self.user_ids = np.asarray(users, dtype=np.int32)
+        counts = np.zeros(self.n_users + 1, dtype=np.int64)
+        chunks = []
+        for j, u in enumerate(users):
+            m = np.unique(np.asarray(train_user_dict[u], dtype=np.int64))     # KeyError like metric.py:50
+            m = np.where(m < 0, m + self.n_items, m)                           # python-style negative index
+            if m.size and (m.min() < 0 or m.max() >= self.n_items):
+                raise IndexError("train item index out of range for user %r" % (u,))
+            chunks.append(np.sort(m))
+            counts[j + 1] = m.size
+        self.mask_ptr = np.cumsum(counts).astype(np.int32)
+        self.mask_items = (np.concatenate(chunks) if chunks else np.zeros(0)).astype(np.int32)
+        pos_len = np.asarray([len(test_user_dict[u]) for u in users], dtype=np.int64)
+        self.pos_len = pos_len
+        rows = np.repeat(np.arange(self.n_users, dtype=np.int64), pos_len)
+        items = (np.concatenate([np.asarray(test_user_dict[u], dtype=np.int64) for u in users])
+                 if self.n_users else np.zeros(0, dtype=np.int64))
+        self.pos_keys = np.unique(rows * self.n_items + items)
+        self._dev = {}
+
+    def device_arrays(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = tuple(th.from_numpy(a).to(device)
+                                   for a in (self.user_ids, self.mask_ptr, self.mask_items))
+        return self._dev[key]
+
+
+_PLAN_CACHE = {}
+
+
+def _plan_for(train_user_dict, test_user_dict, n_items):
+    key = (id(train_user_dict), id(test_user_dict), len(train_user_dict), len(test_user_dict), n_items)
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None and hit[0] is train_user_dict and hit[1] is test_user_dict:
+        return hit[2]
+    plan = EvalPlan(train_user_dict, test_user_dict, n_items)
+    if len(_PLAN_CACHE) > 8:
+        _PLAN_CACHE.clear()
+    _PLAN_CACHE[key] = (train_user_dict, test_user_dict, plan)
+    return plan
+
+
+def metrics_from_topk(topk: np.ndarray, plan: EvalPlan, K: int):
+    """Recall / NDCG from the (n_users, K) top-K positions; float64 like the reference helpers."""
+    n = plan.n_users
+    keys = np.arange(n, dtype=np.int64)[:, None] * plan.n_items + topk.astype(np.int64)
+    hits = np.isin(keys, plan.pos_keys).astype(np.float64)                     # metric.py:56-59
+    with np.errstate(divide="ignore", invalid="ignore"):
+        recall_u = np.where(plan.pos_len > 0, hits.sum(1) / np.maximum(plan.pos_len, 1), 0.0)   # metric.py:60-61
+    disc = 1.0 / np.log2(np.arange(2, K + 2))
+    dcg = (hits * disc).sum(1)
+    n_hit = hits.sum(1).astype(np.int64)
+    ideal = np.concatenate([[0.0], np.cumsum(disc)])[n_hit]                    # DCG of the sorted hit vector
+    ndcg_u = np.where(ideal > 0, dcg / np.where(ideal > 0, ideal, 1.0), 0.0)
+    return float(recall_u.sum() / n), float(ndcg_u.sum() / n), hits
+
+
+def topk_items(embedding, train_user_dict, test_user_dict, all_item_id_range, K, plan=None):
+    """(n_eval_users, K) int32 device tensor of top-K positions into ``all_item_id_range``."""
+    item_ids = th.as_tensor(all_item_id_range).reshape(-1)
+    n_items = item_ids.numel()
+    if plan is None:
+        plan = _plan_for(train_user_dict, test_user_dict, n_items)
+    dev = embedding.device
+    user_ids, mask_ptr, mask_items = plan.device_arrays(dev)
+    item_ids = item_ids.to(device=dev, dtype=th.int32)
+    return ops.score_topk(embedding, user_ids, item_ids, mask_ptr, mask_items, K), plan
+
+
+def calc_recall_ndcg(embedding, train_user_dict, test_user_dict, all_item_id_range, K, use_cuda=False, plan=None):
+    """Same signature and return value as reference metric.py:36.  ``use_cuda`` is accepted for
+    compatibility; the embedding must live on the GPU (there is no CPU path)."""
+    with th.no_grad():
+        topk, plan = topk_items(embedding, train_user_dict, test_user_dict, all_item_id_range, K, plan)
+        topk = topk.cpu().numpy()
+    recall, ndcg, _ = metrics_from_topk(topk, plan, K)
+    return recall, ndcg

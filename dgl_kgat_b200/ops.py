@@ -1,0 +1,162 @@
+"""Operator layer: torch tensors in, C-ABI kernel launches out (include/kgat_b200.h).
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every
+number on the hot path is produced by the sm_100a kernels in ``csrc/``.
+"""
+from __future__ import annotations
+
+import torch as th
+
+from . import _lib
+from .graph import DeviceGraph
+
+LEAKY_SLOPE = 0.01      # F.leaky_relu default used at reference models.py:66
+
+
+def _f32c(t: th.Tensor, device) -> th.Tensor:
+    if t.device != device:
+        raise _lib.KgatError("tensor on %s, graph structure on %s" % (t.device, device))
+    if t.dtype != th.float32:
+        raise _lib.KgatError("the KGAT kernels compute in fp32; got %s" % t.dtype)
+    return t.contiguous()
+
+
+def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Tensor, rows=None):
+    """Logits + per-destination softmax (reference models.py:146-154).
+
+    Returns ``(w_eid, w_csr)``: ``w_eid`` is the (E, 1) tensor ``compute_attention``
+    returns (original edge order); ``w_csr`` the same weights in CSR order.
+    """
+    lib = _lib.load()
+    dev = dg.device
+    entity, rel_emb, W_R = (_f32c(t.detach(), dev) for t in (entity, rel_emb, W_R))
+    d, rd = entity.shape[1], rel_emb.shape[1]
+    if tuple(W_R.shape) != (dg.n_rel, d, rd) or entity.shape[0] != dg.n_nodes or rel_emb.shape[0] != dg.n_rel:
+        raise _lib.KgatError("attention: parameter shapes do not match the graph (N=%d, R=%d)" % (dg.n_nodes, dg.n_rel))
+    E = max(dg.n_edges, 1)
+    logits = th.empty(E, dtype=th.float32, device=dev)
+    w_csr = th.empty(E, dtype=th.float32, device=dev)
+    w_eid = th.zeros(dg.n_edges, 1, dtype=th.float32, device=dev) if rows is not None else \
+        th.empty(dg.n_edges, 1, dtype=th.float32, device=dev)
+    r0, r1 = (0, dg.n_nodes) if rows is None else rows
+    with th.cuda.device(dev):
+        st = _lib.stream_ptr()
+        _lib.check(lib.kgat_attention_logits(dg.ref, entity.data_ptr(), rel_emb.data_ptr(), W_R.data_ptr(),
+                                             d, rd, logits.data_ptr(), st), "kgat_attention_logits")
+        _lib.check(lib.kgat_segment_softmax(dg.ref, r0, r1, logits.data_ptr(), w_csr.data_ptr(),
+                                            w_eid.data_ptr() if dg.n_edges else None, st), "kgat_segment_softmax")
+    return w_eid, w_csr
+
+
+def weights_to_csc(dg: DeviceGraph, w_eid: th.Tensor) -> th.Tensor:
+    lib = _lib.load()
+    w_csc = th.empty(max(dg.n_edges, 1), dtype=th.float32, device=dg.device)
+    with th.cuda.device(dg.device):
+        _lib.check(lib.kgat_edge_weights_from_eid(dg.ref, w_eid.data_ptr(), None, w_csc.data_ptr(),
+                                                  _lib.stream_ptr()), "kgat_edge_weights_from_eid")
+    return w_csc
+
+
+class Propagate(th.autograd.Function):
+    """All KGATConv layers + normalise + concat of ``Model.gnn`` (reference models.py:156-168)
+    as one autograd node; ``single_layer=True`` gives the bare ``KGATConv.forward`` output."""
+
+    @staticmethod
+    def forward(ctx, dg: DeviceGraph, w_csr, w_csc, masks, single_layer, entity, *weights):
+        lib = _lib.load()
+        dev = dg.device
+        entity = _f32c(entity, dev)
+        weights = [_f32c(w, dev) for w in weights]
+        N, L = dg.n_nodes, len(weights)
+        if entity.shape[0] != N:
+            raise _lib.KgatError("node feature matrix has %d rows, graph has %d nodes" % (entity.shape[0], N))
+        dims = [entity.shape[1]] + [w.shape[0] for w in weights]
+        for l, w in enumerate(weights):
+            if w.shape[1] != dims[l]:
+                raise _lib.KgatError("layer %d weight is %s, expected (*, %d)" % (l, tuple(w.shape), dims[l]))
+        masks = [None] * L if masks is None else [None if m is None else _f32c(m, dev) for m in masks]
+        concat = None if single_layer else th.empty(N, sum(dims), dtype=th.float32, device=dev)
+        cstride = 0 if concat is None else concat.shape[1]
+        saved = []
+        h, off = entity, dims[0]
+        with th.cuda.device(dev):
+            st = _lib.stream_ptr()
+            for l in range(L):
+                d_in, d_out = dims[l], dims[l + 1]
+                h_nb = th.empty(N, d_in, dtype=th.float32, device=dev)
+                h_out = th.empty(N, d_out, dtype=th.float32, device=dev)
+                act = th.empty(N, d_out, dtype=th.float32, device=dev) if masks[l] is not None else None
+                _lib.check(lib.kgat_layer_fwd(
+                    dg.ref, 0, N, h.data_ptr(), w_csr.data_ptr(), weights[l].data_ptr(), _lib.ptr(masks[l]),
+                    d_in, d_out, LEAKY_SLOPE, h_nb.data_ptr(), _lib.ptr(act), h_out.data_ptr(),
+                    _lib.ptr(concat), cstride, off, 0 if (l == 0 and concat is not None) else -1, st),
+                    "kgat_layer_fwd")
+                saved.append((h, h_nb, act, h_out))
+                h, off = h_out, off + d_out
+        ctx.dg, ctx.w_csc, ctx.masks, ctx.dims, ctx.single = dg, w_csc, masks, dims, single_layer
+        ctx.saved, ctx.weights = saved, weights
+        return h if single_layer else concat
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        dg, dims, L = ctx.dg, ctx.dims, len(ctx.weights)
+        dev, N = dg.device, dg.n_nodes
+        grad_out = _f32c(grad_out, dev)
+        n_part = lib.kgat_layer_bwd_partials()
+        d_concat = None if ctx.single else grad_out
+        cstride = 0 if ctx.single else grad_out.shape[1]
+        offs = [0]
+        for d in dims:
+            offs.append(offs[-1] + d)
+        d_weights = [None] * L
+        nxt_dx, nxt_dh = None, None
+        with th.cuda.device(dev):
+            st = _lib.stream_ptr()
+            for l in reversed(range(L)):
+                d_in, d_out = dims[l], dims[l + 1]
+                h_in, h_nb, act, h_out = ctx.saved[l]
+                dx = th.empty(N, d_in, dtype=th.float32, device=dev)
+                dh = th.empty(N, d_in, dtype=th.float32, device=dev)
+                dW = th.empty(d_out, d_in, dtype=th.float32, device=dev)
+                part = th.empty(n_part * d_out * d_in, dtype=th.float32, device=dev)
+                if ctx.single:
+                    # bare KGATConv: the incoming gradient IS the gradient of the layer output
+                    up_dx, up_dh = grad_out, None
+                else:
+                    up_dx, up_dh = nxt_dx, nxt_dh
+                _lib.check(lib.kgat_layer_bwd(
+                    dg.ref, 0, N, _lib.ptr(d_concat), cstride, offs[l + 1],
+                    _lib.ptr(up_dx), _lib.ptr(up_dh), ctx.w_csc.data_ptr(),
+                    h_in.data_ptr(), h_nb.data_ptr(), _lib.ptr(act), h_out.data_ptr(), _lib.ptr(ctx.masks[l]),
+                    ctx.weights[l].data_ptr(), d_in, d_out, LEAKY_SLOPE,
+                    dx.data_ptr(), dh.data_ptr(), dW.data_ptr(), part.data_ptr(), st), "kgat_layer_bwd")
+                d_weights[l] = dW
+                nxt_dx, nxt_dh = dx, dh
+            d_entity = None
+            if ctx.needs_input_grad[5]:
+                d_entity = th.empty(N, dims[0], dtype=th.float32, device=dev)
+                _lib.check(lib.kgat_input_bwd(dg.ref, 0, N, _lib.ptr(d_concat), cstride, 0, nxt_dx.data_ptr(),
+                                              nxt_dh.data_ptr(), ctx.w_csc.data_ptr(), dims[0],
+                                              d_entity.data_ptr(), st), "kgat_input_bwd")
+        return (None, None, None, None, None, d_entity, *d_weights)
+
+
+def score_topk(emb: th.Tensor, user_ids: th.Tensor, item_ids: th.Tensor, mask_ptr, mask_items, K: int,
+               want_scores: bool = False):
+    """Fused scoring + per-row top-K (reference metric.py:44-51).  ids are int32 device tensors;
+    returns (n_users, K) int32 positions into ``item_ids`` (and the scores when asked)."""
+    lib = _lib.load()
+    dev = emb.device
+    emb = _f32c(emb.detach(), dev)
+    n_users, n_items = user_ids.numel(), item_ids.numel()
+    if n_items < K:
+        raise _lib.KgatError("top-%d of %d items" % (K, n_items))
+    topk = th.empty(n_users, K, dtype=th.int32, device=dev)
+    scores = th.empty(n_users, K, dtype=th.float32, device=dev) if want_scores else None
+    with th.cuda.device(dev):
+        _lib.check(lib.kgat_score_topk(emb.data_ptr(), emb.stride(0), emb.shape[1], user_ids.data_ptr(), n_users,
+                                       item_ids.data_ptr(), n_items, _lib.ptr(mask_ptr),
+                                       _lib.ptr(mask_items) if mask_items is not None and mask_items.numel() else None,
+                                       K, topk.data_ptr(), _lib.ptr(scores), _lib.stream_ptr()), "kgat_score_topk")
+    return (topk, scores) if want_scores else topk

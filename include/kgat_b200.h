@@ -1,0 +1,179 @@
+/*
+ * kgat_b200.h -- C ABI of the B200-native KGAT hot path (libkgat_b200.so).
+ *
+ * The reference (jennyzhang0215/DGL-KGAT) is pure Python and has no FFI layer of
+ * its own: its GPU work happens inside DGL 0.4.x and ATen.  Each entry point
+ * below replaces one group of those library calls; the reference call site it
+ * stands in for is cited as file:line.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions (all entry points)
+ *   - return 0 on success, a negative kgat_status on failure; nothing throws,
+ *     nothing is printed.  kgat_error_string() maps a code to text;
+ *     kgat_last_cuda_error() returns the cudaError_t seen by the failing call.
+ *   - every pointer is a DEVICE pointer to contiguous row-major data owned by the
+ *     caller (fp32 values, int32 ids), unless its name ends in _host;
+ *   - the library allocates nothing and keeps no state between calls; scratch
+ *     comes in through an explicit workspace argument sized by a *_workspace_bytes
+ *     query;
+ *   - work is enqueued on the given stream and the call returns without
+ *     synchronising (CUDA-graph capturable), except kgat_graph_build which
+ *     performs no host read-back either;
+ *   - 16-byte alignment is required for every float array; all feature widths
+ *     must be multiples of 4.
+ */
+#ifndef KGAT_B200_H
+#define KGAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define KGAT_API __attribute__((visibility("default")))
+#else
+#define KGAT_API
+#endif
+
+typedef void* kgat_stream_t;          /* a cudaStream_t */
+
+enum kgat_status {
+    KGAT_OK = 0,
+    KGAT_ERR_INVALID_ARG = -1,        /* null pointer, negative size, misaligned buffer */
+    KGAT_ERR_UNSUPPORTED_DIM = -2,    /* feature width not a multiple of 4 or above the compiled maximum */
+    KGAT_ERR_WORKSPACE = -3,          /* workspace smaller than *_workspace_bytes says */
+    KGAT_ERR_CUDA = -4,               /* a CUDA runtime call failed; see kgat_last_cuda_error() */
+    KGAT_ERR_NO_DEVICE = -5           /* no sm_100 device is current */
+};
+
+KGAT_API int         kgat_version(void);                   /* ABI version, currently 1 */
+KGAT_API const char* kgat_error_string(int status);
+KGAT_API int         kgat_last_cuda_error(void);
+/* 0 when the current device can run the kernels (compute capability 10.x). */
+KGAT_API int         kgat_device_check(void);
+
+/*
+ * Collaborative knowledge graph in the three layouts the kernels read.
+ * Built from the (E,3) int32 (h, r, t) triplet array of dataset.py:84-93; edge i
+ * runs src = t[i] (tail) -> dst = h[i] (head) and has edge id i, exactly as
+ * dataset.py:114-119 hands it to DGL (add_edges(t, h); edata['type'] = r).
+ *
+ *   CSR, destination-sorted: position c = rank of the edge under (head, rel, eid)
+ *   CSC, source-sorted:      position k = rank of CSR position under (tail, c)
+ *   relation buckets:        position p = rank of CSR position under (rel, c);
+ *                            bucket r = the edges filter_edges(type == r) selects
+ *                            (models.py:150)
+ */
+typedef struct kgat_graph {
+    int64_t  n_nodes, n_edges, n_rel;
+    int32_t *csr_ptr;   /* [n_nodes+1] */
+    int32_t *csr_src;   /* [E] tail  */
+    int32_t *csr_dst;   /* [E] head  */
+    int32_t *csr_rel;   /* [E]       */
+    int32_t *csr_eid;   /* [E] triplet row */
+    int32_t *csc_ptr;   /* [n_nodes+1] */
+    int32_t *csc_dst;   /* [E] head of the k-th out-edge */
+    int32_t *csc_pos;   /* [E] its CSR position */
+    int32_t *csc_eid;   /* [E] its triplet row */
+    int32_t *rel_ptr;   /* [n_rel+1] */
+    int32_t *bk_pos;    /* [E] CSR position */
+    int32_t *bk_head;   /* [E] */
+    int32_t *bk_tail;   /* [E] */
+} kgat_graph_t;
+
+/* (1) graph construction -- replaces DGLGraph()/add_nodes/add_edges/readonly
+ *     (dataset.py:112-130, :203-211) and the per-relation filter_edges scans
+ *     (models.py:150).  head/rel/tail: device int32 columns of the triplet array.
+ *     Fills every array of *g (the caller allocated them).  Deterministic and
+ *     bit-exact against oracle/graph_ref.py. */
+KGAT_API size_t kgat_graph_build_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t n_rel);
+KGAT_API int    kgat_graph_build(const kgat_graph_t* g, const int32_t* head, const int32_t* rel,
+                        const int32_t* tail, void* workspace, size_t workspace_bytes,
+                        kgat_stream_t stream);
+
+/* (2) TransR attention logits pi(h,r,t) = (e_t W_r) . tanh(e_h W_r + e_r) for every
+ *     edge, relation-grouped -- replaces the loop of apply_edges(_att_score)
+ *     (models.py:135-152).  entity [n_nodes,d], rel_emb [n_rel,rd], W_R [n_rel,d,rd].
+ *     logits_csr[c] is the logit of the edge at CSR position c. */
+KGAT_API int kgat_attention_logits(const kgat_graph_t* g, const float* entity, const float* rel_emb,
+                          const float* W_R, int d, int rd, float* logits_csr,
+                          kgat_stream_t stream);
+
+/* (3a) softmax over the in-edges of every destination row -- replaces
+ *      edge_softmax (models.py:153).  Rows [row_begin,row_end).  Writes the weights
+ *      in CSR order and, when non-null, scattered to original edge-id order
+ *      (what compute_attention returns). */
+KGAT_API int kgat_segment_softmax(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                         const float* logits_csr, float* w_csr, float* w_eid,
+                         kgat_stream_t stream);
+
+/* (3b) edge-weight re-layout: w_csr[c] = w_eid[csr_eid[c]] and
+ *      w_csc[k] = w_eid[csc_eid[k]] -- what `g.edata['w'] = A_w` (kgat.py:144, :58)
+ *      means for the CSR/CSC kernels.  Either output may be null. */
+KGAT_API int kgat_edge_weights_from_eid(const kgat_graph_t* g, const float* w_eid, float* w_csr,
+                               float* w_csc, kgat_stream_t stream);
+
+/* (3c)+(4) one KGATConv forward over rows [row_begin,row_end) -- replaces
+ *      update_all(u_mul_e, sum) + mul + Linear + leaky_relu + Dropout
+ *      (models.py:60-70) and the F.normalize / cat of Model.gnn (models.py:163-167):
+ *        h_nb[v]  = sum_{c in CSR row v} w_csr[c] * h_in[csr_src[c]]
+ *        act[v]   = LeakyReLU_slope((h_in[v] (.) h_nb[v]) W2^T)
+ *        h_out[v] = act[v] (.) drop_mask[v]            (drop_mask null: no dropout)
+ *        concat[v, out_off : out_off+d_out] = h_out[v] / max(|h_out[v]|_2, 1e-12)
+ *        concat[v, in_off  : in_off +d_in ] = h_in[v]  (only when in_off >= 0)
+ *      W2 is [d_out, d_in] (nn.Linear weight).  act may be null when drop_mask is
+ *      null (then act == h_out).  concat may be null. */
+KGAT_API int kgat_layer_fwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                   const float* h_in, const float* w_csr, const float* W2,
+                   const float* drop_mask, int d_in, int d_out, float slope,
+                   float* h_nb, float* act, float* h_out,
+                   float* concat, int64_t concat_stride, int64_t out_off, int64_t in_off,
+                   kgat_stream_t stream);
+
+/* Backward of one KGATConv for rows [row_begin,row_end) -- replaces the autograd
+ * of the ops above incl. DGL's BackwardBinaryReduce (transposed aggregation).
+ * Gradient w.r.t. this layer's output row v is assembled in-kernel from
+ *   - the normalised copy:   d_concat[v, out_off : out_off+d_out]   (d_concat may be null)
+ *   - the next layer (both null for the last layer; each term is optional on its own):
+ *       nxt_dx_direct[v] + sum_{k in CSC row v} w_csc[k] * nxt_dh_nb[csc_dst[k]]
+ * then pushed through dropout / LeakyReLU / Linear / (.):
+ *   dW2       = sum_v dpre[v]^T (h_in[v] (.) h_nb[v])      (summed over the given rows)
+ *   dx_direct = (dpre W2) (.) h_nb        dh_nb = (dpre W2) (.) h_in
+ * dW2_partials: scratch of kgat_layer_bwd_partials() * d_out * d_in floats. */
+KGAT_API int kgat_layer_bwd_partials(void);
+KGAT_API int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                   const float* d_concat, int64_t concat_stride, int64_t out_off,
+                   const float* nxt_dx_direct, const float* nxt_dh_nb, const float* w_csc,
+                   const float* h_in, const float* h_nb, const float* act, const float* h_out,
+                   const float* drop_mask, const float* W2, int d_in, int d_out, float slope,
+                   float* dx_direct, float* dh_nb, float* dW2, float* dW2_partials,
+                   kgat_stream_t stream);
+
+/* Gradient of the entity table (input of layer 0) for rows [row_begin,row_end):
+ *   d_entity[v] = d_concat[v, in_off : in_off+d] + dx_direct[v]
+ *               + sum_{k in CSC row v} w_csc[k] * dh_nb[csc_dst[k]] */
+KGAT_API int kgat_input_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                   const float* d_concat, int64_t concat_stride, int64_t in_off,
+                   const float* dx_direct, const float* dh_nb, const float* w_csc, int d,
+                   float* d_entity, kgat_stream_t stream);
+
+/* (5) full-rank scoring with fused per-row top-K -- replaces the per-user loop of
+ *     metric.calc_recall_ndcg (metric.py:44-51): for eval user j,
+ *       score[i] = <emb[user_ids[j]], emb[item_ids[i]]>,
+ *       score[mask_items[mask_ptr[j] .. mask_ptr[j+1])] = 0.0   (train items, metric.py:50;
+ *                                  positions into item_ids, ascending per user),
+ *       topk_idx[j, :] = the K best positions, descending score, ties -> lower position.
+ *     The U x I score matrix is never materialised.  topk_score may be null. */
+KGAT_API int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
+                    const int32_t* user_ids, int64_t n_users,
+                    const int32_t* item_ids, int64_t n_items,
+                    const int32_t* mask_ptr, const int32_t* mask_items,
+                    int K, int32_t* topk_idx, float* topk_score, kgat_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGAT_B200_H */
