@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- KGAT attention + aggregation (fwd+bwd) edges/s and eval users/s on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config amazon-book]
+
+One "step"  = one compute_attention(g) (logits +
+per-head softmax, forward only - the reference never back-props it) + one gnn(g) forward + one
+backward from a BPR loss on B = 10 240 random (u, i+, i-) triples, dropout 0.  edges/s = E / T_step.
+Prints ONE JSON line (rank 0).
+
+ value      the step with inputs resident in HBM (batch ids already on the device), CUDA-event
+            timed over exactly K steps after W warm-ups, max over ranks.
+ e2e        the same step through the public Model API with the batch ids copied from pinned host
+            memory and the loss read back every step (the call sequence of kgat.py:153-165).
+ roofline   the dominant kernel of the step: algorithmic bytes (SURVEY.md section 8(d) E-model) / its
+            mean launch duration from CUDA events recorded around every launch inside the timed
+            region, against the measured HBM copy bandwidth of MEASURED_PEAKS.json.
+ cpu_baseline  the oracle port (oracle/kgat_ref.py = the reference's models.py op sequence on
+            pure-torch message passing) on the host cores, bounded sample.
+ --impl reference   times that CPU port alone, same metric/config, and prints the same line.
+Multi-GPU (torchrun): destination-partitioned graph, strong scaling (fixed graph).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch as th  # noqa: E402
+
+METRIC = "KG attention+aggregation edges/sec (fwd+bwd), amazon-book shape; eval users/s"
+BATCH = 10240
+REG = 1e-4
+K_EVAL = 20
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--config", default="amazon-book")
+    p.add_argument("--cpu-budget-s", type=float, default=25.0, help="CPU-baseline time budget inside the default run")
+    p.add_argument("--ref-budget-s", type=float, default=150.0, help="time budget of --impl reference")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-eval", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(N, E, R, dims):
+    """SURVEY.md section 8(d) E-model (fp32, 4-byte ids, every per-edge gather counted)."""
+    d0 = dims[0]
+    out = {"attention_logits": E * (4 + 4 + 4 * d0 + 4) + N * 4 * d0 + R * (d0 * d0 + d0) * 4,
+           "segment_softmax": E * 12 + N * 4, "edge_weights_to_csc": E * 12}
+    for l in range(len(dims) - 1):
+        d_in, d_out = dims[l], dims[l + 1]
+        out["layer_fwd_%dx%d" % (d_in, d_out)] = E * (8 + 4 * d_in) + N * 4 * d_in
+        # backward of layer l gathers the d_out-wide dh_nb of layer l+1 (none for the last layer)
+        gather = E * (8 + 4 * d_out) if l + 1 < len(dims) - 1 else 0
+        out["layer_bwd_%dx%d" % (d_in, d_out)] = gather + N * 4 * (4 * d_in + 3 * d_out)
+    out["input_bwd_%d" % d0] = E * (8 + 4 * d0) + N * 4 * 3 * d0
+    return out
+
+
+def step_bytes(N, E, R):
+    return E * 1596 + N * 1536 + R * 16640        # SURVEY.md section 8(d) B_step
+
+
+def make_batches(cfg, n, seed=99):
+    rng = np.random.default_rng(seed)
+    U, I = cfg.n_users, cfg.n_items
+    return [tuple(th.from_numpy(rng.integers(lo, hi, BATCH)).pin_memory() if th.cuda.is_available()
+                  else th.from_numpy(rng.integers(lo, hi, BATCH))
+                  for lo, hi in ((0, U), (U, U + I), (U, U + I))) for _ in range(n)]
+
+
+# ------------------------------------------------------------------------------------------ CPU port
+def cpu_port_steps(ck, budget_s, max_steps, warmup=1, seed=1234):
+    """Times the oracle port (reference op sequence on pure-torch message passing) on the host cores.
+    Bounded: if the full graph does not fit the budget, a sample of COMPLETE destination rows is used
+    (softmax groups stay intact, the entity table stays full size)."""
+    from oracle import kgat_ref
+    cores = os.cpu_count() or 1
+    th.set_num_threads(cores)
+    cfg = ck.cfg
+    N, R = cfg.n_nodes, cfg.n_relations
+    params = kgat_ref.init_params(N, R, seed=seed)
+    rng = np.random.default_rng(5)
+    batches = make_batches(cfg, 1)
+    ids = [b.clone() for b in batches[0]]
+
+    def one_step(trip):
+        t0 = time.perf_counter()
+        w = kgat_ref.compute_attention(params, trip, N)
+        kgat_ref.cf_step(params, trip, w, N, *ids, REG)
+        return time.perf_counter() - t0
+
+    # calibrate on 5 % of the rows
+    rows = rng.permutation(N)
+    frac0 = 0.05
+    sel = np.isin(ck.triplets[:, 0], rows[: int(N * frac0)])
+    t_cal = one_step(ck.triplets[sel])
+    rate = sel.sum() / t_cal
+    want_steps = max(1, min(max_steps, 3))
+    frac = min(1.0, budget_s * rate / ((want_steps + warmup) * ck.triplets.shape[0]))
+    if frac < 1.0:
+        sel = np.isin(ck.triplets[:, 0], rows[: max(1, int(N * frac))])
+        trip = ck.triplets[sel]
+        sample = "%.1f%% of destination rows (complete rows, %d edges), %d timed steps" % (100 * frac, trip.shape[0], want_steps)
+    else:
+        trip = ck.triplets
+        sample = "full graph (%d edges), %d timed steps" % (trip.shape[0], want_steps)
+    for _ in range(warmup):
+        one_step(trip)
+    times = [one_step(trip) for _ in range(want_steps)]
+    t = float(np.median(times))
+    return {"value": trip.shape[0] / t, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,
+            "ms_per_step": t * 1e3, "edges": int(trip.shape[0])}
+
+
+def cpu_port_eval(ck, n_users=256):
+    """metric.calc_recall_ndcg restated per user (the reference's loop) on a fixed user sample."""
+    from oracle import kgat_ref
+    from dgl_kgat_b200.synth import pairs_to_user_dict
+    cfg = ck.cfg
+    th.manual_seed(0)
+    emb = th.randn(cfg.n_nodes, 176)
+    tr = pairs_to_user_dict(ck.train_pairs, cfg.n_users)
+    te_all = pairs_to_user_dict(ck.valid_pairs, cfg.n_users)
+    users = list(te_all.keys())[:n_users]
+    te = {u: te_all[u] for u in users}
+    t0 = time.perf_counter()
+    kgat_ref.calc_recall_ndcg(emb, tr, te, ck.item_id_range, K_EVAL)
+    return len(users) / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) alone."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dgl_kgat_b200.synth import synth_ckg
+    ck = synth_ckg(args.config, seed=1234)
+    cfg = ck.cfg
+    res = cpu_port_steps(ck, args.ref_budget_s, args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg.name + "-shaped synthetic CKG", "nodes": cfg.n_nodes, "edges": cfg.n_edges,
+                   "relations": cfg.n_relations, "layers": "64-32-16", "batch": BATCH},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference models.py op sequence on pure-torch CPU message passing (DGL itself cannot be installed)",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch.distributed as tdist
+    from dgl_kgat_b200 import _lib, metric, models
+    from dgl_kgat_b200.graph import CKGraph
+    from dgl_kgat_b200.synth import pairs_to_user_dict, synth_ckg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not th.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 GPU: the KGAT hot path has no CPU fallback")
+    th.cuda.set_device(local)
+    dev = th.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        tdist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().kgat_device_check(), "kgat_device_check")
+
+    ck = synth_ckg(args.config, seed=1234)
+    cfg = ck.cfg
+    N, E, R = cfg.n_nodes, cfg.n_edges, cfg.n_relations
+    th.manual_seed(1234)
+    model = models.Model(True, 64, "kgat", 3, 64, 0.0, n_entities=N, n_relations=R, relation_dim=64,
+                         reg_lambda_kg=REG, reg_lambda_gnn=REG).to(dev)
+    dims = [64, 64, 32, 16]
+    n_total = args.steps + args.warmup
+    batches = make_batches(cfg, n_total)
+    dev_batches = [tuple(b.to(dev) for b in bt) for bt in batches]
+
+    if distributed:
+        from dgl_kgat_b200.dist import DistKGAT
+        dk = DistKGAT(model, N, ck.triplets, R, dev)
+
+        def step(ids):
+            model.zero_grad(set_to_none=True)
+            dk.compute_attention()
+            emb = dk.gnn()
+            loss = dk.get_loss(emb, *ids)
+            loss.backward()
+            return loss
+    else:
+        g = CKGraph(N, ck.triplets, n_rel=R)
+        g.ndata["id"] = g.ndata["id"].to(dev)
+        g.device_graph(dev)
+
+        def step(ids):
+            model.zero_grad(set_to_none=True)
+            with th.no_grad():
+                A_w = model.compute_attention(g)
+            g.edata["w"] = A_w
+            emb = model.gnn(g, g.ndata["id"])
+            loss = model.get_loss(emb, *ids)
+            loss.backward()
+            return loss
+
+    def barrier():
+        if distributed:
+            tdist.barrier()
+        th.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if not distributed:
+            return ms
+        t = th.tensor([ms], dtype=th.float64, device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    rec = _lib.RECORDER
+    # ---- value: inputs resident in HBM -------------------------------------------------------
+    for i in range(args.warmup):
+        step(dev_batches[i])
+    barrier()
+    rec.reset(enabled=True, time_kernels=True)
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(dev_batches[args.warmup + i])
+        e1.record()
+        barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = rec.launches
+    kernel_ms = {k: float(np.mean(v)) for k, v in rec.durations_ms().items()}
+    rec.reset(enabled=False)
+    ms_step = ms_total / args.steps
+    value = E / (ms_step * 1e-3)
+
+    # ---- e2e: host batch ids in, loss out, every step ----------------------------------------
+    for i in range(min(args.warmup, 3)):
+        step(tuple(b.to(dev, non_blocking=True) for b in batches[i]))
+    barrier()
+    t_e2e = []
+    e0.record()
+    for i in range(args.steps):
+        ids = tuple(b.to(dev, non_blocking=True) for b in batches[args.warmup + i])
+        loss = step(ids)
+        loss_val = loss.item()                       # device -> host read of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e = {"value": E / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 3 * BATCH * 8,
+           "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": loss_val}
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    alg = algorithmic_bytes(N, E, R, dims)
+    table = {}
+    for name, ms in kernel_ms.items():
+        b = alg.get(name)
+        table[name] = {"ms": round(ms, 4), "alg_MB": None if b is None else round(b / 1e6, 2),
+                       "GBps": None if b is None else round(b / (ms * 1e-3) / 1e9, 1)}
+    roofline = None
+    if kernel_ms and not distributed:
+        top = max(kernel_ms, key=kernel_ms.get)
+        ach = alg[top] / (kernel_ms[top] * 1e-3) / 1e9
+        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "launch_ms": kernel_ms[top],
+                    "step_frac": (step_bytes(N, E, R) / (ms_step * 1e-3) / 1e9) / peak,
+                    "step_alg_GB": step_bytes(N, E, R) / 1e9}
+
+    # ---- eval users/s -------------------------------------------------------------------------
+    eval_info = None
+    if not args.no_eval:
+        tr = pairs_to_user_dict(ck.train_pairs, cfg.n_users)
+        te = pairs_to_user_dict(ck.valid_pairs, cfg.n_users)
+        users = list(te.keys())
+        if distributed:
+            users = users[rank::world]
+            te = {u: te[u] for u in users}
+        with th.no_grad():
+            if distributed:
+                emb = dk.full_embedding(dk.gnn())
+            else:
+                emb = model.gnn(g, g.ndata["id"]).detach()
+        items = th.as_tensor(ck.item_id_range, device=dev)
+        plan = metric.EvalPlan(tr, te, cfg.n_items)
+        metric.topk_items(emb, tr, te, items, K_EVAL, plan=plan)          # warm-up (uploads the plan)
+        barrier()
+        e0.record()
+        topk, _ = metric.topk_items(emb, tr, te, items, K_EVAL, plan=plan)
+        e1.record()
+        barrier()
+        ms_k = max_over_ranks(e0.elapsed_time(e1))
+        t0 = time.perf_counter()
+        r, n_ = metric.calc_recall_ndcg(emb, tr, te, items, K_EVAL, plan=plan)
+        th.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        n_users_total = len(pairs_to_user_dict(ck.valid_pairs, cfg.n_users))
+        flops = 2.0 * n_users_total * cfg.n_items * emb.shape[1]
+        eval_info = {"users": n_users_total, "items": cfg.n_items, "dim": int(emb.shape[1]),
+                     "users_per_s": n_users_total / (ms_k * 1e-3), "kernel_ms": ms_k,
+                     "tflops": flops / (ms_k * 1e-3) / 1e12,
+                     "users_per_s_e2e": len(users) * (world if distributed else 1) / wall,
+                     "recall": r, "ndcg": n_}
+
+    # ---- CPU baseline (rank 0, N = 1) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and not distributed and not args.no_cpu_baseline:
+        res = cpu_port_steps(ck, args.cpu_budget_s, 2)
+        cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if not args.no_eval:
+            cpu["eval_users_per_s"] = cpu_port_eval(ck, 128)
+
+    if rank == 0:
+        work_mb = (N * 4 * (176 + 2 * (64 + 64 + 32) + 64 + 32 + 16) + E * 4 * 12) / 1e6
+        line = {
+            "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg.name + "-shaped synthetic CKG, 1 attention + 1 gnn fwd+bwd per step",
+                       "nodes": N, "edges": E, "relations": R, "layers": "64-32-16", "batch": BATCH,
+                       "l2_policy": "inputs larger than L2 (%.0f MB touched per step vs 126 MB L2)" % work_mb,
+                       "parallelism": "dst-partition x%d" % world if distributed else "single GPU"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+            "roofline": roofline, "cpu_baseline": cpu, "kernels": table, "eval": eval_info,
+        }
+        print(json.dumps(line))
+    if distributed:
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

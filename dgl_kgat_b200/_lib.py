@@ -95,3 +95,50 @@ def ptr(t):
 def stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+class Recorder:
+    """Counts the kernels this library launches and, when ``time_kernels`` is set, brackets every
+    C-ABI call with CUDA events on the launching stream (bench.py reads both).  Off by default."""
+
+    def __init__(self):
+        self.enabled = False
+        self.time_kernels = False
+        self.launches = 0
+        self.events = {}        # name -> list of (start, stop)
+
+    def reset(self, enabled=True, time_kernels=False):
+        self.enabled, self.time_kernels, self.launches, self.events = enabled, time_kernels, 0, {}
+
+    def durations_ms(self):
+        """name -> list of per-call durations (call after a synchronize)."""
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.events.items()}
+
+
+RECORDER = Recorder()
+
+
+class record:
+    """``with record("kgat_layer_fwd", 1): lib.kgat_layer_fwd(...)``"""
+    __slots__ = ("name", "n", "start")
+
+    def __init__(self, name, n_launches=1):
+        self.name, self.n, self.start = name, n_launches, None
+
+    def __enter__(self):
+        r = RECORDER
+        if r.enabled:
+            r.launches += self.n
+            if r.time_kernels:
+                import torch
+                self.start = torch.cuda.Event(enable_timing=True)
+                self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.start is not None:
+            import torch
+            stop = torch.cuda.Event(enable_timing=True)
+            stop.record()
+            RECORDER.events.setdefault(self.name, []).append((self.start, stop))
+        return False

@@ -74,11 +74,12 @@ class KGATConv(nn.Module):
         ``drop_mask`` overrides the mask nn.Dropout would draw (used by the parity tests)."""
         _require_graph(g)
         g = g.local_var()
-        dg = g.device_graph(nfeat.device)
         w_csr, w_csc = g.edge_weight_layouts(nfeat.device)
+        dg = g.device_graph(nfeat.device)
         if drop_mask is None:
             drop_mask = _dropout_mask(self.mess_drop, g.n_nodes, self.res_fc_2.out_features, nfeat.device)
-        return ops.Propagate.apply(dg, w_csr, w_csc, [drop_mask], True, nfeat, self.res_fc_2.weight)
+        return ops.Propagate.apply(ops.PropagatePlan(dg, w_csr, w_csc), [drop_mask], True, nfeat,
+                                   self.res_fc_2.weight)
 
 
 class Model(nn.Module):
@@ -160,13 +161,13 @@ class Model(nn.Module):
         _require_graph(g)
         g = g.local_var()
         dev = self.entity_embed.weight.device
-        dg = g.device_graph(dev)
         w_csr, w_csc = g.edge_weight_layouts(dev)
+        dg = g.device_graph(dev)
         h = self._node_features(g)
         if drop_masks is None:
             drop_masks = [_dropout_mask(l.mess_drop, g.n_nodes, l.res_fc_2.out_features, dev) for l in self.layers]
         weights = [l.res_fc_2.weight for l in self.layers]
-        return ops.Propagate.apply(dg, w_csr, w_csc, list(drop_masks), False, h, *weights)
+        return ops.Propagate.apply(ops.PropagatePlan(dg, w_csr, w_csc), list(drop_masks), False, h, *weights)
 
     def get_loss(self, embedding, src_ids, pos_dst_ids, neg_dst_ids):
         """BPR loss + L2 regulariser on the gathered rows (models.py:170-178)."""

@@ -41,10 +41,12 @@ def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Te
     r0, r1 = (0, dg.n_nodes) if rows is None else rows
     with th.cuda.device(dev):
         st = _lib.stream_ptr()
-        _lib.check(lib.kgat_attention_logits(dg.ref, entity.data_ptr(), rel_emb.data_ptr(), W_R.data_ptr(),
-                                             d, rd, logits.data_ptr(), st), "kgat_attention_logits")
-        _lib.check(lib.kgat_segment_softmax(dg.ref, r0, r1, logits.data_ptr(), w_csr.data_ptr(),
-                                            w_eid.data_ptr() if dg.n_edges else None, st), "kgat_segment_softmax")
+        with _lib.record("attention_logits"):
+            _lib.check(lib.kgat_attention_logits(dg.ref, entity.data_ptr(), rel_emb.data_ptr(), W_R.data_ptr(),
+                                                 d, rd, logits.data_ptr(), st), "kgat_attention_logits")
+        with _lib.record("segment_softmax"):
+            _lib.check(lib.kgat_segment_softmax(dg.ref, r0, r1, logits.data_ptr(), w_csr.data_ptr(),
+                                                w_eid.data_ptr() if dg.n_edges else None, st), "kgat_segment_softmax")
     return w_eid, w_csr
 
 
@@ -52,9 +54,29 @@ def weights_to_csc(dg: DeviceGraph, w_eid: th.Tensor) -> th.Tensor:
     lib = _lib.load()
     w_csc = th.empty(max(dg.n_edges, 1), dtype=th.float32, device=dg.device)
     with th.cuda.device(dg.device):
-        _lib.check(lib.kgat_edge_weights_from_eid(dg.ref, w_eid.data_ptr(), None, w_csc.data_ptr(),
-                                                  _lib.stream_ptr()), "kgat_edge_weights_from_eid")
+        with _lib.record("edge_weights_to_csc"):
+            _lib.check(lib.kgat_edge_weights_from_eid(dg.ref, w_eid.data_ptr(), None, w_csc.data_ptr(),
+                                                      _lib.stream_ptr()), "kgat_edge_weights_from_eid")
     return w_csc
+
+
+class PropagatePlan:
+    """Everything ``Propagate`` needs besides the differentiable inputs.
+
+    Single GPU: one DeviceGraph, all rows.  Multi-GPU (dist.py): ``dg_fwd`` holds the CSR of the
+    in-edges of the owned destination rows ``[r0, r1)``, ``dg_bwd`` the CSC of the out-edges of the
+    same rows, and ``exchange(t)`` all-gathers the owned rows of a full-size (N, d) buffer in place;
+    ``reduce(t)`` sums a small replicated tensor over ranks."""
+
+    def __init__(self, dg_fwd, w_csr, w_csc, dg_bwd=None, rows=None, exchange=None, reduce=None):
+        self.dg_fwd, self.dg_bwd = dg_fwd, dg_bwd if dg_bwd is not None else dg_fwd
+        self.w_csr, self.w_csc = w_csr, w_csc
+        self.r0, self.r1 = (0, dg_fwd.n_nodes) if rows is None else rows
+        self.exchange, self.reduce = exchange, reduce
+
+    @property
+    def distributed(self):
+        return self.exchange is not None
 
 
 class Propagate(th.autograd.Function):
@@ -62,8 +84,9 @@ class Propagate(th.autograd.Function):
     as one autograd node; ``single_layer=True`` gives the bare ``KGATConv.forward`` output."""
 
     @staticmethod
-    def forward(ctx, dg: DeviceGraph, w_csr, w_csc, masks, single_layer, entity, *weights):
+    def forward(ctx, plan: PropagatePlan, masks, single_layer, entity, *weights):
         lib = _lib.load()
+        dg = plan.dg_fwd
         dev = dg.device
         entity = _f32c(entity, dev)
         weights = [_f32c(w, dev) for w in weights]
@@ -75,7 +98,8 @@ class Propagate(th.autograd.Function):
             if w.shape[1] != dims[l]:
                 raise _lib.KgatError("layer %d weight is %s, expected (*, %d)" % (l, tuple(w.shape), dims[l]))
         masks = [None] * L if masks is None else [None if m is None else _f32c(m, dev) for m in masks]
-        concat = None if single_layer else th.empty(N, sum(dims), dtype=th.float32, device=dev)
+        alloc = th.zeros if plan.distributed else th.empty      # rows of other ranks stay defined
+        concat = None if single_layer else alloc(N, sum(dims), dtype=th.float32, device=dev)
         cstride = 0 if concat is None else concat.shape[1]
         saved = []
         h, off = entity, dims[0]
@@ -84,23 +108,27 @@ class Propagate(th.autograd.Function):
             for l in range(L):
                 d_in, d_out = dims[l], dims[l + 1]
                 h_nb = th.empty(N, d_in, dtype=th.float32, device=dev)
-                h_out = th.empty(N, d_out, dtype=th.float32, device=dev)
+                h_out = alloc(N, d_out, dtype=th.float32, device=dev)
                 act = th.empty(N, d_out, dtype=th.float32, device=dev) if masks[l] is not None else None
-                _lib.check(lib.kgat_layer_fwd(
-                    dg.ref, 0, N, h.data_ptr(), w_csr.data_ptr(), weights[l].data_ptr(), _lib.ptr(masks[l]),
-                    d_in, d_out, LEAKY_SLOPE, h_nb.data_ptr(), _lib.ptr(act), h_out.data_ptr(),
-                    _lib.ptr(concat), cstride, off, 0 if (l == 0 and concat is not None) else -1, st),
-                    "kgat_layer_fwd")
+                with _lib.record("layer_fwd_%dx%d" % (d_in, d_out)):
+                    _lib.check(lib.kgat_layer_fwd(
+                        dg.ref, plan.r0, plan.r1, h.data_ptr(), plan.w_csr.data_ptr(), weights[l].data_ptr(),
+                        _lib.ptr(masks[l]), d_in, d_out, LEAKY_SLOPE, h_nb.data_ptr(), _lib.ptr(act),
+                        h_out.data_ptr(), _lib.ptr(concat), cstride, off,
+                        0 if (l == 0 and concat is not None) else -1, st), "kgat_layer_fwd")
+                if plan.distributed and l + 1 < L:
+                    plan.exchange(h_out)                # the next layer gathers rows owned by other ranks
                 saved.append((h, h_nb, act, h_out))
                 h, off = h_out, off + d_out
-        ctx.dg, ctx.w_csc, ctx.masks, ctx.dims, ctx.single = dg, w_csc, masks, dims, single_layer
+        ctx.plan, ctx.masks, ctx.dims, ctx.single = plan, masks, dims, single_layer
         ctx.saved, ctx.weights = saved, weights
         return h if single_layer else concat
 
     @staticmethod
     def backward(ctx, grad_out):
         lib = _lib.load()
-        dg, dims, L = ctx.dg, ctx.dims, len(ctx.weights)
+        plan, dims, L = ctx.plan, ctx.dims, len(ctx.weights)
+        dg = plan.dg_bwd
         dev, N = dg.device, dg.n_nodes
         grad_out = _f32c(grad_out, dev)
         n_part = lib.kgat_layer_bwd_partials()
@@ -111,13 +139,14 @@ class Propagate(th.autograd.Function):
             offs.append(offs[-1] + d)
         d_weights = [None] * L
         nxt_dx, nxt_dh = None, None
+        alloc = th.zeros if plan.distributed else th.empty
         with th.cuda.device(dev):
             st = _lib.stream_ptr()
             for l in reversed(range(L)):
                 d_in, d_out = dims[l], dims[l + 1]
                 h_in, h_nb, act, h_out = ctx.saved[l]
                 dx = th.empty(N, d_in, dtype=th.float32, device=dev)
-                dh = th.empty(N, d_in, dtype=th.float32, device=dev)
+                dh = alloc(N, d_in, dtype=th.float32, device=dev)
                 dW = th.empty(d_out, d_in, dtype=th.float32, device=dev)
                 part = th.empty(n_part * d_out * d_in, dtype=th.float32, device=dev)
                 if ctx.single:
@@ -125,21 +154,28 @@ class Propagate(th.autograd.Function):
                     up_dx, up_dh = grad_out, None
                 else:
                     up_dx, up_dh = nxt_dx, nxt_dh
-                _lib.check(lib.kgat_layer_bwd(
-                    dg.ref, 0, N, _lib.ptr(d_concat), cstride, offs[l + 1],
-                    _lib.ptr(up_dx), _lib.ptr(up_dh), ctx.w_csc.data_ptr(),
-                    h_in.data_ptr(), h_nb.data_ptr(), _lib.ptr(act), h_out.data_ptr(), _lib.ptr(ctx.masks[l]),
-                    ctx.weights[l].data_ptr(), d_in, d_out, LEAKY_SLOPE,
-                    dx.data_ptr(), dh.data_ptr(), dW.data_ptr(), part.data_ptr(), st), "kgat_layer_bwd")
+                with _lib.record("layer_bwd_%dx%d" % (d_in, d_out), 2):
+                    _lib.check(lib.kgat_layer_bwd(
+                        dg.ref, plan.r0, plan.r1, _lib.ptr(d_concat), cstride, offs[l + 1],
+                        _lib.ptr(up_dx), _lib.ptr(up_dh), plan.w_csc.data_ptr(),
+                        h_in.data_ptr(), h_nb.data_ptr(), _lib.ptr(act), h_out.data_ptr(), _lib.ptr(ctx.masks[l]),
+                        ctx.weights[l].data_ptr(), d_in, d_out, LEAKY_SLOPE,
+                        dx.data_ptr(), dh.data_ptr(), dW.data_ptr(), part.data_ptr(), st), "kgat_layer_bwd")
+                if plan.distributed:
+                    plan.exchange(dh)                   # dh_nb rows of every rank feed the transposed gather below
+                    plan.reduce(dW)
                 d_weights[l] = dW
                 nxt_dx, nxt_dh = dx, dh
             d_entity = None
-            if ctx.needs_input_grad[5]:
-                d_entity = th.empty(N, dims[0], dtype=th.float32, device=dev)
-                _lib.check(lib.kgat_input_bwd(dg.ref, 0, N, _lib.ptr(d_concat), cstride, 0, nxt_dx.data_ptr(),
-                                              nxt_dh.data_ptr(), ctx.w_csc.data_ptr(), dims[0],
-                                              d_entity.data_ptr(), st), "kgat_input_bwd")
-        return (None, None, None, None, None, d_entity, *d_weights)
+            if ctx.needs_input_grad[3]:
+                d_entity = alloc(N, dims[0], dtype=th.float32, device=dev)
+                with _lib.record("input_bwd_%d" % dims[0]):
+                    _lib.check(lib.kgat_input_bwd(dg.ref, plan.r0, plan.r1, _lib.ptr(d_concat), cstride, 0,
+                                                  nxt_dx.data_ptr(), nxt_dh.data_ptr(), plan.w_csc.data_ptr(),
+                                                  dims[0], d_entity.data_ptr(), st), "kgat_input_bwd")
+                if plan.distributed:
+                    plan.exchange(d_entity)             # replicated parameters: every rank needs the full gradient
+        return (None, None, None, d_entity, *d_weights)
 
 
 def score_topk(emb: th.Tensor, user_ids: th.Tensor, item_ids: th.Tensor, mask_ptr, mask_items, K: int,
@@ -155,8 +191,9 @@ def score_topk(emb: th.Tensor, user_ids: th.Tensor, item_ids: th.Tensor, mask_pt
     topk = th.empty(n_users, K, dtype=th.int32, device=dev)
     scores = th.empty(n_users, K, dtype=th.float32, device=dev) if want_scores else None
     with th.cuda.device(dev):
-        _lib.check(lib.kgat_score_topk(emb.data_ptr(), emb.stride(0), emb.shape[1], user_ids.data_ptr(), n_users,
-                                       item_ids.data_ptr(), n_items, _lib.ptr(mask_ptr),
-                                       _lib.ptr(mask_items) if mask_items is not None and mask_items.numel() else None,
-                                       K, topk.data_ptr(), _lib.ptr(scores), _lib.stream_ptr()), "kgat_score_topk")
+        with _lib.record("score_topk"):
+            _lib.check(lib.kgat_score_topk(emb.data_ptr(), emb.stride(0), emb.shape[1], user_ids.data_ptr(), n_users,
+                                           item_ids.data_ptr(), n_items, _lib.ptr(mask_ptr),
+                                           _lib.ptr(mask_items) if mask_items is not None and mask_items.numel() else None,
+                                           K, topk.data_ptr(), _lib.ptr(scores), _lib.stream_ptr()), "kgat_score_topk")
     return (topk, scores) if want_scores else topk

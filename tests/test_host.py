@@ -1,0 +1,206 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares, the host
+mirror of the reference interface behaves like the reference's, and the product refuses to run
+without its CUDA path (no fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch as th
+
+from dgl_kgat_b200 import _lib, dataset, metric, models, synth
+from dgl_kgat_b200.graph import CKGraph
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "kgat_b200.h")).read()
+    return sorted(set(re.findall(r"KGAT_API\s+[\w\s\*]+?\b(kgat_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) >= 14
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), "libkgat_b200.so does not export %s" % s
+    assert sorted(_lib.SIGNATURES) == syms          # the ctypes binding covers the header exactly
+    loaded = _lib.load()
+    assert loaded.kgat_version() == 1
+    assert loaded.kgat_error_string(-2).decode().startswith("unsupported")
+
+
+def test_graph_struct_layout_matches_header():
+    text = open(os.path.join(ROOT, "include", "kgat_b200.h")).read()
+    body = text[text.index("typedef struct kgat_graph {"): text.index("} kgat_graph_t;")]
+    fields = re.findall(r"\*(\w+);", body)
+    assert fields == _lib.GRAPH_ARRAYS
+    assert ctypes.sizeof(_lib.KgatGraph) == 3 * 8 + len(fields) * 8
+
+
+def test_no_cpu_fallback():
+    dl = dataset.DataLoader.from_synthetic("tiny")
+    th.manual_seed(0)
+    m = models.Model(True, 64, "kgat", 3, 64, 0.0, n_entities=dl.n_KG_entity, n_relations=dl.n_KG_relation,
+                     relation_dim=64)
+    with pytest.raises(_lib.KgatError):
+        m.compute_attention(dl.train_g)             # parameters on the CPU: refuse, do not emulate
+    with pytest.raises(KeyError):
+        m.gnn(dl.train_g, None)                     # edata['w'] not set
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dgl_kgat_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_model_surface_and_state_dict_keys():
+    th.manual_seed(1234)
+    m = models.Model(True, 64, "kgat", 3, 64, 0.1, n_entities=100, n_relations=5, relation_dim=64,
+                     reg_lambda_kg=1e-4, reg_lambda_gnn=1e-4)
+    sd = m.state_dict()
+    assert list(sd.keys()) == ["W_R", "entity_embed.weight", "relation_embed.weight",
+                               "layers.0.res_fc_2.weight", "layers.1.res_fc_2.weight", "layers.2.res_fc_2.weight"]
+    assert [tuple(sd["layers.%d.res_fc_2.weight" % i].shape) for i in range(3)] == [(64, 64), (32, 64), (16, 32)]
+    assert tuple(sd["W_R"].shape) == (5, 64, 64)
+    # same seed -> same numbers as the oracle's restatement of the reference initialisers
+    from oracle import kgat_ref
+    p = kgat_ref.init_params(100, 5, seed=1234)
+    for k in sd:
+        assert th.equal(sd[k], p[k]), k
+    with pytest.raises(NotImplementedError):
+        models.Model(True, 64, "graphsage", 3, 64, 0.1, n_entities=10, n_relations=2, relation_dim=64)
+    # the torch-side heads run anywhere
+    ids = th.arange(10)
+    assert m.transR(ids, ids % 5, ids + 1, ids + 2).ndim == 0
+    emb = th.randn(100, 176)
+    assert m.get_loss(emb, ids, ids + 10, ids + 20).ndim == 0
+
+
+def test_get_loss_and_transr_match_oracle():
+    from oracle import kgat_ref
+    th.manual_seed(3)
+    m = models.Model(True, 64, "kgat", 3, 64, 0.0, n_entities=50, n_relations=4, relation_dim=64,
+                     reg_lambda_kg=1e-3, reg_lambda_gnn=1e-3)
+    p = {k: v.detach() for k, v in m.state_dict().items()}
+    emb = th.randn(50, 176)
+    a, b, c = th.randint(0, 50, (3, 32))
+    assert th.allclose(m.get_loss(emb, a, b, c), kgat_ref.get_loss(emb, a, b, c, 1e-3))
+    r = th.randint(0, 4, (32,))
+    assert th.allclose(m.transR(a, r, b, c), kgat_ref.transr_loss(p, a, r, b, c, 1e-3))
+
+
+def test_graph_surface():
+    trip = np.array([(0, 0, 1), (0, 1, 2), (3, 0, 0), (0, 0, 3), (1, 1, 3)], np.int32)
+    g = CKGraph(4, trip)
+    assert g.number_of_nodes() == 4 and g.number_of_edges() == 5 and g.n_rel == 2
+    assert th.equal(g.ndata["id"], th.arange(4)) and g.edata["type"].tolist() == [0, 1, 0, 0, 1]
+    src, dst = g.all_edges()
+    assert src.tolist() == [1, 2, 0, 3, 3] and dst.tolist() == [0, 0, 3, 0, 1]      # src = tail, dst = head
+    lv = g.local_var()
+    lv.edata["w"] = th.ones(5, 1)
+    assert "w" not in g.edata                       # writes on the local view do not leak
+    assert g.ids_are_identity()
+    with pytest.raises(ValueError):
+        CKGraph(3, trip)
+    with pytest.raises(ValueError):
+        CKGraph(4, trip, n_rel=1)
+
+
+def test_dataloader_tsv_roundtrip(tmp_path):
+    """Files in the reference's on-disk format give the same object as the in-memory path."""
+    ck = synth.synth_ckg("tiny")
+    U = ck.cfg.n_users
+    d = tmp_path / "datasets" / "toy" / "data"
+    d.mkdir(parents=True)
+
+    def dump(name, cols, arr):
+        with open(d / name, "w") as f:
+            f.write("\t".join(cols) + "\n")
+            np.savetxt(f, arr, fmt="%d", delimiter="\t")
+    tr = ck.train_pairs.copy(); tr[:, 1] -= U
+    va = ck.valid_pairs.copy(); va[:, 1] -= U
+    kg = ck.kg.copy(); kg[:, 0] -= U; kg[:, 2] -= U
+    dump("uv_train.pd", ["u", "v"], tr)
+    dump("uv_val.pd", ["u", "v"], va)
+    dump("uv_test.pd", ["u", "v"], va)
+    dump("kg_item.pd", ["h", "r", "t"], kg)
+    a = dataset.DataLoader("toy", data_dir=str(d))
+    b = dataset.DataLoader.from_synthetic("tiny")
+    assert (a.n_users, a.n_items, a.n_KG_entity, a.n_KG_relation) == (b.n_users, b.n_items, b.n_KG_entity, b.n_KG_relation)
+    assert (a.n_users, a.n_items, a.n_KG_entity, a.n_KG_relation) == (2000, 2000, 7000, 11)
+    assert np.array_equal(a.train_KG_triplet, b.train_KG_triplet) and a.train_KG_triplet.dtype == np.int32
+    assert np.array_equal(a.test_KG_triplet, b.test_KG_triplet)
+    assert a.n_train_KG_triplet == 80000 and a.n_test_KG_triplet == 80000 + 2 * a.n_valid
+    assert np.array_equal(a.item_id_range, np.arange(2000, 4000))
+    # triplet layout [KG ; (u, R, v) ; (v, R+1, u)], dataset.py:84-93,165-185
+    n = a.n_train
+    t = a.train_KG_triplet
+    assert np.array_equal(t[:40000], ck.kg)
+    assert np.all(t[40000:40000 + n, 1] == 9) and np.all(t[40000 + n:, 1] == 10)
+    assert np.array_equal(t[40000:40000 + n, [0, 2]], t[40000 + n:, [2, 0]])
+    # dicts hold raw item ids
+    u0 = next(iter(a.train_user_dict))
+    assert a.train_user_dict[u0].max() < a.n_items
+    assert sorted(a.train_valid_user_dict[u0].tolist()) == sorted(
+        a.train_user_dict[u0].tolist() + a.valid_user_dict.get(u0, np.zeros(0, int)).tolist())
+    assert a.train_g is a.train_g and a.train_g.n_edges == 80000 and a.test_g.n_edges == a.n_test_KG_triplet
+
+
+def test_samplers_semantics():
+    dl = dataset.DataLoader.from_synthetic("tiny")
+    t = dl.train_KG_triplet
+    edges = set(map(tuple, t[:, [2, 0, 1]].tolist()))
+    seen = 0
+    for h, r, pos_t, neg_t, fn in dl.KG_sampler(batch_size=30000):
+        seen += len(h)
+        # "h" is the graph source (= KG tail), "pos_t" the destination (= KG head): SURVEY Q11
+        assert all((int(a), int(b), int(c)) in edges for a, b, c in zip(h[:50], pos_t[:50], r[:50]))
+        assert neg_t.min() >= 0 and neg_t.max() < dl.n_KG_entity
+        chk = [(int(a), int(b), int(c)) in edges for a, b, c in zip(h[:200], neg_t[:200], r[:200])]
+        assert chk == [bool(x) for x in fn[:200]]
+    assert seen == dl.n_train_KG_triplet                      # one shuffled pass over all edges
+    tot = 0
+    for users, pos, neg, fn in dl.CF_pair_sampler(batch_size=10240):
+        tot += len(users)
+        assert len(users) <= 10240 and neg.max() < dl.n_users + dl.n_items
+    assert tot == 2 * dl.n_train
+
+
+def test_metric_helpers_and_plan(golden_g3, golden_eval, golden_small):
+    for r, want in zip(golden_g3["hit_vectors"], golden_g3["ndcg"]):
+        assert abs(metric.one_ndcg_at_k(r.tolist(), 20) - want) < 1e-12
+    for r, want in zip(golden_g3["hit_vectors"], golden_g3["dcg"]):
+        assert abs(metric.one_dcg_at_k(r.tolist(), 20) - want) < 1e-12
+    for r, want in zip(golden_g3["hit_vectors"], golden_g3["recall7"]):
+        assert abs(metric.one_recall_at_k(r.tolist(), 20, 7) - want) < 1e-12
+    # metrics_from_topk on the reference's own top-20 lists reproduces its recall / ndcg
+    e = golden_eval
+    users = e["users"]
+    tr = {int(u): e["train_items"][e["train_ptr"][j]: e["train_ptr"][j + 1]] for j, u in enumerate(users)}
+    te = {int(u): e["test_items"][e["test_ptr"][j]: e["test_ptr"][j + 1]] for j, u in enumerate(users)}
+    plan = metric.EvalPlan(tr, te, int(golden_small["n_items"]))
+    top = np.argsort(-e["masked_scores"], axis=1, kind="stable")[:, :20]
+    rec, ndcg, _ = metric.metrics_from_topk(top, plan, 20)
+    assert abs(rec - float(e["recall"])) < 1e-12 and abs(ndcg - float(e["ndcg"])) < 1e-12
+    assert plan.mask_ptr[-1] == plan.mask_items.size and np.all(np.diff(plan.mask_ptr) >= 0)
+
+
+def test_synth_shapes():
+    for name, (N, E, R) in {"tiny": (7000, 80000, 11)}.items():
+        ck = synth.synth_ckg(name)
+        assert (ck.cfg.n_nodes, ck.triplets.shape[0], ck.cfg.n_relations) == (N, E, R)
+        assert np.unique(ck.triplets[:, [0, 2]]).size == N and np.unique(ck.triplets[:, 1]).size == R
+    c = synth.CONFIGS["amazon-book"]
+    assert (c.n_nodes, c.n_edges, c.n_relations) == (159251, 3663302, 41)
+    c = synth.CONFIGS["last-fm"]
+    assert (c.n_nodes, c.n_edges, c.n_relations) == (81832, 4834673, 11)
+    c = synth.CONFIGS["yelp2018"]
+    assert (c.n_nodes, c.n_edges, c.n_relations) == (136880, 3492324, 44)
+    c = synth.CONFIGS["amazon-book-10x"]
+    assert (c.n_nodes, c.n_edges, c.n_relations) == (1706790, 36633020, 41)
