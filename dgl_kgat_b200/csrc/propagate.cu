@@ -333,16 +333,20 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
     }
 }
 
-// dW2[idx] = sum_p partials[p][idx], fixed order; 8 threads per element, combined by shuffle
+// dW2[idx] = sum_p partials[p][idx], fixed order, accumulated in fp64 (the per-CTA partials are
+// fp32 sums over a few hundred rows; the cross-CTA sum must not add its own rounding on top);
+// 8 threads per element, combined by shuffle
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int n_elem, float* __restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int idx = t >> 3, part = t & 7;
-    float s = 0.f;
+    double s = 0.0;
     if (idx < n_elem)
-        for (int p = part; p < n_partials; p += 8) s += __ldg(partials + static_cast<size_t>(p) * n_elem + idx);
-    s = group_sum<8>(s);
-    if (idx < n_elem && part == 0) out[idx] = s;
+        for (int p = part; p < n_partials; p += 8)
+            s += static_cast<double>(__ldg(partials + static_cast<size_t>(p) * n_elem + idx));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
+    if (idx < n_elem && part == 0) out[idx] = static_cast<float>(s);
 }
 
 // d_entity[v] = d_concat[v, in_off:+D] + dx_direct[v] + sum_{k in CSC row v} w[k] * dh_nb[dst[k]]

@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Turn the ncu artefacts that profiles/capture.sh leaves in gpurun_out/ into the tracked summaries:
+
+    python profiles/summarize.py r1      ->  profiles/launches_r1.md, profiles/counters_r1.md
+
+launches: per-kernel launch count, total device time and SHARE of the profiled run (per-launch
+times are cold-cache and serialised; only shares are comparable with bench.py).
+counters: one row per profiled launch of our kernels from the `--set full` capture.
+"""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+src = os.path.join(ROOT, "gpurun_out")
+out = os.path.join(ROOT, "profiles")
+
+
+def short(name):
+    name = re.sub(r"\(.*", "", name)
+    name = name.replace("void ", "").replace("kgat::<unnamed>::", "kgat::").replace("at::native::", "at::")
+    return name[:90]
+
+
+rows = list(csv.reader(open(os.path.join(src, "launches_%s.csv" % tag))))
+hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+hdr, data = rows[hi], rows[hi + 1:]
+ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+agg = collections.OrderedDict()
+for r in data:
+    if len(r) <= vi:
+        continue
+    v = float(r[vi].replace(",", ""))
+    v = {"ns": v / 1e3, "us": v, "usecond": v, "ms": v * 1e3, "msecond": v * 1e3, "nsecond": v / 1e3}.get(r[ui], v)
+    a = agg.setdefault(short(r[ki]), [0, 0.0])
+    a[0] += 1
+    a[1] += v
+tot = sum(v[1] for v in agg.values())
+ours = sum(v[1] for k, v in agg.items() if k.startswith("kgat::"))
+with open(os.path.join(out, "launches_%s.md" % tag), "w") as f:
+    f.write("# ncu launch list, round %s\n\n" % tag)
+    f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv python bench.py "
+            "--steps 2 --warmup 1 --no-cpu-baseline` (profiles/capture.sh).\n")
+    f.write("Covers graph build, 3 value steps, 3 e2e steps and the eval kernel. %d launches, %.1f us total, "
+            "%.1f%% of the time in kgat:: kernels.\n\n" % (len(data), tot, 100 * ours / tot))
+    f.write("| kernel | launches | total us | us / launch | share |\n|---|---:|---:|---:|---:|\n")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+        f.write("| `%s` | %d | %.1f | %.1f | %.1f%% |\n" % (k, v[0], v[1], v[1] / v[0], 100 * v[1] / tot))
+
+rep = os.path.join(src, "prof_%s.ncu-rep" % tag)
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    cols = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"),
+            ("dram__bytes_write.sum", "dram wr"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+            ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
+            ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
+            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
+            ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
+            ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
+            ("launch__occupancy_limit_registers", "occ lim regs"), ("launch__occupancy_limit_shared_mem", "occ lim smem")]
+    idx = [(hdr.index(c) if c in hdr else None, t) for c, t in cols]
+    with open(os.path.join(out, "counters_%s.md" % tag), "w") as f:
+        f.write("# ncu --set full counters, round %s\n\nOne row per profiled launch (`ncu --set full --clock-control "
+                "none --import-source on`, profiles/capture.sh).\n\n" % tag)
+        f.write("| " + " | ".join(t for _, t in idx) + " |\n|" + "---|" * len(idx) + "\n")
+        for r in data:
+            cells = []
+            for i, t in idx:
+                if i is None:
+                    cells.append("n/a")
+                elif t == "kernel":
+                    cells.append("`%s`" % short(r[i]))
+                else:
+                    cells.append((r[i] + " " + units[i]).strip())
+            f.write("| " + " | ".join(cells) + " |\n")
+print("wrote", [p for p in os.listdir(out) if tag in p])
