@@ -47,6 +47,9 @@ SIGNATURES = {
                                  c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "kgat_input_bwd": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p,
                                  C.c_int, c_f32p, C.c_void_p]),
+    "kgat_umma_error_flag": (C.c_int, []),
+    "kgat_selftest_umma": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p]),
     "kgat_score_topk": (C.c_int, [c_f32p, C.c_int64, C.c_int, c_i32p, C.c_int64, c_i32p, C.c_int64, c_i32p, c_i32p,
                                   C.c_int, c_i32p, c_f32p, C.c_void_p]),
 }

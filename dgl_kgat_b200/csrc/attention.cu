@@ -244,6 +244,22 @@ __global__ void gather_weights_kernel(const float* __restrict__ w_eid, const int
 
 using namespace kgat;
 
+#include <cstdlib>
+#include <cstring>
+
+int kgat_launch_att_logits_umma(const kgat_graph_t* g, const float* entity, const float* rel_emb, const float* W_R,
+                                float* logits_csr, int variant, cudaStream_t st);
+
+// KGAT_ATT_IMPL=ffma selects the fp32 FFMA tile kernel instead of the tcgen05 3xTF32 kernel (A/B runs).
+static bool use_umma() {
+    const char* e = std::getenv("KGAT_ATT_IMPL");
+    return !(e && std::strcmp(e, "ffma") == 0);
+}
+static int umma_variant() {
+    const char* e = std::getenv("KGAT_UMMA_VARIANT");
+    return (e && e[0] == '1') ? 1 : 0;
+}
+
 extern "C" int kgat_attention_logits(const kgat_graph_t* g, const float* entity, const float* rel_emb,
                                      const float* W_R, int d, int rd, float* logits_csr,
                                      kgat_stream_t stream) {
@@ -253,7 +269,9 @@ extern "C" int kgat_attention_logits(const kgat_graph_t* g, const float* entity,
     if (g->n_edges == 0) return KGAT_OK;
     cudaStream_t st = as_stream(stream);
     const int64_t E = g->n_edges;
-    if (d == 64 && rd == 64) {
+    if (d == 64 && rd == 64 && g->n_rel <= 1024 && use_umma()) {
+        return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, umma_variant(), st);
+    } else if (d == 64 && rd == 64) {
         using S = AttSmem<64, 64>;
         static bool configured = false;
         if (!configured) {

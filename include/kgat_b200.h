@@ -97,7 +97,9 @@ KGAT_API int    kgat_graph_build(const kgat_graph_t* g, const int32_t* head, con
 /* (2) TransR attention logits pi(h,r,t) = (e_t W_r) . tanh(e_h W_r + e_r) for every
  *     edge, relation-grouped -- replaces the loop of apply_edges(_att_score)
  *     (models.py:135-152).  entity [n_nodes,d], rel_emb [n_rel,rd], W_R [n_rel,d,rd].
- *     logits_csr[c] is the logit of the edge at CSR position c. */
+ *     logits_csr[c] is the logit of the edge at CSR position c.
+ *     d = rd = 64 runs on the tensor cores (tcgen05, 3xTF32, fp32 accumulate in TMEM); other widths use
+ *     fp32 FFMA kernels.  Environment: KGAT_ATT_IMPL=ffma forces the FFMA kernel (A/B measurements). */
 KGAT_API int kgat_attention_logits(const kgat_graph_t* g, const float* entity, const float* rel_emb,
                           const float* W_R, int d, int rd, float* logits_csr,
                           kgat_stream_t stream);
@@ -172,6 +174,15 @@ KGAT_API int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
                     const int32_t* item_ids, int64_t n_items,
                     const int32_t* mask_ptr, const int32_t* mask_items,
                     int K, int32_t* topk_idx, float* topk_score, kgat_stream_t stream);
+
+/* Hardware self-test of the tcgen05 path (diagnostics; not on the hot path):
+ * C[128,N] = A[128,K] * B[N,K]^T on one CTA, mode 0 = one TF32 pass, mode 1 = 3xTF32.
+ * *err_flag (device int) is set to 1 if the tensor-core completion barrier never fires. */
+/* 1 if a tensor-core completion barrier ever timed out since the last call (then cleared); 0 otherwise.
+ * Synchronises the device. */
+KGAT_API int kgat_umma_error_flag(void);
+KGAT_API int kgat_selftest_umma(const float* A, const float* B, float* C, int N, int K, int variant, int mode,
+                       int* err_flag, kgat_stream_t stream);
 
 #ifdef __cplusplus
 }
