@@ -248,16 +248,12 @@ using namespace kgat;
 #include <cstring>
 
 int kgat_launch_att_logits_umma(const kgat_graph_t* g, const float* entity, const float* rel_emb, const float* W_R,
-                                float* logits_csr, int variant, cudaStream_t st);
+                                float* logits_csr, cudaStream_t st);
 
 // KGAT_ATT_IMPL=ffma selects the fp32 FFMA tile kernel instead of the tcgen05 3xTF32 kernel (A/B runs).
 static bool use_umma() {
     const char* e = std::getenv("KGAT_ATT_IMPL");
     return !(e && std::strcmp(e, "ffma") == 0);
-}
-static int umma_variant() {
-    const char* e = std::getenv("KGAT_UMMA_VARIANT");
-    return (e && e[0] == '1') ? 1 : 0;
 }
 
 extern "C" int kgat_attention_logits(const kgat_graph_t* g, const float* entity, const float* rel_emb,
@@ -270,7 +266,7 @@ extern "C" int kgat_attention_logits(const kgat_graph_t* g, const float* entity,
     cudaStream_t st = as_stream(stream);
     const int64_t E = g->n_edges;
     if (d == 64 && rd == 64 && g->n_rel <= 1024 && use_umma()) {
-        return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, umma_variant(), st);
+        return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, st);
     } else if (d == 64 && rd == 64) {
         using S = AttSmem<64, 64>;
         static bool configured = false;

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int32_t* __restrict__ bk_head,
                        const int32_t* __restrict__ bk_tail, const int32_t* __restrict__ bk_pos,
                        const float* __restrict__ ent, const float* __restrict__ rel_emb,
-                       const float* __restrict__ W_R, float* __restrict__ logits_csr, int variant,
+                       const float* __restrict__ W_R, float* __restrict__ logits_csr,
                        int* __restrict__ err) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -97,9 +97,7 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
 
     // gather mapping: a warp instruction covers 8 rows x 4 consecutive 16-byte chunks
     const int r8 = lane & 7, cq = lane >> 3;
-    const uint32_t k_stride = umma::LBO_BYTES;
-    const uint32_t lbo = variant == 0 ? k_stride : SBO;
-    const uint32_t sbo = variant == 0 ? SBO : k_stride;
+    const uint32_t lbo = umma::LBO_BYTES, sbo = SBO;
     const uint32_t idesc128 = umma::make_idesc_tf32(TILE, 128), idesc64 = umma::make_idesc_tf32(TILE, 64);
 
     int rel = 0;
@@ -250,7 +248,7 @@ extern "C" int kgat_umma_error_flag(void) {
 
 // Launcher used by kgat_attention_logits for d = rd = 64 (declared in attention.cu).
 int kgat_launch_att_logits_umma(const kgat_graph_t* g, const float* entity, const float* rel_emb, const float* W_R,
-                                float* logits_csr, int variant, cudaStream_t st) {
+                                float* logits_csr, cudaStream_t st) {
     int* err_flag = nullptr;
     KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&err_flag), g_umma_error));
     static bool configured = false;
@@ -263,7 +261,7 @@ int kgat_launch_att_logits_umma(const kgat_graph_t* g, const float* entity, cons
     const int grid = static_cast<int>(max_tiles < num_sms() ? max_tiles : num_sms());
     att_logits_umma_kernel<<<grid, THREADS, sizeof(Smem), st>>>(
         g->rel_ptr, static_cast<int>(g->n_rel), g->bk_head, g->bk_tail, g->bk_pos, entity, rel_emb, W_R, logits_csr,
-        variant, err_flag);
+        err_flag);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }

@@ -53,7 +53,7 @@ def test_umma_selftest_variants(dev):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(report, open(os.path.join(ROOT, "gpurun_out", "umma_selftest.json"), "w"), indent=1)
     print(json.dumps(report, indent=1))
-    assert 0 in good, "descriptor variant 0 (documented LBO/SBO meaning) does not reproduce the GEMM: %r" % report
+    assert good == [0], "descriptor variant 0 (documented LBO/SBO meaning) does not reproduce the GEMM: %r" % report
     # one TF32 pass is NOT good enough for the 1e-5 bar; 3xTF32 is
     assert report["v0_m0_N128_K64"]["rel"] > 1e-5 > report["v0_m1_N128_K64"]["rel"]
 
