@@ -4,18 +4,23 @@
 //   pi(h,r,t) = (e_t W_r) . tanh(e_h W_r + e_r)                        (reference models.py:135-144)
 //
 // One persistent CTA per SM walks a contiguous range of 128-edge tiles of the relation buckets.
-// Per tile:
-//   gather   the 128 tail rows and 128 head rows of the entity table (128-bit loads, 8 rows x 64 B per
-//            warp instruction), split every value x = hi + lo (hi = RN-TF32(x), lo exact) and store
-//            both halves in shared memory in the K-major no-swizzle core-matrix layout (umma.cuh);
-//   MMA      A = gathered rows (M = 128 edges, K = 64), B = [W_hi | W_lo] (N = 128, staged once per
-//            relation): T_hi x [W_hi|W_lo] (N=128) and T_lo x W_hi (N=64) accumulate hi*hi + lo*hi in
-//            TMEM columns 0..63 and hi*lo in columns 64..127; same for the head rows.  fp32
-//            accumulation in TMEM; 32 tcgen05.mma per tile issued by one thread;
-//   epilogue (overlaps the next tile's MMAs, TMEM double-buffered) tcgen05.ld, t = c[0:64]+c[64:128],
-//            logit = sum_c t_r[c] * tanh(h_r[c] + e_r[c]), scattered to the edge's CSR position.
+// Warp-specialised, three roles connected by mbarriers:
+//   producers (warps 0-3)  gather the 128 tail rows and 128 head rows of the tile from the entity table
+//            (128-bit loads, a warp instruction covers 8 rows x 64 B), split every value x = hi + lo
+//            (hi = RN-TF32(x), lo exact) and store both halves in shared memory in the K-major
+//            no-swizzle core-matrix layout (umma.cuh).  A stage holds one K-half (32 of the 64 input
+//            features) of a tile: 4 arrays x 16 KB; two stages ring.  Loads for the next stage are in
+//            flight while the current one is split and stored.  W_r is staged as B = [W_hi | W_lo]
+//            (N = 128) once per relation.
+//   MMA      (warp 8, one lane) per stage: T_hi x [W_hi|W_lo] (N=128), T_lo x W_hi (N=64) and the same
+//            for the head rows -> hi*hi + lo*hi in TMEM columns 0..63, hi*lo in 64..127; fp32
+//            accumulation in TMEM, two accumulator buffers (2 x 256 columns).  tcgen05.commit releases
+//            the shared-memory stage and, after the second K-half, publishes the accumulator.
+//   epilogue (warps 4-7, one TMEM lane quarter each) tcgen05.ld, t = c[0:64] + c[64:128],
+//            logit = sum_c t_r[c] * tanh(h_r[c] + e_r[c]), scattered to the edge's CSR position; runs
+//            while the tensor core works on the next tile.
 // Neither projection ever exists in HBM.  3xTF32 keeps the result inside the 1e-5 relative bar
-// (a single TF32 pass is ~5e-4).
+// (a single TF32 pass is ~4e-4).
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -23,34 +28,46 @@ namespace kgat {
 namespace {
 
 constexpr int TILE = 128;
-constexpr int D = 64;            // entity and relation width of this specialisation
-constexpr int THREADS = 256;
+constexpr int D = 64;                 // entity and relation width of this specialisation
+constexpr int KH = 32;                // K-half held by one stage
+constexpr int N_PROD = 128;           // producer threads (warps 0-3)
+constexpr int N_EPI = 128;            // epilogue threads (warps 4-7)
+constexpr int THREADS = N_PROD + N_EPI + 32;
+constexpr int MMA_WARP = 8;
 constexpr int MAX_REL = 1024;
-constexpr uint32_t A_BYTES = TILE * D * 4;          // 32 KB per operand array
-constexpr uint32_t SBO = (D / 4) * 128;             // 8-row group stride for kt = 64
-constexpr uint32_t TMEM_COLS = 512;                 // 2 buffers x (T: 128 + H: 128)
+constexpr uint32_t ARR_BYTES = TILE * KH * 4;        // 16 KB: one operand array of one stage
+constexpr uint32_t STAGE_BYTES = 4 * ARR_BYTES;      // T_hi, T_lo, H_hi, H_lo
+constexpr uint32_t SBO_A = (KH / 4) * 128;           // 8-row group stride inside a stage array
+constexpr uint32_t SBO_B = (D / 4) * 128;            // ... inside the W tile (full K)
+constexpr uint32_t TMEM_COLS = 512;                  // 2 buffers x (T: 128 + H: 128)
 
 struct Smem {
-    unsigned char B[2 * 64 * D * 4];                // rows 0..63: W_hi^T, rows 64..127: W_lo^T
-    unsigned char A[4][A_BYTES];                    // T_hi, T_lo, H_hi, H_lo
+    unsigned char B[2 * 64 * D * 4];                 // rows 0..63: W_hi^T, rows 64..127: W_lo^T
+    unsigned char A[2][STAGE_BYTES];
     float er[2][D];
-    float part[TILE];
-    int tail[TILE], head[TILE];
-    int pos[2][TILE];
     int prefix[MAX_REL + 1];
-    uint64_t mma_bar[2];
+    uint64_t full[2], empty[2], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
-    int cur_rel_loaded;
+    volatile int abort_flag;                         // a bounded barrier wait timed out somewhere
+    volatile int epi_abort;                          // the epilogue group's agreed view of it
 };
 
-// tanh to ~3e-7 absolute: odd polynomial below 0.1, 1 - 2 / (1 + exp(2|x|)) above
+// tanh with ~1e-7 ABSOLUTE error (what the logit needs): 1 - 2 / (1 + exp(2|x|)), sign restored
 __device__ __forceinline__ float tanh_fast(float x) {
-    const float ax = fabsf(x);
-    const float x2 = x * x;
-    const float poly = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.05396825f, 0.13333334f), -0.33333334f), 1.0f);
-    const float e = __expf(2.0f * ax);
-    const float big = copysignf(1.0f - __fdividef(2.0f, 1.0f + e), x);
-    return ax < 0.1f ? poly : big;
+    const float e = __expf(2.0f * fabsf(x));
+    return copysignf(1.0f - __fdividef(2.0f, 1.0f + e), x);
+}
+
+struct TileInfo { int rel, e0, n_e; };
+
+__device__ __forceinline__ TileInfo tile_info(const int* prefix, const int32_t* __restrict__ rel_ptr, int tile,
+                                              int& rel) {
+    while (tile >= prefix[rel + 1]) ++rel;
+    TileInfo t;
+    t.rel = rel;
+    t.e0 = __ldg(rel_ptr + rel) + (tile - prefix[rel]) * TILE;
+    t.n_e = min(TILE, __ldg(rel_ptr + rel + 1) - t.e0);
+    return t;
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -80,12 +97,17 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
         }
         if (lane == 0) s.prefix[0] = 0;
     }
-    if (warp == 1) umma::tmem_alloc(&s.tmem_base, TMEM_COLS);
-    if (tid == 64) {
-        umma::mbar_init(&s.mma_bar[0], 1);
-        umma::mbar_init(&s.mma_bar[1], 1);
+    if (warp == MMA_WARP) umma::tmem_alloc(&s.tmem_base, TMEM_COLS);
+    if (tid == 32) {
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&s.full[i], N_PROD);
+            umma::mbar_init(&s.empty[i], 1);
+            umma::mbar_init(&s.acc_full[i], 1);
+            umma::mbar_init(&s.acc_empty[i], N_EPI);
+        }
         umma::fence_barrier_init();
-        s.cur_rel_loaded = -1;
+        s.abort_flag = 0;
+        s.epi_abort = 0;
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -95,147 +117,169 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
     const int t0 = static_cast<int>(static_cast<long long>(n_tiles) * blockIdx.x / gridDim.x);
     const int t1 = static_cast<int>(static_cast<long long>(n_tiles) * (blockIdx.x + 1) / gridDim.x);
 
-    // gather mapping: a warp instruction covers 8 rows x 4 consecutive 16-byte chunks
-    const int r8 = lane & 7, cq = lane >> 3;
-    const uint32_t lbo = umma::LBO_BYTES, sbo = SBO;
-    const uint32_t idesc128 = umma::make_idesc_tf32(TILE, 128), idesc64 = umma::make_idesc_tf32(TILE, 64);
+    if (warp < 4) {
+        // =========================================================== producers
+        const int r8 = lane & 7, cq = lane >> 3;
+        // this thread's 16 (row, 16-byte chunk) slots of a stage: slot j -> row group rg (0..15 tail rows,
+        // 16..31 head rows), chunk group cg (0..1); row = (rg & 15)*8 + r8, chunk = cg*4 + cq (of the K-half)
+        int ids[16];            // node id of slot j's row for the tile being loaded (-1: padding row)
+        float4 va[16], vb[16];  // in-flight gathers: K-half 0 / K-half 1
+        int rel = 0, loaded_rel = -1;
 
-    int rel = 0;
-    int prev_ne = 0;
-    bool failed = false;
-
-    // epilogue of the tile whose accumulators sit in TMEM buffer `buf`
-    auto epilogue = [&](int buf, int n_e) {
-        const int q = warp & 3, half = warp >> 2;
-        const int row = q * 32 + lane, c0 = half * 32;
-        const uint32_t ta = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
-        float a[32], b[32], t[32];
-        umma::tmem_ld32(ta + c0, a);
-        umma::tmem_ld32(ta + 64 + c0, b);
+        auto load_ids = [&](const TileInfo& t) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) t[i] = a[i] + b[i];
-        umma::tmem_ld32(ta + 128 + c0, a);
-        umma::tmem_ld32(ta + 192 + c0, b);
-        float p = 0.f;
+            for (int j = 0; j < 16; ++j) {
+                const int rg = (warp * 16 + j) >> 1;
+                const int rl = (rg & 15) * 8 + r8;
+                ids[j] = rl < t.n_e ? __ldg((rg < 16 ? bk_tail : bk_head) + t.e0 + rl) : -1;
+            }
+        };
+        auto issue = [&](float4* v, int h) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) p = fmaf(t[i], tanh_fast(a[i] + b[i] + s.er[buf][c0 + i]), p);
-        if (half == 1) s.part[row] = p;
-        umma::fence_before_sync();
-        __syncthreads();
-        if (half == 0 && row < n_e) logits_csr[s.pos[buf][row]] = p + s.part[row];
-    };
+            for (int j = 0; j < 16; ++j) {
+                const int cg = (warp * 16 + j) & 1;
+                v[j] = ids[j] >= 0 ? ldg4(ent + static_cast<size_t>(ids[j]) * D + h * KH + (cg * 4 + cq) * 4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto store = [&](const float4* v, int stage) {
+            unsigned char* base = s.A[stage];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int combo = warp * 16 + j, rg = combo >> 1, cg = combo & 1;
+                const int rl = (rg & 15) * 8 + r8;
+                const uint32_t off =
+                    (rg < 16 ? 0u : 2u * ARR_BYTES) + (rl >> 3) * SBO_A + (cg * 4 + cq) * 128 + r8 * 16;
+                float4 hi, lo;
+                umma::split_tf32(v[j].x, hi.x, lo.x);
+                umma::split_tf32(v[j].y, hi.y, lo.y);
+                umma::split_tf32(v[j].z, hi.z, lo.z);
+                umma::split_tf32(v[j].w, hi.w, lo.w);
+                *reinterpret_cast<float4*>(base + off) = hi;
+                *reinterpret_cast<float4*>(base + ARR_BYTES + off) = lo;
+            }
+        };
 
-    for (int tile = t0; tile < t1; ++tile) {
-        const int it = tile - t0, buf = it & 1;
-        while (tile >= s.prefix[rel + 1]) ++rel;                       // uniform across the CTA
-        const int e0 = __ldg(rel_ptr + rel) + (tile - s.prefix[rel]) * TILE;
-        const int n_e = min(TILE, __ldg(rel_ptr + rel + 1) - e0);
-
-        // (a) edge ids of this tile
-        if (tid < TILE) {
-            const bool ok = tid < n_e;
-            s.tail[tid] = ok ? __ldg(bk_tail + e0 + tid) : -1;
-            s.head[tid] = ok ? __ldg(bk_head + e0 + tid) : -1;
-            s.pos[buf][tid] = ok ? __ldg(bk_pos + e0 + tid) : -1;
+        if (t0 < t1) {
+            TileInfo cur = tile_info(s.prefix, rel_ptr, t0, rel);
+            load_ids(cur);
+            issue(va, 0);
+            for (int tile = t0; tile < t1 && !s.abort_flag; ++tile) {
+                const int it = tile - t0;
+                issue(vb, 1);                                        // K-half 1 of this tile
+                // ---- stage 0 <- K-half 0
+                if (!umma::mbar_wait(&s.empty[0], (it & 1) ^ 1)) s.abort_flag = 1;
+                if (loaded_rel != cur.rel) {
+                    // W_r changes: every MMA issued so far must be done reading B (they complete in order)
+                    if (it > 0 && !umma::mbar_wait(&s.empty[1], (it - 1) & 1)) s.abort_flag = 1;
+                    const float* Wg = W_R + static_cast<size_t>(cur.rel) * D * D;
+                    for (int idx = tid; idx < D * D; idx += N_PROD) {
+                        const int k = idx >> 6, n = idx & 63;
+                        float hi, lo;
+                        umma::split_tf32(__ldg(Wg + idx), hi, lo);
+                        *reinterpret_cast<float*>(s.B + umma::tile_offset(n, k, D)) = hi;
+                        *reinterpret_cast<float*>(s.B + umma::tile_offset(64 + n, k, D)) = lo;
+                    }
+                    loaded_rel = cur.rel;
+                }
+                store(va, 0);
+                umma::fence_proxy_async();
+                umma::mbar_arrive(&s.full[0]);
+                // ---- prefetch the next tile's ids and its K-half 0 (vb of this tile is already in flight)
+                TileInfo nxt = cur;
+                if (tile + 1 < t1) {
+                    nxt = tile_info(s.prefix, rel_ptr, tile + 1, rel);
+                    load_ids(nxt);
+                    issue(va, 0);
+                }
+                // ---- stage 1 <- K-half 1
+                if (!umma::mbar_wait(&s.empty[1], (it & 1) ^ 1)) s.abort_flag = 1;
+                store(vb, 1);
+                umma::fence_proxy_async();
+                umma::mbar_arrive(&s.full[1]);
+                cur = nxt;
+            }
         }
-        __syncthreads();
-
-        // (b) issue the row gather into registers: 16 x 128-bit loads in flight per thread
-        float4 v[16];
+    } else if (warp == MMA_WARP) {
+        // =========================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc128 = umma::make_idesc_tf32(TILE, 128), idesc64 = umma::make_idesc_tf32(TILE, 64);
+            const uint32_t bW = umma::smem_u32(s.B);
+            for (int tile = t0; tile < t1 && !s.abort_flag; ++tile) {
+                const int it = tile - t0, buf = it & 1;
+                if (!umma::mbar_wait(&s.acc_empty[buf], ((it >> 1) & 1) ^ 1)) s.abort_flag = 1;
+                umma::fence_after_sync();
+                const uint32_t tT = tmem + buf * 256, tH = tT + 128;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int combo = warp * 16 + j;
-            const int rg = combo >> 2, cg = combo & 3;                 // row group 0..31 (16.. = head rows)
-            const int rl = (rg & 15) * 8 + r8;
-            const int id = rg < 16 ? s.tail[rl] : s.head[rl];
-            v[j] = id >= 0 ? ldg4(ent + static_cast<size_t>(id) * D + (cg * 4 + cq) * 4)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int h = 0; h < 2; ++h) {
+                    if (!umma::mbar_wait(&s.full[h], it & 1)) s.abort_flag = 1;
+                    umma::fence_after_sync();
+                    const uint32_t aT = umma::smem_u32(s.A[h]), aH = aT + 2 * ARR_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < KH / 8; ++ks) {
+                        const uint32_t off = ks * 2 * umma::CORE_BYTES;
+                        const uint64_t dB =
+                            umma::make_smem_desc(bW + h * (KH / 4) * 128 + off, umma::LBO_BYTES, SBO_B);
+                        const uint32_t acc = (h | ks) != 0;
+                        umma::mma_tf32(tT, umma::make_smem_desc(aT + off, umma::LBO_BYTES, SBO_A), dB, idesc128, acc);
+                        umma::mma_tf32(tT, umma::make_smem_desc(aT + ARR_BYTES + off, umma::LBO_BYTES, SBO_A), dB,
+                                       idesc64, 1);
+                        umma::mma_tf32(tH, umma::make_smem_desc(aH + off, umma::LBO_BYTES, SBO_A), dB, idesc128, acc);
+                        umma::mma_tf32(tH, umma::make_smem_desc(aH + ARR_BYTES + off, umma::LBO_BYTES, SBO_A), dB,
+                                       idesc64, 1);
+                    }
+                    umma::mma_commit(&s.empty[h]);                   // stage h may be refilled once these finish
+                }
+                umma::mma_commit(&s.acc_full[buf]);                  // accumulator of this tile is complete
+            }
         }
-
-        // (c) the previous tile's MMAs must have finished reading shared memory
-        if (it > 0) {
-            const bool ok = umma::mbar_wait(&s.mma_bar[buf ^ 1], ((it - 1) >> 1) & 1);
-            failed = __syncthreads_or(!ok) != 0;          // CTA-uniform: a timeout aborts the whole CTA
+    } else {
+        // =========================================================== epilogue (warps 4..7)
+        const int q = warp & 3;                                       // TMEM lane quarter of this warp
+        const int row = q * 32 + lane;
+        const int et = tid - N_PROD;                                  // 0..127
+        int rel = 0;
+        for (int tile = t0; tile < t1; ++tile) {
+            const int it = tile - t0, buf = it & 1;
+            const TileInfo t = tile_info(s.prefix, rel_ptr, tile, rel);
+            if (et < D) s.er[buf][et] = __ldg(rel_emb + static_cast<size_t>(t.rel) * D + et);
+            const int pos = row < t.n_e ? __ldg(bk_pos + t.e0 + row) : -1;
+            if (!umma::mbar_wait(&s.acc_full[buf], (it >> 1) & 1)) { s.abort_flag = 1; s.epi_abort = 1; }
+            if (et == 0 && s.abort_flag) s.epi_abort = 1;
             umma::fence_after_sync();
-            if (failed) break;
-        }
-
-        // (d) restage W_r / e_r when the relation changes
-        if (s.cur_rel_loaded != rel) {
-            const float* Wg = W_R + static_cast<size_t>(rel) * D * D;
-            for (int idx = tid; idx < D * D; idx += THREADS) {
-                const int k = idx >> 6, n = idx & 63;
-                float hi, lo;
-                umma::split_tf32(__ldg(Wg + idx), hi, lo);
-                *reinterpret_cast<float*>(s.B + umma::tile_offset(n, k, D)) = hi;
-                *reinterpret_cast<float*>(s.B + umma::tile_offset(64 + n, k, D)) = lo;
-            }
-        }
-        if (tid < D) s.er[buf][tid] = __ldg(rel_emb + static_cast<size_t>(rel) * D + tid);
-
-        // (e) split and store the gathered rows
+            asm volatile("bar.sync 1, %0;" ::"n"(N_EPI) : "memory");  // er[buf] visible, abort view agreed
+            if (s.epi_abort) break;
+            const uint32_t ta = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
+            float p = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int combo = warp * 16 + j;
-            const int rg = combo >> 2, cg = combo & 3;
-            const int rl = (rg & 15) * 8 + r8;
-            const uint32_t off = (rl >> 3) * SBO + (cg * 4 + cq) * 128 + r8 * 16;
-            float4 hi, lo;
-            umma::split_tf32(v[j].x, hi.x, lo.x);
-            umma::split_tf32(v[j].y, hi.y, lo.y);
-            umma::split_tf32(v[j].z, hi.z, lo.z);
-            umma::split_tf32(v[j].w, hi.w, lo.w);
-            unsigned char* base = rg < 16 ? s.A[0] : s.A[2];
-            *reinterpret_cast<float4*>(base + off) = hi;
-            *reinterpret_cast<float4*>(base + A_BYTES + off) = lo;
-        }
-        umma::fence_proxy_async();
-        umma::fence_before_sync();
-        __syncthreads();
-        umma::fence_after_sync();
-        if (tid == 0) s.cur_rel_loaded = rel;
-
-        // (f) one thread issues the tile's 32 MMAs
-        if (tid == 0) {
-            const uint32_t tT = tmem + buf * 256, tH = tT + 128;
-            const uint32_t aT = umma::smem_u32(s.A[0]), aH = umma::smem_u32(s.A[2]), bW = umma::smem_u32(s.B);
+            for (int c0 = 0; c0 < D; c0 += 32) {
+                float a[32], b[32], tt[32];
+                umma::tmem_ld32(ta + c0, a);
+                umma::tmem_ld32(ta + 64 + c0, b);
 #pragma unroll
-            for (int ks = 0; ks < D / 8; ++ks) {
-                const uint32_t off = ks * 2 * umma::CORE_BYTES;
-                const uint64_t dB = umma::make_smem_desc(bW + off, lbo, sbo);
-                umma::mma_tf32(tT, umma::make_smem_desc(aT + off, lbo, sbo), dB, idesc128, ks > 0);
-                umma::mma_tf32(tT, umma::make_smem_desc(aT + A_BYTES + off, lbo, sbo), dB, idesc64, 1);
-                umma::mma_tf32(tH, umma::make_smem_desc(aH + off, lbo, sbo), dB, idesc128, ks > 0);
-                umma::mma_tf32(tH, umma::make_smem_desc(aH + A_BYTES + off, lbo, sbo), dB, idesc64, 1);
+                for (int i = 0; i < 32; ++i) tt[i] = a[i] + b[i];
+                umma::tmem_ld32(ta + 128 + c0, a);
+                umma::tmem_ld32(ta + 192 + c0, b);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) p = fmaf(tt[i], tanh_fast(a[i] + b[i] + s.er[buf][c0 + i]), p);
             }
-            umma::mma_commit(&s.mma_bar[buf]);
+            umma::fence_before_sync();
+            umma::mbar_arrive(&s.acc_empty[buf]);                     // TMEM buffer may be overwritten
+            if (pos >= 0) logits_csr[pos] = p;
         }
-
-        // (g) epilogue of the previous tile overlaps these MMAs
-        if (it > 0) epilogue(buf ^ 1, prev_ne);
-        prev_ne = n_e;
     }
 
-    // drain: last tile
-    if (t1 > t0 && !failed) {
-        const int it = t1 - t0 - 1, buf = it & 1;
-        const bool ok = umma::mbar_wait(&s.mma_bar[buf], (it >> 1) & 1);
-        failed = __syncthreads_or(!ok) != 0;
-        umma::fence_after_sync();
-        if (!failed) epilogue(buf, prev_ne);
-    }
-    if (failed && tid == 0) atomicExch(err, 1);
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tmem, TMEM_COLS);
+    if (tid == 0 && s.abort_flag) atomicExch(err, 1);
+    if (warp == MMA_WARP) umma::tmem_dealloc(tmem, TMEM_COLS);
 }
 
 }  // namespace
-}  // namespace kgat
 
-namespace kgat {
 __device__ int g_umma_error = 0;      // set when a tensor-core completion barrier timed out
-}
+
+}  // namespace kgat
 
 using namespace kgat;
 

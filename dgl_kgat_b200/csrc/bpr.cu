@@ -1,0 +1,228 @@
+// BPR loss head of the CF step, fused (reference models.py:170-178):
+//   loss = -mean(logsigmoid(<s,p> - <s,n>)) + lambda * (mean|s|^2/2 + mean|p|^2/2 + mean|n|^2/2)
+// with s, p, n = embedding[src], embedding[pos], embedding[neg].
+//
+// Forward: one warp per batch element gathers its three rows with 128-bit loads; a fixed-order
+// two-stage fp64 reduction produces the scalar.  Backward: the gradient touches at most 3B of the N
+// embedding rows, so instead of a dense (N, dim) tensor it is produced COMPACT: the 3B (node, slot)
+// pairs are radix-sorted by node, one warp per distinct node sums that node's contributions in slot
+// order (deterministic, no atomics) into rows[position of the segment head], and row_slot[node] points
+// there (-1 elsewhere).  kgat_layer_bwd / kgat_input_bwd read the gradient through row_slot.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace kgat {
+namespace {
+
+constexpr int BPR_THREADS = 256;
+constexpr int BPR_WARPS = BPR_THREADS / 32;
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+    return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+
+__global__ void __launch_bounds__(BPR_THREADS)
+bpr_fwd_kernel(const float* __restrict__ emb, int64_t stride, int dim, const int64_t* __restrict__ src,
+               const int64_t* __restrict__ pos, const int64_t* __restrict__ neg, int B,
+               float* __restrict__ sig, double* __restrict__ partial) {
+    __shared__ double s_cf[BPR_WARPS], s_reg[BPR_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * BPR_WARPS + warp;
+    double cf = 0.0, reg = 0.0;
+    if (b < B) {
+        const float* s = emb + src[b] * stride;
+        const float* p = emb + pos[b] * stride;
+        const float* n = emb + neg[b] * stride;
+        float sp = 0.f, sn = 0.f, ss = 0.f, pp = 0.f, nn = 0.f;
+        for (int c = lane * 4; c < dim; c += 128) {
+            const float4 a = ldg4(s + c), q = ldg4(p + c), r = ldg4(n + c);
+            sp += dot4(a, q); sn += dot4(a, r); ss += dot4(a, a); pp += dot4(q, q); nn += dot4(r, r);
+        }
+        sp = warp_sum(sp); sn = warp_sum(sn); ss = warp_sum(ss); pp = warp_sum(pp); nn = warp_sum(nn);
+        const float x = sp - sn;
+        // -logsigmoid(x) = -(min(x, 0) - log1p(exp(-|x|)))
+        cf = -static_cast<double>(fminf(x, 0.f) - log1pf(expf(-fabsf(x))));
+        reg = 0.5 * (static_cast<double>(ss) + static_cast<double>(pp) + static_cast<double>(nn));
+        if (lane == 0) sig[b] = 1.0f / (1.0f + expf(x));            // sigmoid(-x)
+    }
+    if (lane == 0) { s_cf[warp] = cf; s_reg[warp] = reg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, r = 0.0;
+        for (int w = 0; w < BPR_WARPS; ++w) { a += s_cf[w]; r += s_reg[w]; }
+        partial[2 * blockIdx.x] = a;
+        partial[2 * blockIdx.x + 1] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bpr_finish_kernel(const double* __restrict__ partial, int n_blocks, int B, float lambda, float* __restrict__ loss) {
+    __shared__ double s_a[256], s_r[256];
+    double a = 0.0, r = 0.0;
+    for (int i = threadIdx.x; i < n_blocks; i += 256) { a += partial[2 * i]; r += partial[2 * i + 1]; }
+    s_a[threadIdx.x] = a; s_r[threadIdx.x] = r;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s_a[threadIdx.x] += s_a[threadIdx.x + o]; s_r[threadIdx.x] += s_r[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = static_cast<float>(s_a[0] / B + static_cast<double>(lambda) * s_r[0] / B);
+}
+
+__global__ void bpr_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ pos,
+                                const int64_t* __restrict__ neg, int B, uint32_t* __restrict__ keys,
+                                int32_t* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * B) return;
+    const int role = i / B, b = i - role * B;
+    const int64_t id = role == 0 ? src[b] : (role == 1 ? pos[b] : neg[b]);
+    keys[i] = static_cast<uint32_t>(id);
+    vals[i] = i;
+}
+
+// one warp per sorted position that starts a segment of equal node ids
+__global__ void __launch_bounds__(BPR_THREADS)
+bpr_bwd_kernel(const float* __restrict__ emb, int64_t stride, int dim, const int64_t* __restrict__ src,
+               const int64_t* __restrict__ pos, const int64_t* __restrict__ neg, int B, float lambda,
+               const float* __restrict__ sig, const float* __restrict__ grad_loss,
+               const uint32_t* __restrict__ keys, const int32_t* __restrict__ slots,
+               float* __restrict__ rows, int64_t rows_stride, int32_t* __restrict__ row_slot,
+               int32_t* __restrict__ rows_node) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * BPR_WARPS + warp;
+    if (i >= 3 * B) return;
+    const uint32_t node = keys[i];
+    const bool head = i == 0 || keys[i - 1] != node;
+    if (!head) {
+        if (lane == 0) rows_node[i] = -1;
+        return;
+    }
+    const float scale = grad_loss[0] / static_cast<float>(B);
+    // dim <= 256: each lane owns up to two float4 column groups
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+    const int c0 = lane * 4, c1 = c0 + 128;
+    for (int j = i; j < 3 * B && keys[j] == node; ++j) {
+        const int slot = slots[j];
+        const int role = slot / B, b = slot - role * B;
+        const float sg = __ldg(sig + b);
+        const float* s = emb + src[b] * stride;
+        const float* p = emb + pos[b] * stride;
+        const float* n = emb + neg[b] * stride;
+        // d loss / d s = scale * (-sg * (p - n) + lambda * s);  d/dp = scale * (-sg * s + lambda * p);
+        // d/dn = scale * (sg * s + lambda * n)
+        auto contrib = [&](int c, float4& acc) {
+            if (c >= dim) return;
+            const float4 a = ldg4(s + c);
+            float4 g;
+            if (role == 0) {
+                const float4 q = ldg4(p + c), r = ldg4(n + c);
+                g = make_float4(fmaf(-sg, q.x - r.x, lambda * a.x), fmaf(-sg, q.y - r.y, lambda * a.y),
+                                fmaf(-sg, q.z - r.z, lambda * a.z), fmaf(-sg, q.w - r.w, lambda * a.w));
+            } else if (role == 1) {
+                const float4 q = ldg4(p + c);
+                g = make_float4(fmaf(-sg, a.x, lambda * q.x), fmaf(-sg, a.y, lambda * q.y),
+                                fmaf(-sg, a.z, lambda * q.z), fmaf(-sg, a.w, lambda * q.w));
+            } else {
+                const float4 r = ldg4(n + c);
+                g = make_float4(fmaf(sg, a.x, lambda * r.x), fmaf(sg, a.y, lambda * r.y),
+                                fmaf(sg, a.z, lambda * r.z), fmaf(sg, a.w, lambda * r.w));
+            }
+            acc.x = fmaf(scale, g.x, acc.x); acc.y = fmaf(scale, g.y, acc.y);
+            acc.z = fmaf(scale, g.z, acc.z); acc.w = fmaf(scale, g.w, acc.w);
+        };
+        contrib(c0, acc0);
+        contrib(c1, acc1);
+    }
+    float* out = rows + static_cast<int64_t>(i) * rows_stride;
+    if (c0 < dim) *reinterpret_cast<float4*>(out + c0) = acc0;
+    if (c1 < dim) *reinterpret_cast<float4*>(out + c1) = acc1;
+    if (lane == 0) {
+        row_slot[node] = i;
+        rows_node[i] = static_cast<int32_t>(node);
+    }
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct BwdWs { size_t keys_a, keys_b, vals_a, vals_b, cub, cub_bytes, total; };
+
+BwdWs plan_bwd(int B) {
+    BwdWs w{};
+    const size_t n = static_cast<size_t>(3) * (B > 0 ? B : 1);
+    size_t off = 0;
+    w.keys_a = off; off += align_up(n * 4);
+    w.keys_b = off; off += align_up(n * 4);
+    w.vals_a = off; off += align_up(n * 4);
+    w.vals_b = off; off += align_up(n * 4);
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                    static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr),
+                                    static_cast<int>(n), 0, 32);
+    w.cub_bytes = bytes;
+    w.cub = off; off += align_up(bytes);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+}  // namespace kgat
+
+using namespace kgat;
+
+extern "C" size_t kgat_bpr_workspace_bytes(int64_t batch) {
+    if (batch <= 0) return 256;
+    const size_t fwd = align_up(static_cast<size_t>(2) * sizeof(double) * ((batch + BPR_WARPS - 1) / BPR_WARPS));
+    const size_t bwd = plan_bwd(static_cast<int>(batch)).total;
+    return fwd > bwd ? fwd : bwd;
+}
+
+extern "C" int kgat_bpr_loss_fwd(const float* emb, int64_t emb_stride, int dim, const int64_t* src,
+                                 const int64_t* pos, const int64_t* neg, int64_t batch, float reg_lambda,
+                                 float* loss, float* sig, void* workspace, size_t workspace_bytes,
+                                 kgat_stream_t stream) {
+    KGAT_REQUIRE(emb && src && pos && neg && loss && sig && workspace);
+    KGAT_REQUIRE(batch > 0 && batch < (int64_t(1) << 28) && aligned16(emb) && emb_stride % 4 == 0);
+    if (dim <= 0 || dim % 4 != 0 || dim > 256) return KGAT_ERR_UNSUPPORTED_DIM;
+    if (workspace_bytes < kgat_bpr_workspace_bytes(batch)) return KGAT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    const int B = static_cast<int>(batch);
+    const int blocks = (B + BPR_WARPS - 1) / BPR_WARPS;
+    double* partial = static_cast<double*>(workspace);
+    bpr_fwd_kernel<<<blocks, BPR_THREADS, 0, st>>>(emb, emb_stride, dim, src, pos, neg, B, sig, partial);
+    KGAT_LAUNCH_CHECK();
+    bpr_finish_kernel<<<1, 256, 0, st>>>(partial, blocks, B, reg_lambda, loss);
+    KGAT_LAUNCH_CHECK();
+    return KGAT_OK;
+}
+
+extern "C" int kgat_bpr_loss_bwd(const float* emb, int64_t emb_stride, int dim, const int64_t* src,
+                                 const int64_t* pos, const int64_t* neg, int64_t batch, float reg_lambda,
+                                 const float* sig, const float* grad_loss, int64_t n_nodes,
+                                 float* rows, int32_t* rows_node, int32_t* row_slot,
+                                 void* workspace, size_t workspace_bytes, kgat_stream_t stream) {
+    KGAT_REQUIRE(emb && src && pos && neg && sig && grad_loss && rows && rows_node && row_slot && workspace);
+    KGAT_REQUIRE(batch > 0 && batch < (int64_t(1) << 28) && n_nodes > 0 && aligned16(emb) && aligned16(rows) &&
+                 emb_stride % 4 == 0);
+    if (dim <= 0 || dim % 4 != 0 || dim > 256) return KGAT_ERR_UNSUPPORTED_DIM;
+    if (workspace_bytes < kgat_bpr_workspace_bytes(batch)) return KGAT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    const int B = static_cast<int>(batch);
+    const BwdWs w = plan_bwd(B);
+    char* ws = static_cast<char*>(workspace);
+    uint32_t* ka = reinterpret_cast<uint32_t*>(ws + w.keys_a);
+    uint32_t* kb = reinterpret_cast<uint32_t*>(ws + w.keys_b);
+    int32_t* va = reinterpret_cast<int32_t*>(ws + w.vals_a);
+    int32_t* vb = reinterpret_cast<int32_t*>(ws + w.vals_b);
+    KGAT_CUDA(cudaMemsetAsync(row_slot, 0xff, sizeof(int32_t) * n_nodes, st));          // -1 everywhere
+    bpr_keys_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(src, pos, neg, B, ka, va);
+    KGAT_LAUNCH_CHECK();
+    int bits = 1;
+    while (bits < 32 && (static_cast<uint64_t>(n_nodes) >> bits) != 0) ++bits;
+    size_t bytes = w.cub_bytes;
+    KGAT_CUDA(cub::DeviceRadixSort::SortPairs(ws + w.cub, bytes, ka, kb, va, vb, 3 * B, 0, bits, st));
+    bpr_bwd_kernel<<<(3 * B + BPR_WARPS - 1) / BPR_WARPS, BPR_THREADS, 0, st>>>(
+        emb, emb_stride, dim, src, pos, neg, B, reg_lambda, sig, grad_loss, kb, vb, rows, dim, row_slot, rows_node);
+    KGAT_LAUNCH_CHECK();
+    return KGAT_OK;
+}

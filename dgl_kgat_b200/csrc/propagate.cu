@@ -178,7 +178,8 @@ template <int DIN, int DOUT>
 __global__ void __launch_bounds__(THREADS)
 layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
                  const float* __restrict__ w_csc, int row_begin, int row_end, int n_tiles,
-                 const float* __restrict__ d_concat, int64_t cstride, int64_t out_off,
+                 const float* __restrict__ d_concat, const int32_t* __restrict__ dc_slot, int64_t cstride,
+                 int64_t out_off,
                  const float* __restrict__ nxt_dx_direct, const float* __restrict__ nxt_dh_nb,
                  const float* __restrict__ h_in, const float* __restrict__ h_nb,
                  const float* __restrict__ act, const float* __restrict__ h_out,
@@ -225,8 +226,15 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                     g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
                 }
                 const float4 y = ldg4(h_out + oo);
-                if (d_concat) {
-                    const float4 dc = ldg4(d_concat + static_cast<size_t>(row) * cstride + out_off + lo * 4);
+                const float* dcp = nullptr;         // this row's slice of the concat gradient, if any
+                if (dc_slot) {
+                    const int slot = __ldg(dc_slot + row);
+                    if (slot >= 0) dcp = d_concat + static_cast<size_t>(slot) * cstride + out_off + lo * 4;
+                } else if (d_concat) {
+                    dcp = d_concat + static_cast<size_t>(row) * cstride + out_off + lo * 4;
+                }
+                if (dcp) {
+                    const float4 dc = ldg4(dcp);
                     float ss = y.x * y.x;
                     ss = fmaf(y.y, y.y, ss); ss = fmaf(y.z, y.z, ss); ss = fmaf(y.w, y.w, ss);
                     ss = group_sum<LPO>(ss);
@@ -354,8 +362,8 @@ template <int D>
 __global__ void __launch_bounds__(THREADS)
 input_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
                  const float* __restrict__ w_csc, int row_begin, int row_end,
-                 const float* __restrict__ d_concat, int64_t cstride, int64_t in_off,
-                 const float* __restrict__ dx_direct, const float* __restrict__ dh_nb,
+                 const float* __restrict__ d_concat, const int32_t* __restrict__ dc_slot, int64_t cstride,
+                 int64_t in_off, const float* __restrict__ dx_direct, const float* __restrict__ dh_nb,
                  float* __restrict__ d_entity) {
     constexpr int LP = D / 4;
     const int lane = threadIdx.x & 31;
@@ -367,8 +375,15 @@ input_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
         const size_t o = static_cast<size_t>(row) * D + lane * 4;
         const float4 t = ldg4(dx_direct + o);
         g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
-        if (d_concat) {
-            const float4 c = ldg4(d_concat + static_cast<size_t>(row) * cstride + in_off + lane * 4);
+        const float* dcp = nullptr;
+        if (dc_slot) {
+            const int slot = __ldg(dc_slot + row);
+            if (slot >= 0) dcp = d_concat + static_cast<size_t>(slot) * cstride + in_off + lane * 4;
+        } else if (d_concat) {
+            dcp = d_concat + static_cast<size_t>(row) * cstride + in_off + lane * 4;
+        }
+        if (dcp) {
+            const float4 c = ldg4(dcp);
             g.x += c.x; g.y += c.y; g.z += c.z; g.w += c.w;
         }
         *reinterpret_cast<float4*>(d_entity + o) = g;
@@ -404,7 +419,7 @@ int launch_fwd(const FwdArgs& a) {
 
 struct BwdArgs {
     const kgat_graph_t* g; int row_begin, row_end;
-    const float* d_concat; int64_t cstride, out_off;
+    const float* d_concat; const int32_t* dc_slot; int64_t cstride, out_off;
     const float *nxt_dx_direct, *nxt_dh_nb, *w_csc, *h_in, *h_nb, *act, *h_out, *drop_mask, *W2; float slope;
     float *dx_direct, *dh_nb, *dW2, *partials; cudaStream_t st;
 };
@@ -424,7 +439,8 @@ int launch_bwd(const BwdArgs& a) {
     const int n_tiles = (rows + TM - 1) / TM;
     const int grid = n_tiles < bwd_max_ctas() ? n_tiles : bwd_max_ctas();
     layer_bwd_kernel<DIN, DOUT><<<grid, THREADS, smem, a.st>>>(
-        a.g->csc_ptr, a.g->csc_dst, a.w_csc, a.row_begin, a.row_end, n_tiles, a.d_concat, a.cstride, a.out_off,
+        a.g->csc_ptr, a.g->csc_dst, a.w_csc, a.row_begin, a.row_end, n_tiles, a.d_concat, a.dc_slot, a.cstride,
+        a.out_off,
         a.nxt_dx_direct, a.nxt_dh_nb, a.h_in, a.h_nb, a.act, a.h_out, a.drop_mask, a.W2, a.slope, a.dx_direct,
         a.dh_nb, a.partials);
     KGAT_LAUNCH_CHECK();
@@ -471,8 +487,8 @@ extern "C" int kgat_layer_fwd(const kgat_graph_t* g, int64_t row_begin, int64_t 
 extern "C" int kgat_layer_bwd_partials(void) { return bwd_max_ctas(); }
 
 extern "C" int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
-                              const float* d_concat, int64_t concat_stride, int64_t out_off,
-                              const float* nxt_dx_direct, const float* nxt_dh_nb, const float* w_csc,
+                              const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride,
+                              int64_t out_off, const float* nxt_dx_direct, const float* nxt_dh_nb, const float* w_csc,
                               const float* h_in, const float* h_nb, const float* act, const float* h_out,
                               const float* drop_mask, const float* W2, int d_in, int d_out, float slope,
                               float* dx_direct, float* dh_nb, float* dW2, float* dW2_partials,
@@ -489,7 +505,8 @@ extern "C" int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t 
         KGAT_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * d_in * d_out, st));
         return KGAT_OK;
     }
-    BwdArgs a{g, (int)row_begin, (int)row_end, d_concat, concat_stride, out_off, nxt_dx_direct, nxt_dh_nb, w_csc,
+    KGAT_REQUIRE(!dc_row_slot || d_concat);
+    BwdArgs a{g, (int)row_begin, (int)row_end, d_concat, dc_row_slot, concat_stride, out_off, nxt_dx_direct, nxt_dh_nb, w_csc,
               h_in, h_nb, act, h_out, drop_mask, W2, slope, dx_direct, dh_nb, dW2, dW2_partials, st};
 #define X(DI, DO) if (d_in == DI && d_out == DO) return launch_bwd<DI, DO>(a);
     KGAT_DIM_PAIRS(X)
@@ -498,8 +515,8 @@ extern "C" int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t 
 }
 
 extern "C" int kgat_input_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
-                              const float* d_concat, int64_t concat_stride, int64_t in_off,
-                              const float* dx_direct, const float* dh_nb, const float* w_csc, int d,
+                              const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride,
+                              int64_t in_off, const float* dx_direct, const float* dh_nb, const float* w_csc, int d,
                               float* d_entity, kgat_stream_t stream) {
     KGAT_REQUIRE(g && dx_direct && dh_nb && d_entity);
     KGAT_REQUIRE(g->n_edges == 0 || w_csc);
@@ -513,7 +530,8 @@ extern "C" int kgat_input_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t 
 #define LAUNCH(D)                                                                                          \
     if (d == D) {                                                                                          \
         input_bwd_kernel<D><<<grid, THREADS, 0, st>>>(g->csc_ptr, g->csc_dst, w_csc, (int)row_begin,       \
-                                                      (int)row_end, d_concat, concat_stride, in_off,       \
+                                                      (int)row_end, d_concat, dc_row_slot, concat_stride,  \
+                                                      in_off,                                              \
                                                       dx_direct, dh_nb, d_entity);                         \
         KGAT_LAUNCH_CHECK();                                                                               \
         return KGAT_OK;                                                                                    \

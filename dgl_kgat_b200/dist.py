@@ -125,7 +125,7 @@ class DistKGAT:
         m = self.model
         weights = [l.res_fc_2.weight for l in m.layers]
         masks = list(drop_masks) if drop_masks is not None else [None] * len(weights)
-        return ops.Propagate.apply(self._plan, masks, False, m.entity_embed.weight, *weights)
+        return ops.propagate(self._plan, masks, False, m.entity_embed.weight, *weights)
 
     def get_loss(self, embedding, src_ids, pos_dst_ids, neg_dst_ids):
         """BPR loss of models.py:170-178 on rows gathered from their owners; replicated value."""

@@ -78,8 +78,7 @@ class KGATConv(nn.Module):
         dg = g.device_graph(nfeat.device)
         if drop_mask is None:
             drop_mask = _dropout_mask(self.mess_drop, g.n_nodes, self.res_fc_2.out_features, nfeat.device)
-        return ops.Propagate.apply(ops.PropagatePlan(dg, w_csr, w_csc), [drop_mask], True, nfeat,
-                                   self.res_fc_2.weight)
+        return ops.propagate(ops.PropagatePlan(dg, w_csr, w_csc), [drop_mask], True, nfeat, self.res_fc_2.weight)
 
 
 class Model(nn.Module):
@@ -167,10 +166,15 @@ class Model(nn.Module):
         if drop_masks is None:
             drop_masks = [_dropout_mask(l.mess_drop, g.n_nodes, l.res_fc_2.out_features, dev) for l in self.layers]
         weights = [l.res_fc_2.weight for l in self.layers]
-        return ops.Propagate.apply(ops.PropagatePlan(dg, w_csr, w_csc), list(drop_masks), False, h, *weights)
+        return ops.propagate(ops.PropagatePlan(dg, w_csr, w_csc), list(drop_masks), False, h, *weights)
 
     def get_loss(self, embedding, src_ids, pos_dst_ids, neg_dst_ids):
-        """BPR loss + L2 regulariser on the gathered rows (models.py:170-178)."""
+        """BPR loss + L2 regulariser on the gathered rows (models.py:170-178).  On the GPU this is
+        one fused kernel whose backward hands ``gnn`` a compact row gradient; the plain formula below
+        is the same arithmetic and serves tensors the kernel does not cover (CPU, widths > 256)."""
+        if (embedding.is_cuda and embedding.dtype == th.float32 and embedding.dim() == 2
+                and embedding.shape[1] % 4 == 0 and embedding.shape[1] <= 256 and src_ids.dim() == 1):
+            return ops.bpr_loss(embedding, src_ids, pos_dst_ids, neg_dst_ids, self._reg_lambda_gnn)
         src_vec = embedding[src_ids]
         pos_dst_vec = embedding[pos_dst_ids]
         neg_dst_vec = embedding[neg_dst_ids]

@@ -79,12 +79,33 @@ class PropagatePlan:
         return self.exchange is not None
 
 
+class GradChannel:
+    """Side channel between the fused BPR head and ``Propagate``: the loss gradient touches at most
+    3B of the N embedding rows, so ``BprLoss.backward`` parks it here in compact form (rows +
+    row_slot map) and hands autograd a zero-stride zero tensor instead of a dense (N, dim) one."""
+
+    def __init__(self):
+        self.compact = None         # (rows (3B, dim), row_slot (N,), rows_node (3B,))
+
+
+def propagate(plan, masks, single_layer, entity, *weights):
+    ch = GradChannel()
+    out = Propagate.apply(plan, masks, single_layer, ch, entity, *weights)
+    if not single_layer:
+        out._kgat_channel = ch
+    return out
+
+
+def _is_zero_sentinel(t):
+    return t.dim() == 2 and t.stride() == (0, 0)
+
+
 class Propagate(th.autograd.Function):
     """All KGATConv layers + normalise + concat of ``Model.gnn`` (reference models.py:156-168)
     as one autograd node; ``single_layer=True`` gives the bare ``KGATConv.forward`` output."""
 
     @staticmethod
-    def forward(ctx, plan: PropagatePlan, masks, single_layer, entity, *weights):
+    def forward(ctx, plan: PropagatePlan, masks, single_layer, channel, entity, *weights):
         lib = _lib.load()
         dg = plan.dg_fwd
         dev = dg.device
@@ -121,7 +142,7 @@ class Propagate(th.autograd.Function):
                 saved.append((h, h_nb, act, h_out))
                 h, off = h_out, off + d_out
         ctx.plan, ctx.masks, ctx.dims, ctx.single = plan, masks, dims, single_layer
-        ctx.saved, ctx.weights = saved, weights
+        ctx.saved, ctx.weights, ctx.channel = saved, weights, channel
         return h if single_layer else concat
 
     @staticmethod
@@ -130,10 +151,22 @@ class Propagate(th.autograd.Function):
         plan, dims, L = ctx.plan, ctx.dims, len(ctx.weights)
         dg = plan.dg_bwd
         dev, N = dg.device, dg.n_nodes
-        grad_out = _f32c(grad_out, dev)
         n_part = lib.kgat_layer_bwd_partials()
-        d_concat = None if ctx.single else grad_out
-        cstride = 0 if ctx.single else grad_out.shape[1]
+        dc_slot = None
+        compact, ctx.channel.compact = ctx.channel.compact, None
+        if compact is not None and not ctx.single:
+            rows, row_slot, rows_node = compact
+            if _is_zero_sentinel(grad_out):
+                d_concat, dc_slot, cstride = rows, row_slot, rows.shape[1]
+            else:                       # another consumer contributed a dense gradient as well: densify
+                valid = rows_node >= 0
+                grad_out = _f32c(grad_out, dev).clone()
+                grad_out.index_add_(0, rows_node[valid].long(), rows[valid])
+                d_concat, cstride = grad_out, grad_out.shape[1]
+        else:
+            grad_out = _f32c(grad_out, dev)
+            d_concat = None if ctx.single else grad_out
+            cstride = 0 if ctx.single else grad_out.shape[1]
         offs = [0]
         for d in dims:
             offs.append(offs[-1] + d)
@@ -156,7 +189,7 @@ class Propagate(th.autograd.Function):
                     up_dx, up_dh = nxt_dx, nxt_dh
                 with _lib.record("layer_bwd_%dx%d" % (d_in, d_out), 2):
                     _lib.check(lib.kgat_layer_bwd(
-                        dg.ref, plan.r0, plan.r1, _lib.ptr(d_concat), cstride, offs[l + 1],
+                        dg.ref, plan.r0, plan.r1, _lib.ptr(d_concat), _lib.ptr(dc_slot), cstride, offs[l + 1],
                         _lib.ptr(up_dx), _lib.ptr(up_dh), plan.w_csc.data_ptr(),
                         h_in.data_ptr(), h_nb.data_ptr(), _lib.ptr(act), h_out.data_ptr(), _lib.ptr(ctx.masks[l]),
                         ctx.weights[l].data_ptr(), d_in, d_out, LEAKY_SLOPE,
@@ -167,15 +200,72 @@ class Propagate(th.autograd.Function):
                 d_weights[l] = dW
                 nxt_dx, nxt_dh = dx, dh
             d_entity = None
-            if ctx.needs_input_grad[3]:
+            if ctx.needs_input_grad[4]:
                 d_entity = alloc(N, dims[0], dtype=th.float32, device=dev)
                 with _lib.record("input_bwd_%d" % dims[0]):
-                    _lib.check(lib.kgat_input_bwd(dg.ref, plan.r0, plan.r1, _lib.ptr(d_concat), cstride, 0,
+                    _lib.check(lib.kgat_input_bwd(dg.ref, plan.r0, plan.r1, _lib.ptr(d_concat), _lib.ptr(dc_slot), cstride, 0,
                                                   nxt_dx.data_ptr(), nxt_dh.data_ptr(), plan.w_csc.data_ptr(),
                                                   dims[0], d_entity.data_ptr(), st), "kgat_input_bwd")
                 if plan.distributed:
                     plan.exchange(d_entity)             # replicated parameters: every rank needs the full gradient
-        return (None, None, None, d_entity, *d_weights)
+        return (None, None, None, None, d_entity, *d_weights)
+
+
+class BprLoss(th.autograd.Function):
+    """Fused BPR loss head (reference models.py:170-178): forward = gather + dots + logsigmoid +
+    L2 terms in one kernel; backward = compact, deterministic row gradient (see GradChannel)."""
+
+    @staticmethod
+    def forward(ctx, embedding, src, pos, neg, reg_lambda, channel):
+        lib = _lib.load()
+        dev = embedding.device
+        emb = _f32c(embedding, dev)
+        ids = [i.to(device=dev, dtype=th.int64).contiguous().view(-1) for i in (src, pos, neg)]
+        B, dim = ids[0].numel(), emb.shape[1]
+        if ids[1].numel() != B or ids[2].numel() != B:
+            raise _lib.KgatError("get_loss: id vectors differ in length")
+        ws_bytes = lib.kgat_bpr_workspace_bytes(B)
+        ws = th.empty(ws_bytes, dtype=th.uint8, device=dev)
+        loss = th.empty((), dtype=th.float32, device=dev)
+        sig = th.empty(B, dtype=th.float32, device=dev)
+        with th.cuda.device(dev):
+            with _lib.record("bpr_loss_fwd", 2):
+                _lib.check(lib.kgat_bpr_loss_fwd(emb.data_ptr(), emb.stride(0), dim, ids[0].data_ptr(), ids[1].data_ptr(),
+                                                 ids[2].data_ptr(), B, float(reg_lambda), loss.data_ptr(), sig.data_ptr(),
+                                                 ws.data_ptr(), ws_bytes, _lib.stream_ptr()), "kgat_bpr_loss_fwd")
+        ctx.emb, ctx.ids, ctx.sig, ctx.lam, ctx.channel, ctx.ws = emb, ids, sig, float(reg_lambda), channel, ws
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lib = _lib.load()
+        emb, ids = ctx.emb, ctx.ids
+        dev = emb.device
+        B, (N, dim) = ids[0].numel(), emb.shape
+        g = grad_loss.to(device=dev, dtype=th.float32).contiguous()
+        rows = th.empty(3 * B, dim, dtype=th.float32, device=dev)
+        rows_node = th.empty(3 * B, dtype=th.int32, device=dev)
+        row_slot = th.empty(N, dtype=th.int32, device=dev)
+        ws = ctx.ws
+        with th.cuda.device(dev):
+            with _lib.record("bpr_loss_bwd", 6):
+                _lib.check(lib.kgat_bpr_loss_bwd(emb.data_ptr(), emb.stride(0), dim, ids[0].data_ptr(), ids[1].data_ptr(),
+                                                 ids[2].data_ptr(), B, ctx.lam, ctx.sig.data_ptr(), g.data_ptr(), N,
+                                                 rows.data_ptr(), rows_node.data_ptr(), row_slot.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "kgat_bpr_loss_bwd")
+        ch = ctx.channel
+        if ch is not None and ch.compact is None:
+            ch.compact = (rows, row_slot, rows_node)
+            grad_emb = th.zeros(1, 1, dtype=th.float32, device=dev).expand(N, dim)
+        else:
+            valid = rows_node >= 0
+            grad_emb = th.zeros(N, dim, dtype=th.float32, device=dev)
+            grad_emb.index_add_(0, rows_node[valid].long(), rows[valid])
+        return grad_emb, None, None, None, None, None
+
+
+def bpr_loss(embedding, src, pos, neg, reg_lambda):
+    return BprLoss.apply(embedding, src, pos, neg, reg_lambda, getattr(embedding, "_kgat_channel", None))
 
 
 def score_topk(emb: th.Tensor, user_ids: th.Tensor, item_ids: th.Tensor, mask_ptr, mask_items, K: int,

@@ -138,7 +138,10 @@ KGAT_API int kgat_layer_fwd(const kgat_graph_t* g, int64_t row_begin, int64_t ro
 /* Backward of one KGATConv for rows [row_begin,row_end) -- replaces the autograd
  * of the ops above incl. DGL's BackwardBinaryReduce (transposed aggregation).
  * Gradient w.r.t. this layer's output row v is assembled in-kernel from
- *   - the normalised copy:   d_concat[v, out_off : out_off+d_out]   (d_concat may be null)
+ *   - the normalised copy:   d_concat[v, out_off : out_off+d_out]   (d_concat may be null).
+ *     When dc_row_slot is non-null the gradient of the concat buffer is COMPACT (what
+ *     kgat_bpr_loss_bwd produces): row v's gradient is d_concat[dc_row_slot[v], ...] and is zero
+ *     when dc_row_slot[v] < 0;
  *   - the next layer (both null for the last layer; each term is optional on its own):
  *       nxt_dx_direct[v] + sum_{k in CSC row v} w_csc[k] * nxt_dh_nb[csc_dst[k]]
  * then pushed through dropout / LeakyReLU / Linear / (.):
@@ -147,7 +150,7 @@ KGAT_API int kgat_layer_fwd(const kgat_graph_t* g, int64_t row_begin, int64_t ro
  * dW2_partials: scratch of kgat_layer_bwd_partials() * d_out * d_in floats. */
 KGAT_API int kgat_layer_bwd_partials(void);
 KGAT_API int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
-                   const float* d_concat, int64_t concat_stride, int64_t out_off,
+                   const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride, int64_t out_off,
                    const float* nxt_dx_direct, const float* nxt_dh_nb, const float* w_csc,
                    const float* h_in, const float* h_nb, const float* act, const float* h_out,
                    const float* drop_mask, const float* W2, int d_in, int d_out, float slope,
@@ -158,9 +161,28 @@ KGAT_API int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t ro
  *   d_entity[v] = d_concat[v, in_off : in_off+d] + dx_direct[v]
  *               + sum_{k in CSC row v} w_csc[k] * dh_nb[csc_dst[k]] */
 KGAT_API int kgat_input_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
-                   const float* d_concat, int64_t concat_stride, int64_t in_off,
+                   const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride, int64_t in_off,
                    const float* dx_direct, const float* dh_nb, const float* w_csc, int d,
                    float* d_entity, kgat_stream_t stream);
+
+/* BPR loss head of the CF step -- replaces Model.get_loss (models.py:170-178):
+ *   loss = -mean(logsigmoid(<s,p> - <s,n>)) + reg_lambda * (mean|s|^2/2 + mean|p|^2/2 + mean|n|^2/2),
+ *   s,p,n = emb[src], emb[pos], emb[neg]  (int64 ids, as kgat.py:153-158 produces them).
+ * fwd writes the scalar loss and sig[b] = sigmoid(-(<s,p>-<s,n>)) for the backward.
+ * bwd writes the gradient w.r.t. emb COMPACT: rows[i,:] for the sorted positions i that start a run of
+ * equal node ids (rows_node[i] = node id, -1 for the other positions) and row_slot[node] = i, -1 for
+ * untouched nodes; rows is (3*batch, dim).  grad_loss: device scalar, the upstream gradient.
+ * Deterministic (sorted, fixed-order accumulation; no atomics). */
+KGAT_API size_t kgat_bpr_workspace_bytes(int64_t batch);
+KGAT_API int kgat_bpr_loss_fwd(const float* emb, int64_t emb_stride, int dim, const int64_t* src,
+                      const int64_t* pos, const int64_t* neg, int64_t batch, float reg_lambda,
+                      float* loss, float* sig, void* workspace, size_t workspace_bytes,
+                      kgat_stream_t stream);
+KGAT_API int kgat_bpr_loss_bwd(const float* emb, int64_t emb_stride, int dim, const int64_t* src,
+                      const int64_t* pos, const int64_t* neg, int64_t batch, float reg_lambda,
+                      const float* sig, const float* grad_loss, int64_t n_nodes,
+                      float* rows, int32_t* rows_node, int32_t* row_slot,
+                      void* workspace, size_t workspace_bytes, kgat_stream_t stream);
 
 /* (5) full-rank scoring with fused per-row top-K -- replaces the per-user loop of
  *     metric.calc_recall_ndcg (metric.py:44-51): for eval user j,

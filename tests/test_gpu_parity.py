@@ -507,3 +507,53 @@ def test_full_size_eval_properties(dev, amazon):
         s[r, np.asarray(tr[users[j]])] = 0.0
     want = np.argsort(-s, axis=1, kind="stable")[:, :20]
     assert_topk_parity(top[sel], want, s, 20)
+
+
+# =================================================================================== fused BPR head
+def test_bpr_loss_fused_matches_formula(dev):
+    """Model.get_loss on the GPU (fused kernel, compact deterministic backward) against the reference
+    formula of models.py:170-178 evaluated in fp64; duplicate ids in the batch must accumulate."""
+    th.manual_seed(0)
+    N, dim, B = 3000, 176, 4096
+    m = make_model(50, 3, dev)
+    emb = th.randn(N, dim, device=dev, requires_grad=True)
+    g = th.Generator().manual_seed(1)
+    ids = [th.randint(0, 200 if i == 0 else N, (B,), generator=g).to(dev) for i in range(3)]   # many repeats
+    loss = m.get_loss(emb, *ids)
+    loss.backward()
+    emb64 = emb.detach().cpu().double().requires_grad_(True)
+    loss64 = kgat_ref.get_loss(emb64, *[i.cpu() for i in ids], 1e-4)
+    loss64.backward()
+    assert abs(loss.item() - loss64.item()) < 1e-6 * abs(loss64.item())
+    assert max_rel(emb.grad.cpu().numpy(), emb64.grad.numpy()) < RTOL
+    # deterministic
+    emb.grad = None
+    m.get_loss(emb, *ids).backward()
+    g1 = emb.grad.clone()
+    emb.grad = None
+    m.get_loss(emb, *ids).backward()
+    assert th.equal(g1, emb.grad)
+    # upstream gradient scaling and a second consumer of the embedding
+    emb.grad = None
+    (3.0 * m.get_loss(emb, *ids) + emb.sum()).backward()
+    assert max_rel(emb.grad.cpu().numpy(), 3.0 * emb64.grad.numpy() + 1.0) < RTOL
+
+
+def test_gnn_with_two_consumers_of_the_embedding(dev, golden_small):
+    """The compact-gradient side channel must stay correct when the embedding also feeds another loss."""
+    g = golden_small
+    N, R = int(g["n_nodes"]), int(g["n_rel"])
+    m = make_model(N, R, dev, params=params_from_golden(g))
+    graph = CKGraph(N, g["trip"], n_rel=R)
+    graph.edata["w"] = th.from_numpy(g["att_w"]).to(dev)
+    ids = [th.from_numpy(g[k]).to(dev) for k in ("batch_u", "batch_p", "batch_n")]
+    emb = m.gnn(graph, None)
+    (m.get_loss(emb, *ids) + 1e-3 * emb.pow(2).sum()).backward()
+    p64 = params_from_golden(g, th.float64)
+    leaves = {k: v.clone().requires_grad_(k == "entity_embed.weight" or k.startswith("layers.")) for k, v in p64.items()}
+    emb64 = kgat_ref.gnn(leaves, g["trip"], th.from_numpy(g["att_w"]).double(), N)
+    (kgat_ref.get_loss(emb64, *[i.cpu() for i in ids], 1e-4) + 1e-3 * emb64.pow(2).sum()).backward()
+    assert max_rel(m.entity_embed.weight.grad.cpu().numpy(), leaves["entity_embed.weight"].grad.numpy()) < RTOL
+    for i in range(3):
+        assert max_rel(m.layers[i].res_fc_2.weight.grad.cpu().numpy(),
+                       leaves["layers.%d.res_fc_2.weight" % i].grad.numpy()) < RTOL
