@@ -5,18 +5,18 @@
 //
 // One persistent CTA per SM walks a contiguous range of 128-edge tiles of the relation buckets.
 // Warp-specialised, three roles connected by mbarriers:
-//   producers (warps 0-3)  gather the 128 tail rows and 128 head rows of the tile from the entity table
+//   producers (warps 0-7)  gather the 128 tail rows and 128 head rows of the tile from the entity table
 //            (128-bit loads, a warp instruction covers 8 rows x 64 B), split every value x = hi + lo
 //            (hi = RN-TF32(x), lo exact) and store both halves in shared memory in the K-major
 //            no-swizzle core-matrix layout (umma.cuh).  A stage holds one K-half (32 of the 64 input
 //            features) of a tile: 4 arrays x 16 KB; two stages ring.  Loads for the next stage are in
 //            flight while the current one is split and stored.  W_r is staged as B = [W_hi | W_lo]
 //            (N = 128) once per relation.
-//   MMA      (warp 8, one lane) per stage: T_hi x [W_hi|W_lo] (N=128), T_lo x W_hi (N=64) and the same
+//   MMA      (warp 12, one lane) per stage: T_hi x [W_hi|W_lo] (N=128), T_lo x W_hi (N=64) and the same
 //            for the head rows -> hi*hi + lo*hi in TMEM columns 0..63, hi*lo in 64..127; fp32
 //            accumulation in TMEM, two accumulator buffers (2 x 256 columns).  tcgen05.commit releases
 //            the shared-memory stage and, after the second K-half, publishes the accumulator.
-//   epilogue (warps 4-7, one TMEM lane quarter each) tcgen05.ld, t = c[0:64] + c[64:128],
+//   epilogue (warps 8-11, one TMEM lane quarter each) tcgen05.ld, t = c[0:64] + c[64:128],
 //            logit = sum_c t_r[c] * tanh(h_r[c] + e_r[c]), scattered to the edge's CSR position; runs
 //            while the tensor core works on the next tile.
 // Neither projection ever exists in HBM.  3xTF32 keeps the result inside the 1e-5 relative bar
@@ -30,10 +30,10 @@ namespace {
 constexpr int TILE = 128;
 constexpr int D = 64;                 // entity and relation width of this specialisation
 constexpr int KH = 32;                // K-half held by one stage
-constexpr int N_PROD = 128;           // producer threads (warps 0-3)
-constexpr int N_EPI = 128;            // epilogue threads (warps 4-7)
+constexpr int N_PROD = 256;           // producer threads (warps 0-7: 0-3 tail rows, 4-7 head rows)
+constexpr int N_EPI = 128;            // epilogue threads (warps 8-11, TMEM lane quarter = warp % 4)
 constexpr int THREADS = N_PROD + N_EPI + 32;
-constexpr int MMA_WARP = 8;
+constexpr int MMA_WARP = 12;
 constexpr int MAX_REL = 1024;
 constexpr uint32_t ARR_BYTES = TILE * KH * 4;        // 16 KB: one operand array of one stage
 constexpr uint32_t STAGE_BYTES = 4 * ARR_BYTES;      // T_hi, T_lo, H_hi, H_lo
@@ -117,39 +117,41 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
     const int t0 = static_cast<int>(static_cast<long long>(n_tiles) * blockIdx.x / gridDim.x);
     const int t1 = static_cast<int>(static_cast<long long>(n_tiles) * (blockIdx.x + 1) / gridDim.x);
 
-    if (warp < 4) {
+    if (warp < 8) {
         // =========================================================== producers
+        // Per stage (one K-half) a thread moves 8 x 16 bytes: slot j -> row (j >> 1) of its 4 rows, chunk
+        // group (j & 1).  A warp instruction covers 8 rows (lane & 7) x 4 consecutive chunks (lane >> 3).
+        // Everything that depends on the thread is folded into two base pointers; slot offsets are
+        // compile-time constants.
         const int r8 = lane & 7, cq = lane >> 3;
-        // this thread's 16 (row, 16-byte chunk) slots of a stage: slot j -> row group rg (0..15 tail rows,
-        // 16..31 head rows), chunk group cg (0..1); row = (rg & 15)*8 + r8, chunk = cg*4 + cq (of the K-half)
-        int ids[16];            // node id of slot j's row for the tile being loaded (-1: padding row)
-        float4 va[16], vb[16];  // in-flight gathers: K-half 0 / K-half 1
+        const int32_t* __restrict__ id_src = warp < 4 ? bk_tail : bk_head;
+        const int row_base = (warp & 3) * 32 + r8;                       // rows row_base + 8 * i, i = 0..3
+        const uint32_t st_base = (warp < 4 ? 0u : 2u * ARR_BYTES) + ((warp & 3) * 4) * SBO_A + cq * 128 + r8 * 16;
+        const float* __restrict__ ent_q = ent + cq * 4;
+        int ids[4], ids_next[4];    // node ids of this thread's 4 rows (-1: padding row)
+        float4 va[8], vb[8];        // in-flight gathers: K-half 0 / K-half 1
         int rel = 0, loaded_rel = -1;
 
-        auto load_ids = [&](const TileInfo& t) {
+        auto load_ids = [&](const TileInfo& t, int* dst) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int rg = (warp * 16 + j) >> 1;
-                const int rl = (rg & 15) * 8 + r8;
-                ids[j] = rl < t.n_e ? __ldg((rg < 16 ? bk_tail : bk_head) + t.e0 + rl) : -1;
+            for (int i = 0; i < 4; ++i) {
+                const int rl = row_base + 8 * i;
+                dst[i] = rl < t.n_e ? __ldg(id_src + t.e0 + rl) : -1;
             }
         };
-        auto issue = [&](float4* v, int h) {
+        auto issue = [&](float4* v, const int* id, int h) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int cg = (warp * 16 + j) & 1;
-                v[j] = ids[j] >= 0 ? ldg4(ent + static_cast<size_t>(ids[j]) * D + h * KH + (cg * 4 + cq) * 4)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 8; ++j) {
+                const int i = j >> 1, cg = j & 1;
+                v[j] = id[i] >= 0 ? ldg4(ent_q + static_cast<size_t>(id[i]) * D + h * KH + cg * 16)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         auto store = [&](const float4* v, int stage) {
-            unsigned char* base = s.A[stage];
+            unsigned char* base = s.A[stage] + st_base;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int combo = warp * 16 + j, rg = combo >> 1, cg = combo & 1;
-                const int rl = (rg & 15) * 8 + r8;
-                const uint32_t off =
-                    (rg < 16 ? 0u : 2u * ARR_BYTES) + (rl >> 3) * SBO_A + (cg * 4 + cq) * 128 + r8 * 16;
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t off = (j >> 1) * SBO_A + (j & 1) * 512;
                 float4 hi, lo;
                 umma::split_tf32(v[j].x, hi.x, lo.x);
                 umma::split_tf32(v[j].y, hi.y, lo.y);
@@ -162,11 +164,17 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
 
         if (t0 < t1) {
             TileInfo cur = tile_info(s.prefix, rel_ptr, t0, rel);
-            load_ids(cur);
-            issue(va, 0);
+            load_ids(cur, ids);
+            issue(va, ids, 0);
             for (int tile = t0; tile < t1 && !s.abort_flag; ++tile) {
                 const int it = tile - t0;
-                issue(vb, 1);                                        // K-half 1 of this tile
+                const bool more = tile + 1 < t1;
+                TileInfo nxt = cur;
+                if (more) {                                          // ids of the next tile: a full tile ahead
+                    nxt = tile_info(s.prefix, rel_ptr, tile + 1, rel);
+                    load_ids(nxt, ids_next);
+                }
+                issue(vb, ids, 1);                                   // K-half 1 of this tile
                 // ---- stage 0 <- K-half 0
                 if (!umma::mbar_wait(&s.empty[0], (it & 1) ^ 1)) s.abort_flag = 1;
                 if (loaded_rel != cur.rel) {
@@ -185,18 +193,14 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
                 store(va, 0);
                 umma::fence_proxy_async();
                 umma::mbar_arrive(&s.full[0]);
-                // ---- prefetch the next tile's ids and its K-half 0 (vb of this tile is already in flight)
-                TileInfo nxt = cur;
-                if (tile + 1 < t1) {
-                    nxt = tile_info(s.prefix, rel_ptr, tile + 1, rel);
-                    load_ids(nxt);
-                    issue(va, 0);
-                }
+                if (more) issue(va, ids_next, 0);                    // K-half 0 of the next tile
                 // ---- stage 1 <- K-half 1
                 if (!umma::mbar_wait(&s.empty[1], (it & 1) ^ 1)) s.abort_flag = 1;
                 store(vb, 1);
                 umma::fence_proxy_async();
                 umma::mbar_arrive(&s.full[1]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ids[i] = ids_next[i];
                 cur = nxt;
             }
         }
@@ -234,7 +238,7 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
             }
         }
     } else {
-        // =========================================================== epilogue (warps 4..7)
+        // =========================================================== epilogue (warps 8..11)
         const int q = warp & 3;                                       // TMEM lane quarter of this warp
         const int row = q * 32 + lane;
         const int et = tid - N_PROD;                                  // 0..127
@@ -252,16 +256,16 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
             const uint32_t ta = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
             float p = 0.f;
 #pragma unroll
-            for (int c0 = 0; c0 < D; c0 += 32) {
-                float a[32], b[32], tt[32];
-                umma::tmem_ld32(ta + c0, a);
-                umma::tmem_ld32(ta + 64 + c0, b);
+            for (int c0 = 0; c0 < D; c0 += 16) {
+                float a[16], b[16], c[16], d[16];
+                umma::tmem_ld16(ta + c0, a);                 // T: hi*hi + lo*hi
+                umma::tmem_ld16(ta + 64 + c0, b);            // T: hi*lo
+                umma::tmem_ld16(ta + 128 + c0, c);           // H: hi*hi + lo*hi
+                umma::tmem_ld16(ta + 192 + c0, d);           // H: hi*lo
+                umma::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) tt[i] = a[i] + b[i];
-                umma::tmem_ld32(ta + 128 + c0, a);
-                umma::tmem_ld32(ta + 192 + c0, b);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) p = fmaf(tt[i], tanh_fast(a[i] + b[i] + s.er[buf][c0 + i]), p);
+                for (int i = 0; i < 16; ++i)
+                    p = fmaf(a[i] + b[i], tanh_fast(c[i] + d[i] + s.er[buf][c0 + i]), p);
             }
             umma::fence_before_sync();
             umma::mbar_arrive(&s.acc_empty[buf]);                     // TMEM buffer may be overwritten

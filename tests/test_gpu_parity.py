@@ -303,7 +303,7 @@ def test_aggregation_adjointness(dev):
                                   h_nb.data_ptr(), None, h_out.data_ptr(), None, 0, 0, -1, _lib.stream_ptr()))
     aty = th.empty(N, 64, device=dev)
     zeros = th.zeros(N, 64, device=dev)
-    _lib.check(lib.kgat_input_bwd(dg.ref, 0, N, None, 0, 0, zeros.data_ptr(), y.data_ptr(), w_csc.data_ptr(), 64,
+    _lib.check(lib.kgat_input_bwd(dg.ref, 0, N, None, None, 0, 0, zeros.data_ptr(), y.data_ptr(), w_csc.data_ptr(), 64,
                                   aty.data_ptr(), _lib.stream_ptr()))
     lhs = (h_nb.double() * y.double()).sum().item()
     rhs = (x.double() * aty.double()).sum().item()
