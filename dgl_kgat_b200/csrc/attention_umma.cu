@@ -6,10 +6,11 @@
 // One persistent CTA per SM walks a contiguous range of 128-edge tiles of the relation buckets.
 // Warp-specialised, three roles connected by mbarriers:
 //   producers (warps 0-7)  gather the 128 tail rows and 128 head rows of the tile from the entity table
-//            (128-bit loads, a warp instruction covers 8 rows x 64 B), split every value x = hi + lo
-//            (hi = RN-TF32(x), lo exact) and store both halves in shared memory in the K-major
-//            no-swizzle core-matrix layout (umma.cuh).  A stage holds one K-half (32 of the 64 input
-//            features) of a tile: 4 arrays x 16 KB; two stages ring.  Loads for the next stage are in
+//            (128-bit loads; 8 consecutive lanes read one row's contiguous 128 bytes, a warp instruction
+//            covers 4 rows), split every value x = hi + lo (hi = RN-TF32(x), lo exact) and store both
+//            halves in shared memory in the K-major SWIZZLE_128B layout (umma.cuh): the same 8 lanes
+//            write one conflict-free 128-byte row.  A stage holds one K-half (32 of the 64 input
+//            features = one 128-byte row per edge) of a tile: 4 arrays x 16 KB; two stages ring.  Loads for the next stage are in
 //            flight while the current one is split and stored.  W_r is staged as B = [W_hi | W_lo]
 //            (N = 128) once per relation.
 //   MMA      (warp 12, one lane) per stage: T_hi x [W_hi|W_lo] (N=128), T_lo x W_hi (N=64) and the same
@@ -37,12 +38,11 @@ constexpr int MMA_WARP = 12;
 constexpr int MAX_REL = 1024;
 constexpr uint32_t ARR_BYTES = TILE * KH * 4;        // 16 KB: one operand array of one stage
 constexpr uint32_t STAGE_BYTES = 4 * ARR_BYTES;      // T_hi, T_lo, H_hi, H_lo
-constexpr uint32_t SBO_A = (KH / 4) * 128;           // 8-row group stride inside a stage array
-constexpr uint32_t SBO_B = (D / 4) * 128;            // ... inside the W tile (full K)
+constexpr uint32_t B_HALF_BYTES = 128 * KH * 4;      // 16 KB: [W_hi | W_lo] rows for one K-half
 constexpr uint32_t TMEM_COLS = 512;                  // 2 buffers x (T: 128 + H: 128)
 
 struct Smem {
-    unsigned char B[2 * 64 * D * 4];                 // rows 0..63: W_hi^T, rows 64..127: W_lo^T
+    unsigned char B[2][B_HALF_BYTES];                // per K-half: rows 0..63 W_hi^T, rows 64..127 W_lo^T
     unsigned char A[2][STAGE_BYTES];
     float er[2][D];
     int prefix[MAX_REL + 1];
@@ -119,39 +119,41 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
 
     if (warp < 8) {
         // =========================================================== producers
-        // Per stage (one K-half) a thread moves 8 x 16 bytes: slot j -> row (j >> 1) of its 4 rows, chunk
-        // group (j & 1).  A warp instruction covers 8 rows (lane & 7) x 4 consecutive chunks (lane >> 3).
-        // Everything that depends on the thread is folded into two base pointers; slot offsets are
-        // compile-time constants.
-        const int r8 = lane & 7, cq = lane >> 3;
+        // Per stage (one K-half) a thread moves 8 x 16 bytes: slot j -> row R_j = (warp & 3) * 32 + 4 * j +
+        // (lane >> 3), 16-byte chunk c = lane & 7.  Eight consecutive lanes cover one row's 128 bytes, in
+        // global memory and (chunk-permuted) in shared memory.
+        const int c = lane & 7, rsub = lane >> 3;
         const int32_t* __restrict__ id_src = warp < 4 ? bk_tail : bk_head;
-        const int row_base = (warp & 3) * 32 + r8;                       // rows row_base + 8 * i, i = 0..3
-        const uint32_t st_base = (warp < 4 ? 0u : 2u * ARR_BYTES) + ((warp & 3) * 4) * SBO_A + cq * 128 + r8 * 16;
-        const float* __restrict__ ent_q = ent + cq * 4;
-        int ids[4], ids_next[4];    // node ids of this thread's 4 rows (-1: padding row)
+        const int row_base = (warp & 3) * 32 + rsub;                     // R_j = row_base + 4 * j
+        uint32_t st_base[2];                                             // by parity of j: row-in-group = (j&1)*4 + rsub
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+            const int rr = par * 4 + rsub;
+            st_base[par] = (warp < 4 ? 0u : 2u * ARR_BYTES) + ((warp & 3) * 4) * 1024 + rr * 128 + ((c ^ rr) << 4);
+        }
+        const float* __restrict__ ent_c = ent + c * 4;
+        int ids[8], ids_next[8];    // node ids of this thread's 8 rows (-1: padding row)
         float4 va[8], vb[8];        // in-flight gathers: K-half 0 / K-half 1
         int rel = 0, loaded_rel = -1;
 
         auto load_ids = [&](const TileInfo& t, int* dst) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int rl = row_base + 8 * i;
-                dst[i] = rl < t.n_e ? __ldg(id_src + t.e0 + rl) : -1;
+            for (int j = 0; j < 8; ++j) {
+                const int rl = row_base + 4 * j;
+                dst[j] = rl < t.n_e ? __ldg(id_src + t.e0 + rl) : -1;
             }
         };
         auto issue = [&](float4* v, const int* id, int h) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int i = j >> 1, cg = j & 1;
-                v[j] = id[i] >= 0 ? ldg4(ent_q + static_cast<size_t>(id[i]) * D + h * KH + cg * 16)
+            for (int j = 0; j < 8; ++j)
+                v[j] = id[j] >= 0 ? ldg4(ent_c + static_cast<size_t>(id[j]) * D + h * KH)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
         };
         auto store = [&](const float4* v, int stage) {
-            unsigned char* base = s.A[stage] + st_base;
+            unsigned char* base = s.A[stage];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint32_t off = (j >> 1) * SBO_A + (j & 1) * 512;
+                const uint32_t off = st_base[j & 1] + (j >> 1) * 1024;
                 float4 hi, lo;
                 umma::split_tf32(v[j].x, hi.x, lo.x);
                 umma::split_tf32(v[j].y, hi.y, lo.y);
@@ -185,8 +187,8 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
                         const int k = idx >> 6, n = idx & 63;
                         float hi, lo;
                         umma::split_tf32(__ldg(Wg + idx), hi, lo);
-                        *reinterpret_cast<float*>(s.B + umma::tile_offset(n, k, D)) = hi;
-                        *reinterpret_cast<float*>(s.B + umma::tile_offset(64 + n, k, D)) = lo;
+                        *reinterpret_cast<float*>(s.B[k >> 5] + umma::sw128_offset(n, k & 31)) = hi;
+                        *reinterpret_cast<float*>(s.B[k >> 5] + umma::sw128_offset(64 + n, k & 31)) = lo;
                     }
                     loaded_rel = cur.rel;
                 }
@@ -200,7 +202,7 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
                 umma::fence_proxy_async();
                 umma::mbar_arrive(&s.full[1]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ids[i] = ids_next[i];
+                for (int j = 0; j < 8; ++j) ids[j] = ids_next[j];
                 cur = nxt;
             }
         }
@@ -208,7 +210,6 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
         // =========================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc128 = umma::make_idesc_tf32(TILE, 128), idesc64 = umma::make_idesc_tf32(TILE, 64);
-            const uint32_t bW = umma::smem_u32(s.B);
             for (int tile = t0; tile < t1 && !s.abort_flag; ++tile) {
                 const int it = tile - t0, buf = it & 1;
                 if (!umma::mbar_wait(&s.acc_empty[buf], ((it >> 1) & 1) ^ 1)) s.abort_flag = 1;
@@ -219,18 +220,16 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
                     if (!umma::mbar_wait(&s.full[h], it & 1)) s.abort_flag = 1;
                     umma::fence_after_sync();
                     const uint32_t aT = umma::smem_u32(s.A[h]), aH = aT + 2 * ARR_BYTES;
+                    const uint32_t bW = umma::smem_u32(s.B[h]);
 #pragma unroll
                     for (int ks = 0; ks < KH / 8; ++ks) {
-                        const uint32_t off = ks * 2 * umma::CORE_BYTES;
-                        const uint64_t dB =
-                            umma::make_smem_desc(bW + h * (KH / 4) * 128 + off, umma::LBO_BYTES, SBO_B);
+                        const uint32_t off = ks * 32;                 // K = 8 fp32 inside the 128-byte row
+                        const uint64_t dB = umma::make_smem_desc_sw128(bW + off);
                         const uint32_t acc = (h | ks) != 0;
-                        umma::mma_tf32(tT, umma::make_smem_desc(aT + off, umma::LBO_BYTES, SBO_A), dB, idesc128, acc);
-                        umma::mma_tf32(tT, umma::make_smem_desc(aT + ARR_BYTES + off, umma::LBO_BYTES, SBO_A), dB,
-                                       idesc64, 1);
-                        umma::mma_tf32(tH, umma::make_smem_desc(aH + off, umma::LBO_BYTES, SBO_A), dB, idesc128, acc);
-                        umma::mma_tf32(tH, umma::make_smem_desc(aH + ARR_BYTES + off, umma::LBO_BYTES, SBO_A), dB,
-                                       idesc64, 1);
+                        umma::mma_tf32(tT, umma::make_smem_desc_sw128(aT + off), dB, idesc128, acc);
+                        umma::mma_tf32(tT, umma::make_smem_desc_sw128(aT + ARR_BYTES + off), dB, idesc64, 1);
+                        umma::mma_tf32(tH, umma::make_smem_desc_sw128(aH + off), dB, idesc128, acc);
+                        umma::mma_tf32(tH, umma::make_smem_desc_sw128(aH + ARR_BYTES + off), dB, idesc64, 1);
                     }
                     umma::mma_commit(&s.empty[h]);                   // stage h may be refilled once these finish
                 }

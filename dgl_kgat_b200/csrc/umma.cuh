@@ -1,10 +1,15 @@
 // tcgen05 / TMEM / mbarrier building blocks (inline PTX, sm_100a) used by the tensor-core kernels.
 //
-// Operand layout used everywhere in this repo: K-major, NO swizzle ("interleave").  A tile of R rows
-// x KT fp32 is stored as 8-row x 16-byte core matrices:
-//     byte(r, k) = (r / 8) * SBO + (k / 4) * LBO + (r % 8) * 16 + (k % 4) * 4
-// with LBO = 128 (core matrices adjacent along K) and SBO = (KT / 4) * 128.  One kind::tf32 MMA
-// consumes K = 8 (two core matrices along K), so the k-th MMA of a tile starts 256 * k bytes in.
+// Two K-major operand layouts are supported (both verified on hardware by kgat_selftest_umma):
+//  * SWIZZLE_128B (used by the kernels): a tile row is 32 fp32 = 128 bytes; rows are 128 B apart,
+//    8-row groups 1024 B apart (SBO), and inside a row the eight 16-byte chunks are XOR-permuted by
+//    the row index:  byte(r, k) = (r / 8) * 1024 + (r % 8) * 128 + (((k / 4) ^ (r % 8)) * 16) + (k % 4) * 4.
+//    Eight consecutive lanes can read one row's 128 contiguous bytes from global memory AND write them
+//    as one conflict-free 128-byte shared-memory wavefront.  Tile bases must be 1024-byte aligned.
+//    One kind::tf32 MMA consumes K = 8 = 32 bytes: the k-th MMA of a tile starts 32 * k bytes in.
+//  * no swizzle ("interleave"): 8-row x 16-byte core matrices,
+//    byte(r, k) = (r / 8) * SBO + (k / 4) * 128 + (r % 8) * 16 + (k % 4) * 4, LBO = 128, SBO = (KT / 4) * 128;
+//    the k-th MMA starts 256 * k bytes in.
 // The accumulator of an M = 128 MMA sits in TMEM with row i in lane i and column j in column j.
 #pragma once
 
@@ -120,6 +125,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
     d |= static_cast<uint64_t>(1) << 46;
     return d;
+}
+
+// K-major SWIZZLE_128B descriptor (layout_type [61,64) = 2): 8-row groups 1024 B apart; the leading
+// offset is not used when the MMA's K extent lies inside one 128-byte row (CUTLASS encodes 1)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// byte offset of element (r, k), k in [0, 32), inside a SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
+    return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + (k & 3) * 4);
 }
 
 // instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major

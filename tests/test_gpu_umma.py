@@ -50,9 +50,18 @@ def test_umma_selftest_variants(dev):
                    report["v%d_m0_N%d_K%d" % (v, N, K)]["rel"] < 5e-3
                    for N, K in ((128, 64), (64, 32), (256, 16), (32, 8)))]
     report["good_variants"] = good
+    # variant 2: SWIZZLE_128B layout (the one the attention kernel uses), K in whole 128-byte rows
+    for mode in (0, 1):
+        for N, K in ((128, 64), (64, 32), (256, 32), (32, 64)):
+            rel, err = run_selftest(dev, N, K, 2, mode)
+            report["v2_m%d_N%d_K%d" % (mode, N, K)] = {"rel": rel, "timeout": err}
+    sw_ok = all(report["v2_m1_N%d_K%d" % (N, K)]["rel"] < 1e-5 and report["v2_m0_N%d_K%d" % (N, K)]["rel"] < 5e-3
+                for N, K in ((128, 64), (64, 32), (256, 32), (32, 64)))
+    report["sw128_ok"] = sw_ok
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(report, open(os.path.join(ROOT, "gpurun_out", "umma_selftest.json"), "w"), indent=1)
     print(json.dumps(report, indent=1))
+    assert sw_ok, "SWIZZLE_128B descriptors do not reproduce the GEMM: %r" % report
     assert good == [0], "descriptor variant 0 (documented LBO/SBO meaning) does not reproduce the GEMM: %r" % report
     # one TF32 pass is NOT good enough for the 1e-5 bar; 3xTF32 is
     assert report["v0_m0_N128_K64"]["rel"] > 1e-5 > report["v0_m1_N128_K64"]["rel"]
