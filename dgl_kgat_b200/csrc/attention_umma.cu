@@ -296,10 +296,10 @@ extern "C" int kgat_umma_error_flag(void) {
 // Launcher used by kgat_attention_logits for d = rd = 64 (declared in attention.cu).
 int kgat_launch_att_logits_umma(const kgat_graph_t* g, const float* entity, const float* rel_emb, const float* W_R,
                                 float* logits_csr, cudaStream_t st) {
-    int* err_flag = nullptr;
-    KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&err_flag), g_umma_error));
+    static int* err_flag = nullptr;
     static bool configured = false;
     if (!configured) {
+        KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&err_flag), g_umma_error));
         KGAT_CUDA(cudaFuncSetAttribute(att_logits_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
         configured = true;

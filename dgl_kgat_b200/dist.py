@@ -51,12 +51,27 @@ class Partition:
         self.eid_out = np.flatnonzero((trip[:, 2] >= self.r0) & (trip[:, 2] < self.r1))    # tail owned: backward
         self.g_in = CKGraph(n_nodes, trip[self.eid_in], n_rel=n_rel)
         self.g_out = CKGraph(n_nodes, trip[self.eid_out], n_rel=n_rel)
+        # Global CSR order (rank of an edge under (head, rel, eid)) is the concatenation of the ranks'
+        # local CSR orders because ranks own contiguous head ranges.  csr_rank[e] = global CSR position.
+        order = np.argsort(trip[:, 0].astype(np.int64) * n_rel + trip[:, 1], kind="stable")
+        self.csr_rank = np.empty(trip.shape[0], dtype=np.int64)
+        self.csr_rank[order] = np.arange(trip.shape[0], dtype=np.int64)
+        # edge-count boundaries of the ranks inside the global CSR order
+        self.edge_bounds = np.searchsorted(trip[order, 0], self.bounds, side="left").astype(np.int64)
+        self.edge_bounds[-1] = trip.shape[0]
 
 
 def exchange_rows(buf: th.Tensor, bounds, group=None):
-    """All-gather of row ranges: rank k's rows ``bounds[k]:bounds[k+1]`` of ``buf`` are broadcast to
-    everyone, in place.  Ranges are uneven (edge-balanced), hence one broadcast per owner."""
-    for k in range(len(bounds) - 1):
+    """All-gather of row ranges, in place: rank k's rows ``bounds[k]:bounds[k+1]`` of ``buf`` reach
+    everyone.  Ranges are uneven (edge-balanced).  NCCL runs the uneven all-gather as ONE grouped
+    launch; gloo (CPU tests) has no uneven all-gather, so it gets one broadcast per owner."""
+    world = len(bounds) - 1
+    if tdist.get_backend(group) == "nccl":
+        rank = tdist.get_rank(group)
+        views = [buf[int(bounds[k]): int(bounds[k + 1])] for k in range(world)]
+        tdist.all_gather(views, views[rank], group=group)
+        return buf
+    for k in range(world):
         a, b = int(bounds[k]), int(bounds[k + 1])
         if b > a:
             tdist.broadcast(buf[a:b], src=tdist.get_global_rank(group, k) if group is not None else k, group=group)
@@ -94,28 +109,50 @@ class DistKGAT:
         self.part = Partition(n_nodes, triplets, n_rel, self.rank, self.world)
         self.dg_in = self.part.g_in.device_graph(self.device)
         self.dg_out = self.part.g_out.device_graph(self.device)
-        self._eid_in = th.from_numpy(self.part.eid_in).to(self.device)
-        self._eid_out = th.from_numpy(self.part.eid_out).to(self.device)
+        p = self.part
+        # positions (in the global CSR order) of: every edge by edge id, and this rank's out-edges in the
+        # order edge_weights() of the local out-graph expects them (its local edge-id order)
+        self._csr_rank = th.from_numpy(p.csr_rank).to(self.device)
+        self._out_rank = th.from_numpy(p.csr_rank[p.eid_out]).to(self.device)
         self.w_full = None
         self._plan = None
+        self._dw_views = None
 
     # attention-update mode ---------------------------------------------------------------
     def compute_attention(self):
-        """(E, 1) weights in original edge order on every rank (models.py:146-154)."""
+        """Attention refresh (models.py:146-154) on the partitioned graph; ``attention_weights()``
+        returns the (E, 1) tensor in original edge order when the caller wants it."""
         m, p = self.model, self.part
         with th.no_grad():
-            w_local, w_csr = ops.attention(self.dg_in, m.entity_embed.weight, m.relation_embed.weight, m.W_R,
-                                           rows=(p.r0, p.r1))
-            w_full = th.zeros(p.n_edges, 1, dtype=th.float32, device=self.device)
-            w_full[self._eid_in] = w_local
-            tdist.all_reduce(w_full, group=self.group)
-            _, w_csc = self.dg_out.edge_weights(w_full[self._eid_out])
-        self.w_full = w_full
+            _, w_csr = ops.attention(self.dg_in, m.entity_embed.weight, m.relation_embed.weight, m.W_R,
+                                     rows=(p.r0, p.r1), want_eid=False)
+            # one uneven all-gather assembles the weights of ALL edges in global CSR order
+            w_glob = th.empty(p.n_edges, dtype=th.float32, device=self.device)
+            w_glob[int(p.edge_bounds[self.rank]): int(p.edge_bounds[self.rank + 1])] = w_csr[: self.dg_in.n_edges]
+            exchange_rows(w_glob, p.edge_bounds, self.group)
+            _, w_csc = self.dg_out.edge_weights(w_glob[self._out_rank])
+        self._w_glob = w_glob
+        self.w_full = None
         self._plan = ops.PropagatePlan(
             self.dg_in, w_csr, w_csc, dg_bwd=self.dg_out, rows=(p.r0, p.r1),
             exchange=lambda t: exchange_rows(t, p.bounds, self.group),
-            reduce=lambda t: tdist.all_reduce(t, group=self.group))
-        return w_full
+            reduce=self._reduce_weight_grads)
+        return self
+
+    def attention_weights(self):
+        """(E, 1) weights in original edge order (what Model.compute_attention returns)."""
+        if self.w_full is None:
+            self.w_full = self._w_glob[self._csr_rank].unsqueeze(1)
+        return self.w_full
+
+    def _reduce_weight_grads(self, grads):
+        """ONE all-reduce for all layers' dW2 (called once per backward with the list of tensors)."""
+        flat = th.cat([g.reshape(-1) for g in grads])
+        tdist.all_reduce(flat, group=self.group)
+        off = 0
+        for g in grads:
+            g.copy_(flat[off: off + g.numel()].view_as(g))
+            off += g.numel()
 
     # CF-embedding mode -------------------------------------------------------------------
     def gnn(self, drop_masks=None):

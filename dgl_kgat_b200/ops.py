@@ -21,7 +21,7 @@ def _f32c(t: th.Tensor, device) -> th.Tensor:
     return t.contiguous()
 
 
-def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Tensor, rows=None):
+def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Tensor, rows=None, want_eid=True):
     """Logits + per-destination softmax (reference models.py:146-154).
 
     Returns ``(w_eid, w_csr)``: ``w_eid`` is the (E, 1) tensor ``compute_attention``
@@ -36,8 +36,10 @@ def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Te
     E = max(dg.n_edges, 1)
     logits = th.empty(E, dtype=th.float32, device=dev)
     w_csr = th.empty(E, dtype=th.float32, device=dev)
-    w_eid = th.zeros(dg.n_edges, 1, dtype=th.float32, device=dev) if rows is not None else \
-        th.empty(dg.n_edges, 1, dtype=th.float32, device=dev)
+    w_eid = None
+    if want_eid:
+        w_eid = th.zeros(dg.n_edges, 1, dtype=th.float32, device=dev) if rows is not None else \
+            th.empty(dg.n_edges, 1, dtype=th.float32, device=dev)
     r0, r1 = (0, dg.n_nodes) if rows is None else rows
     with th.cuda.device(dev):
         st = _lib.stream_ptr()
@@ -46,7 +48,8 @@ def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Te
                                                  d, rd, logits.data_ptr(), st), "kgat_attention_logits")
         with _lib.record("segment_softmax"):
             _lib.check(lib.kgat_segment_softmax(dg.ref, r0, r1, logits.data_ptr(), w_csr.data_ptr(),
-                                                w_eid.data_ptr() if dg.n_edges else None, st), "kgat_segment_softmax")
+                                                w_eid.data_ptr() if (want_eid and dg.n_edges) else None, st),
+                       "kgat_segment_softmax")
     return w_eid, w_csr
 
 
@@ -196,7 +199,6 @@ class Propagate(th.autograd.Function):
                         dx.data_ptr(), dh.data_ptr(), dW.data_ptr(), part.data_ptr(), st), "kgat_layer_bwd")
                 if plan.distributed:
                     plan.exchange(dh)                   # dh_nb rows of every rank feed the transposed gather below
-                    plan.reduce(dW)
                 d_weights[l] = dW
                 nxt_dx, nxt_dh = dx, dh
             d_entity = None
@@ -208,6 +210,8 @@ class Propagate(th.autograd.Function):
                                                   dims[0], d_entity.data_ptr(), st), "kgat_input_bwd")
                 if plan.distributed:
                     plan.exchange(d_entity)             # replicated parameters: every rank needs the full gradient
+            if plan.distributed:
+                plan.reduce(d_weights)                  # one all-reduce for every layer's dW2
         return (None, None, None, None, d_entity, *d_weights)
 
 

@@ -557,3 +557,31 @@ def test_gnn_with_two_consumers_of_the_embedding(dev, golden_small):
     for i in range(3):
         assert max_rel(m.layers[i].res_fc_2.weight.grad.cpu().numpy(),
                        leaves["layers.%d.res_fc_2.weight" % i].grad.numpy()) < RTOL
+
+
+def test_graphed_cf_step_matches_eager(dev):
+    """graphed.GraphedCFStep replays the same numbers as the eager public calls."""
+    from dgl_kgat_b200.graphed import GraphedCFStep
+    dl = DataLoader.from_synthetic("tiny")
+    m = make_model(dl.n_KG_entity, dl.n_KG_relation, dev)
+    g = dl.train_g
+    g.ndata["id"] = g.ndata["id"].to(dev)
+    rng = np.random.default_rng(0)
+    U, I = dl.n_users, dl.n_items
+    batches = [[th.as_tensor(rng.integers(lo, hi, 4096)) for lo, hi in ((0, U), (U, U + I), (U, U + I))]
+               for _ in range(3)]
+    step = GraphedCFStep(m, g, 4096, refresh_attention=True)
+    for b in batches:
+        loss_g = step(*b).item()
+        grads_g = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        m.zero_grad(set_to_none=True)
+        with th.no_grad():
+            g.edata["w"] = m.compute_attention(g)
+        emb = m.gnn(g, g.ndata["id"])
+        loss = m.get_loss(emb, *[x.to(dev) for x in b])
+        loss.backward()
+        assert loss.item() == loss_g
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                assert th.equal(p.grad, grads_g[k]), k
+        m.zero_grad(set_to_none=True)
