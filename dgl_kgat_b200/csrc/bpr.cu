@@ -70,14 +70,15 @@ bpr_finish_kernel(const double* __restrict__ partial, int n_blocks, int B, float
     if (threadIdx.x == 0) loss[0] = static_cast<float>(s_a[0] / B + static_cast<double>(lambda) * s_r[0] / B);
 }
 
+// key = node id of slot i, or n_nodes (sorts last, skipped) when the node is not owned by this rank
 __global__ void bpr_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ pos,
-                                const int64_t* __restrict__ neg, int B, uint32_t* __restrict__ keys,
-                                int32_t* __restrict__ vals) {
+                                const int64_t* __restrict__ neg, int B, int64_t own_begin, int64_t own_end,
+                                int64_t n_nodes, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * B) return;
     const int role = i / B, b = i - role * B;
     const int64_t id = role == 0 ? src[b] : (role == 1 ? pos[b] : neg[b]);
-    keys[i] = static_cast<uint32_t>(id);
+    keys[i] = static_cast<uint32_t>((id >= own_begin && id < own_end) ? id : n_nodes);
     vals[i] = i;
 }
 
@@ -86,14 +87,14 @@ __global__ void __launch_bounds__(BPR_THREADS)
 bpr_bwd_kernel(const float* __restrict__ emb, int64_t stride, int dim, const int64_t* __restrict__ src,
                const int64_t* __restrict__ pos, const int64_t* __restrict__ neg, int B, float lambda,
                const float* __restrict__ sig, const float* __restrict__ grad_loss,
-               const uint32_t* __restrict__ keys, const int32_t* __restrict__ slots,
+               const uint32_t* __restrict__ keys, const int32_t* __restrict__ slots, uint32_t n_nodes,
                float* __restrict__ rows, int64_t rows_stride, int32_t* __restrict__ row_slot,
                int32_t* __restrict__ rows_node) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * BPR_WARPS + warp;
     if (i >= 3 * B) return;
     const uint32_t node = keys[i];
-    const bool head = i == 0 || keys[i - 1] != node;
+    const bool head = (i == 0 || keys[i - 1] != node) && node < n_nodes;     // node == n_nodes: not owned
     if (!head) {
         if (lane == 0) rows_node[i] = -1;
         return;
@@ -198,9 +199,13 @@ extern "C" int kgat_bpr_loss_fwd(const float* emb, int64_t emb_stride, int dim, 
 
 extern "C" int kgat_bpr_loss_bwd(const float* emb, int64_t emb_stride, int dim, const int64_t* src,
                                  const int64_t* pos, const int64_t* neg, int64_t batch, float reg_lambda,
-                                 const float* sig, const float* grad_loss, int64_t n_nodes,
+                                 const float* sig, const float* grad_loss,
+                                 const int64_t* node_src, const int64_t* node_pos, const int64_t* node_neg,
+                                 int64_t own_begin, int64_t own_end, int64_t n_nodes,
                                  float* rows, int32_t* rows_node, int32_t* row_slot,
                                  void* workspace, size_t workspace_bytes, kgat_stream_t stream) {
+    KGAT_REQUIRE((node_src == nullptr) == (node_pos == nullptr) && (node_src == nullptr) == (node_neg == nullptr));
+    KGAT_REQUIRE(own_begin >= 0 && own_end <= n_nodes && own_begin <= own_end && n_nodes < (int64_t(1) << 31));
     KGAT_REQUIRE(emb && src && pos && neg && sig && grad_loss && rows && rows_node && row_slot && workspace);
     KGAT_REQUIRE(batch > 0 && batch < (int64_t(1) << 28) && n_nodes > 0 && aligned16(emb) && aligned16(rows) &&
                  emb_stride % 4 == 0);
@@ -215,14 +220,17 @@ extern "C" int kgat_bpr_loss_bwd(const float* emb, int64_t emb_stride, int dim, 
     int32_t* va = reinterpret_cast<int32_t*>(ws + w.vals_a);
     int32_t* vb = reinterpret_cast<int32_t*>(ws + w.vals_b);
     KGAT_CUDA(cudaMemsetAsync(row_slot, 0xff, sizeof(int32_t) * n_nodes, st));          // -1 everywhere
-    bpr_keys_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(src, pos, neg, B, ka, va);
+    bpr_keys_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(node_src ? node_src : src, node_pos ? node_pos : pos,
+                                                         node_neg ? node_neg : neg, B, own_begin, own_end, n_nodes,
+                                                         ka, va);
     KGAT_LAUNCH_CHECK();
     int bits = 1;
-    while (bits < 32 && (static_cast<uint64_t>(n_nodes) >> bits) != 0) ++bits;
+    while (bits < 32 && (static_cast<uint64_t>(n_nodes) >> bits) != 0) ++bits;      // keys go up to n_nodes
     size_t bytes = w.cub_bytes;
     KGAT_CUDA(cub::DeviceRadixSort::SortPairs(ws + w.cub, bytes, ka, kb, va, vb, 3 * B, 0, bits, st));
     bpr_bwd_kernel<<<(3 * B + BPR_WARPS - 1) / BPR_WARPS, BPR_THREADS, 0, st>>>(
-        emb, emb_stride, dim, src, pos, neg, B, reg_lambda, sig, grad_loss, kb, vb, rows, dim, row_slot, rows_node);
+        emb, emb_stride, dim, src, pos, neg, B, reg_lambda, sig, grad_loss, kb, vb, static_cast<uint32_t>(n_nodes), rows,
+        dim, row_slot, rows_node);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }

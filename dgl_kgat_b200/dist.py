@@ -165,13 +165,11 @@ class DistKGAT:
         return ops.propagate(self._plan, masks, False, m.entity_embed.weight, *weights)
 
     def get_loss(self, embedding, src_ids, pos_dst_ids, neg_dst_ids):
-        """BPR loss of models.py:170-178 on rows gathered from their owners; replicated value."""
-        B = src_ids.numel()
-        ids = th.cat([src_ids, pos_dst_ids, neg_dst_ids])
-        rows = _BatchRows.apply(embedding, ids, self.part.r0, self.part.r1, self.group)
-        table = rows            # (3B, d): rows [0,B) sources, [B,2B) positives, [2B,3B) negatives
-        ar = th.arange(B, device=ids.device)
-        return self.model.get_loss(table, ar, ar + B, ar + 2 * B)
+        """BPR loss of models.py:170-178 on rows gathered from their owners; replicated value.  The
+        gradient stays compact and local (ops.DistBprLoss)."""
+        return ops.DistBprLoss.apply(embedding, src_ids, pos_dst_ids, neg_dst_ids, self.model._reg_lambda_gnn,
+                                     getattr(embedding, "_kgat_channel", None), (self.part.r0, self.part.r1),
+                                     self.group)
 
     def full_embedding(self, embedding):
         with th.no_grad():

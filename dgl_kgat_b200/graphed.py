@@ -43,6 +43,8 @@ class GraphedCFStep:
             self.graph = th.cuda.CUDAGraph()
             with th.cuda.graph(self.graph):
                 self.loss = self._body()
+            # the graph writes the gradients into these static tensors on every replay
+            self._grads = [(p, p.grad) for p in model.parameters() if p.grad is not None]
 
     def _body(self):
         m, g = self.model, self.g
@@ -61,4 +63,6 @@ class GraphedCFStep:
         for dst, src in zip(self.ids, (src_ids, pos_ids, neg_ids)):
             dst.copy_(th.as_tensor(src), non_blocking=True)
         self.graph.replay()
+        for p, g in self._grads:            # re-attach in case the caller cleared .grad (zero_grad(set_to_none))
+            p.grad = g
         return self.loss

@@ -215,57 +215,107 @@ class Propagate(th.autograd.Function):
         return (None, None, None, None, d_entity, *d_weights)
 
 
+def _bpr_forward(table, ids, reg_lambda):
+    """Launch the fused forward on ``table`` rows addressed by the three int64 id vectors."""
+    lib = _lib.load()
+    dev = table.device
+    B, dim = ids[0].numel(), table.shape[1]
+    ws_bytes = lib.kgat_bpr_workspace_bytes(B)
+    ws = th.empty(ws_bytes, dtype=th.uint8, device=dev)
+    loss = th.empty((), dtype=th.float32, device=dev)
+    sig = th.empty(B, dtype=th.float32, device=dev)
+    with th.cuda.device(dev):
+        with _lib.record("bpr_loss_fwd", 2):
+            _lib.check(lib.kgat_bpr_loss_fwd(table.data_ptr(), table.stride(0), dim, ids[0].data_ptr(), ids[1].data_ptr(),
+                                             ids[2].data_ptr(), B, float(reg_lambda), loss.data_ptr(), sig.data_ptr(),
+                                             ws.data_ptr(), ws_bytes, _lib.stream_ptr()), "kgat_bpr_loss_fwd")
+    return loss, sig, ws
+
+
+def _bpr_backward(table, ids, node_ids, own, n_nodes, reg_lambda, sig, grad_loss, ws):
+    """Compact gradient (rows, rows_node, row_slot) w.r.t. the (n_nodes, dim) embedding."""
+    lib = _lib.load()
+    dev = table.device
+    B, dim = ids[0].numel(), table.shape[1]
+    g = grad_loss.to(device=dev, dtype=th.float32).contiguous()
+    rows = th.empty(3 * B, dim, dtype=th.float32, device=dev)
+    rows_node = th.empty(3 * B, dtype=th.int32, device=dev)
+    row_slot = th.empty(n_nodes, dtype=th.int32, device=dev)
+    nptr = [None] * 3 if node_ids is None else [t.data_ptr() for t in node_ids]
+    with th.cuda.device(dev):
+        with _lib.record("bpr_loss_bwd", 6):
+            _lib.check(lib.kgat_bpr_loss_bwd(table.data_ptr(), table.stride(0), dim, ids[0].data_ptr(), ids[1].data_ptr(),
+                                             ids[2].data_ptr(), B, float(reg_lambda), sig.data_ptr(), g.data_ptr(),
+                                             nptr[0], nptr[1], nptr[2], own[0], own[1], n_nodes,
+                                             rows.data_ptr(), rows_node.data_ptr(), row_slot.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "kgat_bpr_loss_bwd")
+    return rows, rows_node, row_slot
+
+
+def _deliver_compact(channel, compact, shape, dev):
+    """Park the compact gradient on the channel (zero-stride sentinel for autograd) or densify it."""
+    rows, rows_node, row_slot = compact
+    if channel is not None and channel.compact is None:
+        channel.compact = (rows, row_slot, rows_node)
+        return th.zeros(1, 1, dtype=th.float32, device=dev).expand(*shape)
+    valid = rows_node >= 0
+    grad = th.zeros(*shape, dtype=th.float32, device=dev)
+    grad.index_add_(0, rows_node[valid].long(), rows[valid])
+    return grad
+
+
 class BprLoss(th.autograd.Function):
     """Fused BPR loss head (reference models.py:170-178): forward = gather + dots + logsigmoid +
     L2 terms in one kernel; backward = compact, deterministic row gradient (see GradChannel)."""
 
     @staticmethod
     def forward(ctx, embedding, src, pos, neg, reg_lambda, channel):
-        lib = _lib.load()
         dev = embedding.device
         emb = _f32c(embedding, dev)
         ids = [i.to(device=dev, dtype=th.int64).contiguous().view(-1) for i in (src, pos, neg)]
-        B, dim = ids[0].numel(), emb.shape[1]
-        if ids[1].numel() != B or ids[2].numel() != B:
+        if ids[1].numel() != ids[0].numel() or ids[2].numel() != ids[0].numel():
             raise _lib.KgatError("get_loss: id vectors differ in length")
-        ws_bytes = lib.kgat_bpr_workspace_bytes(B)
-        ws = th.empty(ws_bytes, dtype=th.uint8, device=dev)
-        loss = th.empty((), dtype=th.float32, device=dev)
-        sig = th.empty(B, dtype=th.float32, device=dev)
-        with th.cuda.device(dev):
-            with _lib.record("bpr_loss_fwd", 2):
-                _lib.check(lib.kgat_bpr_loss_fwd(emb.data_ptr(), emb.stride(0), dim, ids[0].data_ptr(), ids[1].data_ptr(),
-                                                 ids[2].data_ptr(), B, float(reg_lambda), loss.data_ptr(), sig.data_ptr(),
-                                                 ws.data_ptr(), ws_bytes, _lib.stream_ptr()), "kgat_bpr_loss_fwd")
+        loss, sig, ws = _bpr_forward(emb, ids, reg_lambda)
         ctx.emb, ctx.ids, ctx.sig, ctx.lam, ctx.channel, ctx.ws = emb, ids, sig, float(reg_lambda), channel, ws
         return loss
 
     @staticmethod
     def backward(ctx, grad_loss):
-        lib = _lib.load()
-        emb, ids = ctx.emb, ctx.ids
-        dev = emb.device
-        B, (N, dim) = ids[0].numel(), emb.shape
-        g = grad_loss.to(device=dev, dtype=th.float32).contiguous()
-        rows = th.empty(3 * B, dim, dtype=th.float32, device=dev)
-        rows_node = th.empty(3 * B, dtype=th.int32, device=dev)
-        row_slot = th.empty(N, dtype=th.int32, device=dev)
-        ws = ctx.ws
-        with th.cuda.device(dev):
-            with _lib.record("bpr_loss_bwd", 6):
-                _lib.check(lib.kgat_bpr_loss_bwd(emb.data_ptr(), emb.stride(0), dim, ids[0].data_ptr(), ids[1].data_ptr(),
-                                                 ids[2].data_ptr(), B, ctx.lam, ctx.sig.data_ptr(), g.data_ptr(), N,
-                                                 rows.data_ptr(), rows_node.data_ptr(), row_slot.data_ptr(),
-                                                 ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "kgat_bpr_loss_bwd")
-        ch = ctx.channel
-        if ch is not None and ch.compact is None:
-            ch.compact = (rows, row_slot, rows_node)
-            grad_emb = th.zeros(1, 1, dtype=th.float32, device=dev).expand(N, dim)
-        else:
-            valid = rows_node >= 0
-            grad_emb = th.zeros(N, dim, dtype=th.float32, device=dev)
-            grad_emb.index_add_(0, rows_node[valid].long(), rows[valid])
-        return grad_emb, None, None, None, None, None
+        emb = ctx.emb
+        N = emb.shape[0]
+        compact = _bpr_backward(emb, ctx.ids, None, (0, N), N, ctx.lam, ctx.sig, grad_loss, ctx.ws)
+        return _deliver_compact(ctx.channel, compact, emb.shape, emb.device), None, None, None, None, None
+
+
+class DistBprLoss(th.autograd.Function):
+    """The same loss on a destination-partitioned embedding: every batch row is contributed by its
+    owner and summed over ranks (one all-reduce of the (3B, dim) table), the loss is replicated, and the
+    backward needs no communication - each rank keeps the gradient rows of the nodes it owns."""
+
+    @staticmethod
+    def forward(ctx, embedding, src, pos, neg, reg_lambda, channel, own, group):
+        import torch.distributed as tdist
+        dev = embedding.device
+        emb = _f32c(embedding, dev)
+        node_ids = [i.to(device=dev, dtype=th.int64).contiguous().view(-1) for i in (src, pos, neg)]
+        B = node_ids[0].numel()
+        cat = th.cat(node_ids)
+        mine = ((cat >= own[0]) & (cat < own[1])).unsqueeze(1)
+        table = emb.index_select(0, cat) * mine
+        tdist.all_reduce(table, group=group)
+        ar = th.arange(B, device=dev)
+        ids = [ar, ar + B, ar + 2 * B]
+        loss, sig, ws = _bpr_forward(table, ids, reg_lambda)
+        ctx.table, ctx.ids, ctx.node_ids, ctx.sig, ctx.ws = table, ids, node_ids, sig, ws
+        ctx.lam, ctx.channel, ctx.own, ctx.shape = float(reg_lambda), channel, own, emb.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        compact = _bpr_backward(ctx.table, ctx.ids, ctx.node_ids, ctx.own, ctx.shape[0], ctx.lam, ctx.sig,
+                                grad_loss, ctx.ws)
+        grad = _deliver_compact(ctx.channel, compact, ctx.shape, ctx.table.device)
+        return grad, None, None, None, None, None, None, None
 
 
 def bpr_loss(embedding, src, pos, neg, reg_lambda):

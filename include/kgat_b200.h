@@ -172,6 +172,9 @@ KGAT_API int kgat_input_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t ro
  * bwd writes the gradient w.r.t. emb COMPACT: rows[i,:] for the sorted positions i that start a run of
  * equal node ids (rows_node[i] = node id, -1 for the other positions) and row_slot[node] = i, -1 for
  * untouched nodes; rows is (3*batch, dim).  grad_loss: device scalar, the upstream gradient.
+ * Multi-GPU: emb may be the (3*batch, dim) table of rows gathered from their owners, indexed by
+ * src/pos/neg = positions in that table, while node_src/node_pos/node_neg (null = same as src/pos/neg)
+ * give the graph node of every slot; only nodes in [own_begin, own_end) receive a gradient row.
  * Deterministic (sorted, fixed-order accumulation; no atomics). */
 KGAT_API size_t kgat_bpr_workspace_bytes(int64_t batch);
 KGAT_API int kgat_bpr_loss_fwd(const float* emb, int64_t emb_stride, int dim, const int64_t* src,
@@ -180,7 +183,9 @@ KGAT_API int kgat_bpr_loss_fwd(const float* emb, int64_t emb_stride, int dim, co
                       kgat_stream_t stream);
 KGAT_API int kgat_bpr_loss_bwd(const float* emb, int64_t emb_stride, int dim, const int64_t* src,
                       const int64_t* pos, const int64_t* neg, int64_t batch, float reg_lambda,
-                      const float* sig, const float* grad_loss, int64_t n_nodes,
+                      const float* sig, const float* grad_loss,
+                      const int64_t* node_src, const int64_t* node_pos, const int64_t* node_neg,
+                      int64_t own_begin, int64_t own_end, int64_t n_nodes,
                       float* rows, int32_t* rows_node, int32_t* row_slot,
                       void* workspace, size_t workspace_bytes, kgat_stream_t stream);
 
