@@ -286,11 +286,15 @@ __device__ int g_umma_error = 0;      // set when a tensor-core completion barri
 
 using namespace kgat;
 
+int kgat_eval_umma_error_take();
+
 extern "C" int kgat_umma_error_flag(void) {
     int v = 0, zero = 0;
     if (cudaMemcpyFromSymbol(&v, g_umma_error, sizeof(int)) != cudaSuccess) return KGAT_ERR_CUDA;
     if (v != 0) cudaMemcpyToSymbol(g_umma_error, &zero, sizeof(int));
-    return v;
+    const int e = kgat_eval_umma_error_take();
+    if (e < 0) return e;
+    return (v != 0 || e != 0) ? 1 : 0;
 }
 
 // Launcher used by kgat_attention_logits for d = rd = 64 (declared in attention.cu).

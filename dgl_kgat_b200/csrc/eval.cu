@@ -1,5 +1,6 @@
 // (5) Full-rank user x item scoring with a fused per-row top-K.
 //
+// fp32 FFMA version (K > 32, dim > 256, or KGAT_EVAL_IMPL=ffma); the tensor-core version is eval_umma.cu.
 // Replaces the per-user Python loop of the reference (metric.py:44-51): gather the item matrix,
 // emb_u @ emb_items^T, score[train items] = 0.0, full descending sort.  Here one CTA owns BM eval
 // users and walks the item axis in BN-wide tiles: an fp32 register-tiled GEMM produces a BM x BN
@@ -134,6 +135,20 @@ score_topk_kernel(const float* __restrict__ emb, int64_t stride, int dim,
 
 using namespace kgat;
 
+#include <cstdlib>
+#include <cstring>
+
+int kgat_launch_score_topk_umma(const float* emb, int64_t emb_stride, int dim, const int32_t* user_ids, int n_users,
+                                const int32_t* item_ids, int n_items, const int32_t* mask_ptr,
+                                const int32_t* mask_items, int K, int32_t* topk_idx, float* topk_score,
+                                cudaStream_t st);
+
+// KGAT_EVAL_IMPL=ffma selects the fp32 FFMA tile kernel instead of the tcgen05 3xTF32 kernel (A/B runs).
+static bool eval_use_umma() {
+    const char* e = std::getenv("KGAT_EVAL_IMPL");
+    return !(e && std::strcmp(e, "ffma") == 0);
+}
+
 extern "C" int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
                                const int32_t* user_ids, int64_t n_users,
                                const int32_t* item_ids, int64_t n_items,
@@ -145,6 +160,10 @@ extern "C" int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
     KGAT_REQUIRE(aligned16(emb) && emb_stride % 4 == 0);
     if (dim <= 0 || dim % 4 != 0 || K <= 0 || K > MAX_K) return KGAT_ERR_UNSUPPORTED_DIM;
     if (n_users == 0) return KGAT_OK;
+    if (dim <= 256 && K <= 32 && eval_use_umma())
+        return kgat_launch_score_topk_umma(emb, emb_stride, dim, user_ids, static_cast<int>(n_users), item_ids,
+                                           static_cast<int>(n_items), mask_ptr, mask_items, K, topk_idx, topk_score,
+                                           as_stream(stream));
     const size_t smem = sizeof(float) * (2 * BK * LDT + BM * (BN + 1)) + (sizeof(float) + sizeof(int)) * BM * K + 16;
     static size_t configured = 0;
     if (smem > configured) {

@@ -1,0 +1,288 @@
+// (5) Full-rank user x item scoring on the tensor cores with a fused per-row top-K.
+//
+// Replaces the per-user loop of the reference (metric.py:44-59).  score[u, i] = <emb[user u], emb[item i]>
+// is a (U x dim) x (dim x I) GEMM (620 GFLOP at Amazon-book shape); it runs as a tcgen05 3xTF32 GEMM
+// (fp32 accumulate in TMEM) so that the ranking keeps fp32 accuracy (a single TF32 pass would reorder
+// near-ties).  One CTA owns 128 eval users and walks all item tiles of 128 items; the U x I score
+// matrix never leaves TMEM.
+//   producers (warps 0-7)  per K-block of 32 features: gather the 128 user rows and the 128 item rows
+//            (8 lanes read one row's contiguous 128 bytes), split x = hi + lo, store U_hi, U_lo, I_hi,
+//            I_lo as SWIZZLE_128B tiles; 3-stage ring, next stage's loads in flight during the split.
+//   MMA      (warp 12, one lane) per K-block: U_hi x [I_hi ; I_lo] (N = 256) and U_lo x I_hi (N = 128):
+//            columns 0..127 accumulate hi*hi + lo*hi, columns 128..255 hi*lo; two accumulator buffers.
+//   epilogue (warps 8-11)  thread = user row: tcgen05.ld, score = c[i] + c[128 + i], train items forced to
+//            0.0 (metric.py:50), strict-greater insertion into the row's sorted top-K list in shared
+//            memory (items arrive in ascending order, so ties keep the lower index first).
+#include <limits.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace kgat {
+namespace {
+
+constexpr int TM = 128, TN = 128, KB = 32;
+constexpr int N_PROD = 256, N_EPI = 128, THREADS = N_PROD + N_EPI + 32, MMA_WARP = 12;
+constexpr int STAGES = 3;
+constexpr int K_MAX = 32;                               // largest top-K this kernel keeps in shared memory
+constexpr uint32_t ARR_BYTES = 128 * KB * 4;            // 16 KB
+constexpr uint32_t STAGE_BYTES = 4 * ARR_BYTES;         // U_hi, U_lo, I_hi, I_lo
+constexpr uint32_t TMEM_COLS = 512;                     // 2 buffers x 256 columns
+
+struct Smem {
+    unsigned char A[STAGES][STAGE_BYTES];
+    float ls[TM * K_MAX];
+    int li[TM * K_MAX];
+    uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    volatile int abort_flag;
+    volatile int epi_abort;
+};
+static_assert(sizeof(Smem) <= 232448 - 1024, "shared-memory budget");
+
+__global__ void __launch_bounds__(THREADS, 1)
+score_topk_umma_kernel(const float* __restrict__ emb, int64_t stride, int dim,
+                       const int32_t* __restrict__ user_ids, int n_users,
+                       const int32_t* __restrict__ item_ids, int n_items,
+                       const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items, int K,
+                       int32_t* __restrict__ topk_idx, float* __restrict__ topk_score, int* __restrict__ err) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int u0 = blockIdx.x * TM;
+    const int n_it = (n_items + TN - 1) / TN;           // item tiles
+    const int n_kb = (dim + KB - 1) / KB;                // K-blocks per tile
+    const int total = n_it * n_kb;                       // stages this CTA streams
+
+    if (warp == MMA_WARP) umma::tmem_alloc(&s.tmem_base, TMEM_COLS);
+    if (tid == 32) {
+        for (int i = 0; i < STAGES; ++i) {
+            umma::mbar_init(&s.full[i], N_PROD);
+            umma::mbar_init(&s.empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&s.acc_full[i], 1);
+            umma::mbar_init(&s.acc_empty[i], N_EPI);
+        }
+        umma::fence_barrier_init();
+        s.abort_flag = 0;
+        s.epi_abort = 0;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = s.tmem_base;
+
+    if (warp < 8) {
+        // =========================================================== producers
+        const int c = lane & 7, rsub = lane >> 3;
+        const bool is_user = warp < 4;
+        const int row_base = (warp & 3) * 32 + rsub;                     // rows row_base + 4 * j, j = 0..7
+        uint32_t st_base[2];
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+            const int rr = par * 4 + rsub;
+            st_base[par] = (is_user ? 0u : 2u * ARR_BYTES) + ((warp & 3) * 4) * 1024 + rr * 128 + ((c ^ rr) << 4);
+        }
+        const float* __restrict__ emb_c = emb + c * 4;
+        int ids[8], ids_next[8];
+        float4 va[8], vb[8];
+
+        auto load_ids = [&](int it, int* dst) {          // embedding rows of this thread's 8 tile rows
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int rl = row_base + 4 * j;
+                if (is_user) dst[j] = u0 + rl < n_users ? __ldg(user_ids + u0 + rl) : -1;
+                else dst[j] = (it < n_it && it * TN + rl < n_items) ? __ldg(item_ids + it * TN + rl) : -1;
+            }
+        };
+        auto issue = [&](float4* v, int kb) {
+            const bool col_ok = kb * KB + c * 4 < dim;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = (ids[j] >= 0 && col_ok) ? ldg4(emb_c + static_cast<size_t>(ids[j]) * stride + kb * KB)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto store = [&](const float4* v, int stage) {
+            unsigned char* base = s.A[stage];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t off = st_base[j & 1] + (j >> 1) * 1024;
+                float4 hi, lo;
+                umma::split_tf32(v[j].x, hi.x, lo.x);
+                umma::split_tf32(v[j].y, hi.y, lo.y);
+                umma::split_tf32(v[j].z, hi.z, lo.z);
+                umma::split_tf32(v[j].w, hi.w, lo.w);
+                *reinterpret_cast<float4*>(base + off) = hi;
+                *reinterpret_cast<float4*>(base + ARR_BYTES + off) = lo;
+            }
+        };
+        // stage n = (item tile n / n_kb, K-block n % n_kb); smem slot n % STAGES, use count n / STAGES
+        int kb_next = 0, it_next = 0;                    // coordinates of the NEXT stage to issue
+        auto advance_issue = [&](float4* v) {            // put the loads of stage (it_next, kb_next) in flight
+            if (kb_next == 0 && !is_user && it_next > 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ids[j] = ids_next[j];
+            }
+            issue(v, kb_next);
+            if (kb_next == 0 && !is_user) load_ids(it_next + 1, ids_next);   // a whole tile ahead
+            if (++kb_next == n_kb) { kb_next = 0; ++it_next; }
+        };
+        auto commit_stage = [&](const float4* v, int slot, int use) {
+            if (!umma::mbar_wait(&s.empty[slot], (use & 1) ^ 1)) s.abort_flag = 1;
+            store(v, slot);
+            umma::fence_proxy_async();
+            umma::mbar_arrive(&s.full[slot]);
+        };
+
+        if (total > 0) {
+            load_ids(0, ids);
+            advance_issue(va);                            // stage 0
+            int slot = 0, use = 0;
+            for (int n = 0; n < total && !s.abort_flag; n += 2) {
+                if (n + 1 < total) advance_issue(vb);
+                commit_stage(va, slot, use);
+                if (++slot == STAGES) { slot = 0; ++use; }
+                if (n + 1 < total) {
+                    if (n + 2 < total) advance_issue(va);
+                    commit_stage(vb, slot, use);
+                    if (++slot == STAGES) { slot = 0; ++use; }
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // =========================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc256 = umma::make_idesc_tf32(TM, 256), idesc128 = umma::make_idesc_tf32(TM, 128);
+            int slot = 0, use = 0;
+            for (int it = 0; it < n_it && !s.abort_flag; ++it) {
+                const int buf = it & 1;
+                if (!umma::mbar_wait(&s.acc_empty[buf], ((it >> 1) & 1) ^ 1)) s.abort_flag = 1;
+                umma::fence_after_sync();
+                const uint32_t tD = tmem + buf * 256;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    if (!umma::mbar_wait(&s.full[slot], use & 1)) s.abort_flag = 1;
+                    umma::fence_after_sync();
+                    const uint32_t aU = umma::smem_u32(s.A[slot]), bI = aU + 2 * ARR_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < KB / 8; ++ks) {
+                        const uint32_t off = ks * 32;
+                        const uint64_t dB = umma::make_smem_desc_sw128(bI + off);     // rows 0..127 I_hi, 128..255 I_lo
+                        umma::mma_tf32(tD, umma::make_smem_desc_sw128(aU + off), dB, idesc256, (kb | ks) != 0);
+                        umma::mma_tf32(tD, umma::make_smem_desc_sw128(aU + ARR_BYTES + off), dB, idesc128, 1);
+                    }
+                    umma::mma_commit(&s.empty[slot]);
+                    if (++slot == STAGES) { slot = 0; ++use; }
+                }
+                umma::mma_commit(&s.acc_full[buf]);
+            }
+        }
+    } else {
+        // =========================================================== epilogue (warps 8..11): mask + top-K
+        const int q = warp & 3, row = q * 32 + lane, et = tid - N_PROD;
+        const bool sel = u0 + row < n_users;
+        int cnt = 0, mp = 0, mend = 0, next_mask = INT_MAX;
+        float thr = -INFINITY;
+        if (sel && mask_ptr) {
+            mp = mask_ptr[u0 + row];
+            mend = mask_ptr[u0 + row + 1];
+            next_mask = (mp < mend && mask_items) ? mask_items[mp] : INT_MAX;
+        }
+        float* myLs = s.ls + row * K;
+        int* myLi = s.li + row * K;
+        for (int it = 0; it < n_it; ++it) {
+            const int buf = it & 1;
+            if (!umma::mbar_wait(&s.acc_full[buf], (it >> 1) & 1)) { s.abort_flag = 1; s.epi_abort = 1; }
+            if (et == 0 && s.abort_flag) s.epi_abort = 1;
+            umma::fence_after_sync();
+            asm volatile("bar.sync 1, %0;" ::"n"(N_EPI) : "memory");
+            if (s.epi_abort) break;
+            const uint32_t ta = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TN; c0 += 16) {
+                float a[16], b[16];
+                umma::tmem_ld16(ta + c0, a);
+                umma::tmem_ld16(ta + 128 + c0, b);
+                umma::tmem_ld_wait();
+                if (sel) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int item = it * TN + c0 + i;
+                        if (item < n_items) {
+                            float sc = a[i] + b[i];
+                            if (item == next_mask) {            // train item: score forced to 0.0 (metric.py:50)
+                                sc = 0.0f;
+                                do {
+                                    ++mp;
+                                    next_mask = mp < mend ? mask_items[mp] : INT_MAX;
+                                } while (next_mask == item);
+                            }
+                            if (cnt < K || sc > thr) {
+                                int p = cnt < K ? cnt : K - 1;
+                                while (p > 0 && myLs[p - 1] < sc) {
+                                    myLs[p] = myLs[p - 1];
+                                    myLi[p] = myLi[p - 1];
+                                    --p;
+                                }
+                                myLs[p] = sc;
+                                myLi[p] = item;
+                                if (cnt < K) ++cnt;
+                                if (cnt == K) thr = myLs[K - 1];
+                            }
+                        }
+                    }
+                }
+            }
+            umma::fence_before_sync();
+            umma::mbar_arrive(&s.acc_empty[buf]);
+        }
+        if (sel && !s.epi_abort) {
+            for (int p = 0; p < K; ++p) {
+                const bool ok = p < cnt;
+                topk_idx[static_cast<size_t>(u0 + row) * K + p] = ok ? myLi[p] : -1;
+                if (topk_score) topk_score[static_cast<size_t>(u0 + row) * K + p] = ok ? myLs[p] : -INFINITY;
+            }
+        }
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid == 0 && s.abort_flag) atomicExch(err, 1);
+    if (warp == MMA_WARP) umma::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+__device__ int g_eval_umma_error = 0;     // set when a tensor-core completion barrier timed out
+
+}  // namespace
+}  // namespace kgat
+
+using namespace kgat;
+
+// read-and-clear, used by kgat_umma_error_flag()
+int kgat_eval_umma_error_take() {
+    int v = 0, zero = 0;
+    if (cudaMemcpyFromSymbol(&v, g_eval_umma_error, sizeof(int)) != cudaSuccess) return KGAT_ERR_CUDA;
+    if (v != 0) cudaMemcpyToSymbol(g_eval_umma_error, &zero, sizeof(int));
+    return v;
+}
+
+// Launcher used by kgat_score_topk (eval.cu) when dim <= 256 and K <= 32.
+int kgat_launch_score_topk_umma(const float* emb, int64_t emb_stride, int dim, const int32_t* user_ids, int n_users,
+                                const int32_t* item_ids, int n_items, const int32_t* mask_ptr,
+                                const int32_t* mask_items, int K, int32_t* topk_idx, float* topk_score,
+                                cudaStream_t st) {
+    static int* err_flag = nullptr;
+    static bool configured = false;
+    if (!configured) {
+        KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&err_flag), g_eval_umma_error));
+        KGAT_CUDA(cudaFuncSetAttribute(score_topk_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(Smem)));
+        configured = true;
+    }
+    const unsigned grid = static_cast<unsigned>((n_users + TM - 1) / TM);
+    score_topk_umma_kernel<<<grid, THREADS, sizeof(Smem), st>>>(emb, emb_stride, dim, user_ids, n_users, item_ids,
+                                                                n_items, mask_ptr, mask_items, K, topk_idx, topk_score,
+                                                                err_flag);
+    KGAT_LAUNCH_CHECK();
+    return KGAT_OK;
+}

@@ -195,7 +195,9 @@ KGAT_API int kgat_bpr_loss_bwd(const float* emb, int64_t emb_stride, int dim, co
  *       score[mask_items[mask_ptr[j] .. mask_ptr[j+1])] = 0.0   (train items, metric.py:50;
  *                                  positions into item_ids, ascending per user),
  *       topk_idx[j, :] = the K best positions, descending score, ties -> lower position.
- *     The U x I score matrix is never materialised.  topk_score may be null. */
+ *     The U x I score matrix is never materialised.  topk_score may be null.
+ *     dim <= 256 and K <= 32 run on the tensor cores (tcgen05 3xTF32, scores stay in TMEM); otherwise an
+ *     fp32 FFMA kernel is used.  Environment: KGAT_EVAL_IMPL=ffma forces the FFMA kernel (A/B runs). */
 KGAT_API int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
                     const int32_t* user_ids, int64_t n_users,
                     const int32_t* item_ids, int64_t n_items,

@@ -101,3 +101,47 @@ def test_attention_umma_ragged_tiles(dev):
     w64 = kgat_ref.compute_attention({k: v.detach().cpu().double() for k, v in m.state_dict().items()}, trip, N).numpy()
     assert float((np.abs(w - w64) / w64).max()) < 1e-5
     assert _lib.load().kgat_umma_error_flag() == 0
+
+
+def test_eval_umma_vs_ffma_vs_oracle(dev):
+    """Tensor-core scoring + top-K against the FFMA kernel and a dense fp64 ranking, ragged shapes."""
+    from dgl_kgat_b200 import metric
+    rng = np.random.default_rng(1)
+    n_nodes, dim = 1500, 176
+    emb = th.from_numpy(rng.standard_normal((n_nodes, dim)).astype(np.float32))
+    emb[307] = emb[303]                                   # exact duplicate item -> exact tie
+    users = list(range(0, 300, 1))
+    items = np.arange(300, 300 + 1111)                    # not a multiple of the 128-item tile
+    tr = {u: np.unique(rng.integers(0, 1111, rng.integers(0, 40))) for u in users}
+    te = {u: rng.integers(0, 1111, 3) for u in users}
+    s64 = emb[users].double() @ emb[items].double().t()
+    for j, u in enumerate(users):
+        s64[j, tr[u]] = 0.0
+    want = np.argsort(-s64.numpy(), axis=1, kind="stable")[:, :20]
+    out = {}
+    for impl in ("ffma", "umma"):
+        os.environ["KGAT_EVAL_IMPL"] = impl
+        try:
+            topk, _ = metric.topk_items(emb.to(dev), tr, te, th.as_tensor(items, device=dev), 20,
+                                        plan=metric.EvalPlan(tr, te, len(items)))
+        finally:
+            os.environ.pop("KGAT_EVAL_IMPL", None)
+        got = topk.cpu().numpy()
+        exact = 0
+        for j in range(len(users)):
+            if np.array_equal(got[j], want[j]):
+                exact += 1
+                continue
+            s = s64[j].numpy()
+            tol = 2e-6 * max(1.0, np.abs(s).max())
+            assert np.allclose(np.sort(s[got[j]])[::-1], s[want[j]], rtol=0, atol=tol), (impl, j)
+            assert all(abs(s[a] - s[b]) <= tol for a, b in zip(got[j], want[j]) if a != b), (impl, j)
+        out[impl] = exact / len(users)
+        # the duplicate pair (items 3 and 7) must appear in index order whenever both are listed
+        for j in range(len(users)):
+            r = got[j].tolist()
+            if 3 in r and 7 in r:
+                assert r.index(3) < r.index(7), (impl, j)
+    assert _lib.load().kgat_umma_error_flag() == 0
+    print("exact top-20 rows:", out)
+    assert out["umma"] > 0.95 and out["ffma"] > 0.95
