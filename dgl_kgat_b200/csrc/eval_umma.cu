@@ -11,8 +11,12 @@
 //   MMA      (warp 12, one lane) per K-block: U_hi x [I_hi ; I_lo] (N = 256) and U_lo x I_hi (N = 128):
 //            columns 0..127 accumulate hi*hi + lo*hi, columns 128..255 hi*lo; two accumulator buffers.
 //   epilogue (warps 8-11)  thread = user row: tcgen05.ld, score = c[i] + c[128 + i], train items forced to
-//            0.0 (metric.py:50), strict-greater insertion into the row's sorted top-K list in shared
-//            memory (items arrive in ascending order, so ties keep the lower index first).
+//            0.0 (metric.py:50).  Scores that beat the row's (possibly stale) K-th best are APPENDED to a
+//            per-row candidate buffer - branch-light, lane-major and bank-conflict-free; only when a
+//            buffer of the warp fills are the candidates merged (all 32 rows of the warp together, so
+//            the serial insertion chain is not replayed per row), in arrival (= ascending item) order, into the sorted
+//            top-K list with strict-greater displacement, so ties keep the lower index first exactly as a
+//            direct insertion would.
 #include <limits.h>
 
 #include "common.cuh"
@@ -23,16 +27,19 @@ namespace {
 
 constexpr int TM = 128, TN = 128, KB = 32;
 constexpr int N_PROD = 256, N_EPI = 128, THREADS = N_PROD + N_EPI + 32, MMA_WARP = 12;
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;
 constexpr int K_MAX = 32;                               // largest top-K this kernel keeps in shared memory
+constexpr int CAP = 32;                                 // candidate-buffer depth per row
 constexpr uint32_t ARR_BYTES = 128 * KB * 4;            // 16 KB
 constexpr uint32_t STAGE_BYTES = 4 * ARR_BYTES;         // U_hi, U_lo, I_hi, I_lo
 constexpr uint32_t TMEM_COLS = 512;                     // 2 buffers x 256 columns
 
 struct Smem {
     unsigned char A[STAGES][STAGE_BYTES];
-    float ls[TM * K_MAX];
-    int li[TM * K_MAX];
+    float ls[K_MAX * TM];                                // sorted top-K lists, [position][row]
+    int li[K_MAX * TM];
+    float cs[CAP * TM];                                  // candidate buffers, [slot][row]
+    int ci[CAP * TM];
     uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     volatile int abort_flag;
@@ -188,8 +195,30 @@ score_topk_umma_kernel(const float* __restrict__ emb, int64_t stride, int dim,
             mend = mask_ptr[u0 + row + 1];
             next_mask = (mp < mend && mask_items) ? mask_items[mp] : INT_MAX;
         }
-        float* myLs = s.ls + row * K;
-        int* myLi = s.li + row * K;
+        float* const ls = s.ls + row;                    // element p of this row's list: ls[p * TM]
+        int* const li = s.li + row;
+        float* const cs = s.cs + row;
+        int* const ci = s.ci + row;
+        int ncand = 0;
+        // merge the buffered candidates, in arrival order, into the sorted list
+        auto flush = [&]() {
+            for (int t = 0; t < ncand; ++t) {
+                const float sc = cs[t * TM];
+                if (cnt < K || sc > thr) {
+                    int p = cnt < K ? cnt : K - 1;
+                    while (p > 0 && ls[(p - 1) * TM] < sc) {
+                        ls[p * TM] = ls[(p - 1) * TM];
+                        li[p * TM] = li[(p - 1) * TM];
+                        --p;
+                    }
+                    ls[p * TM] = sc;
+                    li[p * TM] = ci[t * TM];
+                    if (cnt < K) ++cnt;
+                    if (cnt == K) thr = ls[(K - 1) * TM];
+                }
+            }
+            ncand = 0;
+        };
         for (int it = 0; it < n_it; ++it) {
             const int buf = it & 1;
             if (!umma::mbar_wait(&s.acc_full[buf], (it >> 1) & 1)) { s.abort_flag = 1; s.epi_abort = 1; }
@@ -198,17 +227,34 @@ score_topk_umma_kernel(const float* __restrict__ emb, int64_t stride, int dim,
             asm volatile("bar.sync 1, %0;" ::"n"(N_EPI) : "memory");
             if (s.epi_abort) break;
             const uint32_t ta = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
+            const bool tile_full = (it + 1) * TN <= n_items;
 #pragma unroll 1
             for (int c0 = 0; c0 < TN; c0 += 16) {
                 float a[16], b[16];
                 umma::tmem_ld16(ta + c0, a);
                 umma::tmem_ld16(ta + 128 + c0, b);
                 umma::tmem_ld_wait();
+                // warp-synchronous merge: when ANY row of the warp is about to overflow its buffer, every
+                // row merges now - the serial insertion chain then runs a handful of times per kernel
+                // instead of once per row-event (rows of a warp fill their buffers at similar rates)
+                if (__any_sync(FULL_MASK, sel && ncand > CAP - 16)) flush();
                 if (sel) {
+                    const int item0 = it * TN + c0;
+                    if (tile_full && cnt == K && next_mask >= item0 + 16) {
+                        // fast path (almost every chunk): no bounds, no mask, list already full
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int item = it * TN + c0 + i;
-                        if (item < n_items) {
+                        for (int i = 0; i < 16; ++i) {
+                            const float sc = a[i] + b[i];
+                            if (sc > thr) {
+                                cs[ncand * TM] = sc;
+                                ci[ncand * TM] = item0 + i;
+                                ++ncand;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int item = item0 + i;
                             float sc = a[i] + b[i];
                             if (item == next_mask) {            // train item: score forced to 0.0 (metric.py:50)
                                 sc = 0.0f;
@@ -217,17 +263,10 @@ score_topk_umma_kernel(const float* __restrict__ emb, int64_t stride, int dim,
                                     next_mask = mp < mend ? mask_items[mp] : INT_MAX;
                                 } while (next_mask == item);
                             }
-                            if (cnt < K || sc > thr) {
-                                int p = cnt < K ? cnt : K - 1;
-                                while (p > 0 && myLs[p - 1] < sc) {
-                                    myLs[p] = myLs[p - 1];
-                                    myLi[p] = myLi[p - 1];
-                                    --p;
-                                }
-                                myLs[p] = sc;
-                                myLi[p] = item;
-                                if (cnt < K) ++cnt;
-                                if (cnt == K) thr = myLs[K - 1];
+                            if (item < n_items && (cnt < K || sc > thr)) {
+                                cs[ncand * TM] = sc;
+                                ci[ncand * TM] = item;
+                                ++ncand;
                             }
                         }
                     }
@@ -237,10 +276,11 @@ score_topk_umma_kernel(const float* __restrict__ emb, int64_t stride, int dim,
             umma::mbar_arrive(&s.acc_empty[buf]);
         }
         if (sel && !s.epi_abort) {
+            flush();
             for (int p = 0; p < K; ++p) {
                 const bool ok = p < cnt;
-                topk_idx[static_cast<size_t>(u0 + row) * K + p] = ok ? myLi[p] : -1;
-                if (topk_score) topk_score[static_cast<size_t>(u0 + row) * K + p] = ok ? myLs[p] : -INFINITY;
+                topk_idx[static_cast<size_t>(u0 + row) * K + p] = ok ? li[p * TM] : -1;
+                if (topk_score) topk_score[static_cast<size_t>(u0 + row) * K + p] = ok ? ls[p * TM] : -INFINITY;
             }
         }
     }
