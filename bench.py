@@ -76,7 +76,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -113,6 +113,26 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic_r1.json); None if not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    try:
+        return float(json.load(open(path))["kernels"][kernel]["dram_bytes"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def workload_config(cfg, world=1, work_mb=None):
+    c = {"workload": cfg.name + "-shaped synthetic CKG, 1 attention + 1 gnn fwd+bwd per step",
+         "nodes": cfg.n_nodes, "edges": cfg.n_edges, "relations": cfg.n_relations, "layers": "64-32-16",
+         "batch": BATCH}
+    if work_mb is not None:
+        c["l2_policy"] = "inputs larger than L2 (%.0f MB touched per step vs 126 MB L2)" % work_mb
+        c["parallelism"] = "dst-partition x%d" % world if world > 1 else "single GPU"
+    return c
 
 
 def algorithmic_bytes(N, E, R, dims):
@@ -215,8 +235,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "edges/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg.name + "-shaped synthetic CKG", "nodes": cfg.n_nodes, "edges": cfg.n_edges,
-                   "relations": cfg.n_relations, "layers": "64-32-16", "batch": BATCH},
+        "config": workload_config(cfg),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -350,7 +369,9 @@ def run_ours(args):
         top = max(kernel_ms, key=kernel_ms.get)
         ach = alg[top] / (kernel_ms[top] * 1e-3) / 1e9
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "launch_ms": kernel_ms[top],
+                    "traffic": measured_traffic(top), "peak_source": peak_src, "launch_ms": kernel_ms[top],
+                    "traffic_source": "profiles/traffic_r1.json (ncu --set full, same workload)",
+                    "algorithmic_bytes": alg[top],
                     "step_frac": (step_bytes(N, E, R) / (ms_step * 1e-3) / 1e9) / peak,
                     "step_alg_GB": step_bytes(N, E, R) / 1e9}
 
@@ -403,10 +424,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg.name + "-shaped synthetic CKG, 1 attention + 1 gnn fwd+bwd per step",
-                       "nodes": N, "edges": E, "relations": R, "layers": "64-32-16", "batch": BATCH,
-                       "l2_policy": "inputs larger than L2 (%.0f MB touched per step vs 126 MB L2)" % work_mb,
-                       "parallelism": "dst-partition x%d" % world if distributed else "single GPU"},
+            "config": workload_config(cfg, world, work_mb),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cpu, "kernels": table, "eval": eval_info,
         }

@@ -585,3 +585,18 @@ def test_graphed_cf_step_matches_eager(dev):
             if p.grad is not None:
                 assert th.equal(p.grad, grads_g[k]), k
         m.zero_grad(set_to_none=True)
+
+
+def test_kgat_cli_one_epoch_on_synthetic(dev, tmp_path):
+    """The kgat.py-compatible driver end to end: KG phase, attention refresh, CF phase, eval, CSV logs."""
+    from dgl_kgat_b200 import kgat
+    args = kgat.parse_args(["--synthetic", "tiny", "--max_epoch", "1", "--max_kg_iters", "3", "--max_cf_iters", "3",
+                            "--batch_size", "4096", "--batch_size_kg", "1024", "--log_root", str(tmp_path)])
+    assert (args.entity_embed_dim, args.gnn_num_layer, args.dropout_rate, args.lr) == (64, 3, 0.1, 0.001)
+    test_recall, test_ndcg, best_epoch = kgat.train_eval(args)
+    assert 0.0 <= test_recall <= 1.0 and 0.0 <= test_ndcg <= 1.0
+    files = sorted(f for f in __import__("os").listdir(args.save_dir))
+    assert any(f.startswith("valid") and f.endswith(".csv") for f in files)
+    assert any(f.startswith("log") and f.endswith(".log") for f in files)
+    rows = open(__import__("os").path.join(args.save_dir, "valid%d.csv" % args.save_id)).read().strip().splitlines()
+    assert rows[0] == "epoch,recall,ndcg,is_best" and len(rows) == 2
