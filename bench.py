@@ -9,7 +9,10 @@ backward from a BPR loss on B = 10 240 random (u, i+, i-) triples, dropout 0.  e
 Prints ONE JSON line (rank 0).
 
  value      the step with inputs resident in HBM (batch ids already on the device), CUDA-event
-            timed over exactly K steps after W warm-ups, max over ranks.
+            timed over exactly K steps after W warm-ups, max over ranks.  Single GPU: the step is
+            replayed as one CUDA graph (graphed.GraphedCFStep); an eager, instrumented pass of the
+            same K steps runs first and provides the per-kernel events, the launch count
+            (gpu_launches = kernels per K steps) and eager_ms_per_step.
  e2e        the same step through the public Model API with the batch ids copied from pinned host
             memory and the loss read back every step (the call sequence of kgat.py:153-165).
  roofline   the dominant kernel of the step: algorithmic bytes (SURVEY.md section 8(d) E-model) / its
@@ -313,44 +316,62 @@ def run_ours(args):
         return float(t.item())
 
     rec = _lib.RECORDER
-    # ---- value: inputs resident in HBM -------------------------------------------------------
+    # ---- instrumented eager pass: per-kernel CUDA events + launch count (same inputs, same process) ----
     for i in range(args.warmup):
         step(dev_batches[i])
     barrier()
     rec.reset(enabled=True, time_kernels=True)
     e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(dev_batches[args.warmup + i])
+    e1.record()
+    barrier()
+    ms_eager = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = rec.launches
+    kernel_ms = {k: float(np.mean(v)) for k, v in rec.durations_ms().items()}
+    rec.reset(enabled=False)
+
+    # ---- value: inputs resident in HBM.  Single GPU: the step replayed as one CUDA graph
+    # (graphed.GraphedCFStep = the public call sequence, captured), ids already in its device buffers.
+    # Multi-GPU: the eager DistKGAT step (NCCL collectives are not captured).
+    graphed = None
+    if not distributed:
+        from dgl_kgat_b200.graphed import GraphedCFStep
+        graphed = GraphedCFStep(model, g, BATCH, refresh_attention=True)
+        for dst, src in zip(graphed.ids, dev_batches[0]):
+            dst.copy_(src)
+        run_value = lambda i: graphed.graph.replay()
+    else:
+        run_value = lambda i: step(dev_batches[args.warmup + i])
+    for i in range(args.warmup):
+        run_value(0)
     with ClockSampler(local) as clocks:
         barrier()
         e0.record()
         for i in range(args.steps):
-            step(dev_batches[args.warmup + i])
+            run_value(i)
         e1.record()
         barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = rec.launches
-    kernel_ms = {k: float(np.mean(v)) for k, v in rec.durations_ms().items()}
-    rec.reset(enabled=False)
-    ms_step = ms_total / args.steps
-    value = E / (ms_step * 1e-3)
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        ms_step = ms_total / args.steps
+        value = E / (ms_step * 1e-3)
 
-    # ---- e2e: host batch ids in, loss out, every step ----------------------------------------
-    # Public API: single GPU -> graphed.GraphedCFStep (the same call sequence captured as one CUDA
-    # graph); multi-GPU -> the eager DistKGAT calls.
-    if distributed:
-        def e2e_step(host_ids):
-            return step(tuple(b.to(dev, non_blocking=True) for b in host_ids))
-    else:
-        from dgl_kgat_b200.graphed import GraphedCFStep
-        graphed = GraphedCFStep(model, g, BATCH, refresh_attention=True)
-        e2e_step = lambda host_ids: graphed(*host_ids)
-    for i in range(min(args.warmup, 3)):
-        e2e_step(batches[i]).item()
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        loss_val = e2e_step(batches[args.warmup + i]).item()      # device -> host read of the step's result
-    e1.record()
-    barrier()
+        # ---- e2e: host batch ids in, loss out, every step (public API) ---------------------------
+        if distributed:
+            def e2e_step(host_ids):
+                return step(tuple(b.to(dev, non_blocking=True) for b in host_ids))
+        else:
+            e2e_step = lambda host_ids: graphed(*host_ids)
+        for i in range(min(args.warmup, 3)):
+            e2e_step(batches[i]).item()
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            loss_val = e2e_step(batches[args.warmup + i]).item()      # device -> host read of the step's result
+        e1.record()
+        barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e = {"value": E / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 3 * BATCH * 8,
            "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": loss_val,
@@ -425,7 +446,10 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, world, work_mb),
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+            "e2e": e2e, "gpu_launches": launches, "eager_ms_per_step": ms_eager,
+            "value_path": "eager dist.DistKGAT step" if distributed else
+                          "graphed.GraphedCFStep replay, ids resident (eager instrumented pass: eager_ms_per_step)",
+            "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cpu, "kernels": table, "eval": eval_info,
         }
         print(json.dumps(line))
