@@ -63,13 +63,21 @@ class Partition:
 
 def exchange_rows(buf: th.Tensor, bounds, group=None):
     """All-gather of row ranges, in place: rank k's rows ``bounds[k]:bounds[k+1]`` of ``buf`` reach
-    everyone.  Ranges are uneven (edge-balanced).  NCCL runs the uneven all-gather as ONE grouped
-    launch; gloo (CPU tests) has no uneven all-gather, so it gets one broadcast per owner."""
+    everyone.  Ranges are uneven (edge-balanced).  NCCL: every rank pads its rows to the largest range
+    and ONE ``all_gather_into_tensor`` moves them (a real ring/tree all-gather instead of one
+    broadcast per owner), then a single ``cat`` drops the padding into place.  gloo (CPU tests) gets
+    one broadcast per owner."""
     world = len(bounds) - 1
     if tdist.get_backend(group) == "nccl":
         rank = tdist.get_rank(group)
-        views = [buf[int(bounds[k]): int(bounds[k + 1])] for k in range(world)]
-        tdist.all_gather(views, views[rank], group=group)
+        sizes = [int(bounds[k + 1]) - int(bounds[k]) for k in range(world)]
+        m = max(sizes)
+        tail = tuple(buf.shape[1:])
+        stage_in = th.empty((m,) + tail, dtype=buf.dtype, device=buf.device)
+        stage_in[: sizes[rank]] = buf[int(bounds[rank]): int(bounds[rank + 1])]
+        stage_out = th.empty((world, m) + tail, dtype=buf.dtype, device=buf.device)
+        tdist.all_gather_into_tensor(stage_out, stage_in, group=group)
+        th.cat([stage_out[k, : sizes[k]] for k in range(world)], out=buf)
         return buf
     for k in range(world):
         a, b = int(bounds[k]), int(bounds[k + 1])
