@@ -335,11 +335,16 @@ def run_ours(args):
 
     # ---- value: inputs resident in HBM.  Single GPU: the step replayed as one CUDA graph
     # (graphed.GraphedCFStep = the public call sequence, captured), ids already in its device buffers.
-    # Multi-GPU: the eager DistKGAT step (NCCL collectives are not captured).
+    # Multi-GPU: graphed.GraphedDistCFStep (kernels + NCCL collectives captured per rank);
+    # KGAT_BENCH_EAGER_DIST=1 falls back to the eager DistKGAT calls.
     graphed = None
     if not distributed:
         from dgl_kgat_b200.graphed import GraphedCFStep
         graphed = GraphedCFStep(model, g, BATCH, refresh_attention=True)
+    elif os.environ.get("KGAT_BENCH_EAGER_DIST", "0") != "1":
+        from dgl_kgat_b200.graphed import GraphedDistCFStep
+        graphed = GraphedDistCFStep(dk, BATCH)
+    if graphed is not None:
         for dst, src in zip(graphed.ids, dev_batches[0]):
             dst.copy_(src)
         run_value = lambda i: graphed.graph.replay()
@@ -359,7 +364,7 @@ def run_ours(args):
         value = E / (ms_step * 1e-3)
 
         # ---- e2e: host batch ids in, loss out, every step (public API) ---------------------------
-        if distributed:
+        if graphed is None:
             def e2e_step(host_ids):
                 return step(tuple(b.to(dev, non_blocking=True) for b in host_ids))
         else:
@@ -375,7 +380,9 @@ def run_ours(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e = {"value": E / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 3 * BATCH * 8,
            "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": loss_val,
-           "api": "dist.DistKGAT (eager)" if distributed else "graphed.GraphedCFStep (CUDA graph of the public calls)"}
+           "api": "dist.DistKGAT (eager)" if graphed is None else
+                  ("graphed.GraphedDistCFStep (CUDA graph incl. NCCL collectives)" if distributed
+                   else "graphed.GraphedCFStep (CUDA graph of the public calls)")}
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peak, peak_src = measured_peaks()
@@ -447,8 +454,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, world, work_mb),
             "e2e": e2e, "gpu_launches": launches, "eager_ms_per_step": ms_eager,
-            "value_path": "eager dist.DistKGAT step" if distributed else
-                          "graphed.GraphedCFStep replay, ids resident (eager instrumented pass: eager_ms_per_step)",
+            "value_path": "eager dist.DistKGAT step" if graphed is None else
+                          "CUDA-graph replay of the step, ids resident (eager instrumented pass: eager_ms_per_step)",
             "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cpu, "kernels": table, "eval": eval_info,
         }
