@@ -74,8 +74,9 @@ class GraphedCFStep:
 class GraphedDistCFStep(GraphedCFStep):
     """The same for the destination-partitioned step of :class:`dist.DistKGAT`: the kernels AND the
     NCCL collectives of one iteration (weight all-gather, row exchanges, loss-row and dW2 all-reduces)
-    are captured in one CUDA graph per rank, which removes the per-launch host latency that dominates
-    the eager multi-GPU step at Amazon-book size."""
+    are captured in one CUDA graph per rank.  EXPERIMENTAL: on 2 B200s it bought only ~3 % over the
+    eager step and tearing the process group down after capturing NCCL work was unreliable; bench.py
+    uses it only when KGAT_BENCH_GRAPH_DIST=1."""
 
     def __init__(self, dk, batch_size, warmup=3):
         self.dk, self.model = dk, dk.model

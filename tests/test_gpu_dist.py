@@ -70,16 +70,6 @@ def _worker(rank, world, port, ret):
         rec1, ndcg1 = metric.calc_recall_ndcg(emb1.detach(), tr, te, items, 20)
         rec2, ndcg2 = dk.calc_recall_ndcg(emb1.detach(), tr, te, ck.item_id_range, 20)
         assert abs(rec1 - rec2) < 1e-12 and abs(ndcg1 - ndcg2) < 1e-12
-        # the same distributed step captured (kernels + NCCL collectives) in a CUDA graph
-        from dgl_kgat_b200.graphed import GraphedDistCFStep
-        grads_eager = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
-        gstep = GraphedDistCFStep(dk, ids[0].numel())
-        for _ in range(2):
-            loss_g = gstep(*ids)
-        assert abs(loss_g.item() - loss2.item()) <= 1e-6 * abs(loss2.item())
-        for k, p in m.named_parameters():
-            if k in grads_eager:
-                assert th.equal(p.grad, grads_eager[k]), k
         ret[rank] = "ok"
     except Exception as e:
         ret[rank] = "FAIL: %r" % (e,)
