@@ -193,7 +193,7 @@ class DistKGAT:
         if mine:
             topk, plan = metric.topk_items(embedding_full, train_user_dict, sub, item_id_range, K,
                                            plan=metric.EvalPlan(train_user_dict, sub, len(item_id_range)))
-            rec, ndcg, _ = metric.metrics_from_topk(topk.cpu().numpy(), plan, K)
+            rec, ndcg = metric.metrics_from_topk_device(topk, plan, K)
             sums += th.tensor([rec * len(mine), ndcg * len(mine), len(mine)], dtype=th.float64, device=self.device)
         tdist.all_reduce(sums, group=self.group)
         n = float(sums[2].item())

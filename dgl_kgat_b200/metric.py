@@ -11,8 +11,8 @@ keeps the reference semantics, quirks included:
 
 The per-user Python loop, the 17.5 MB item-matrix re-gather per user, the full sort and
 the per-user device->host sync are replaced by ONE launch of the fused scoring + top-K
-kernel (``kgat_score_topk``) and one (n_users, K) read-back; the metric arithmetic is
-done in float64 numpy like the reference's helpers.
+kernel (``kgat_score_topk``); the hit matching and the Recall / NDCG sums run on the device in
+float64 (same formulas as the reference's numpy helpers) and only two scalars are read back.
 """
 from __future__ import annotations
 
@@ -80,6 +80,14 @@ class EvalPlan:
                                    for a in (self.user_ids, self.mask_ptr, self.mask_items))
         return self._dev[key]
 
+    def device_positives(self, device):
+        """(sorted positive keys int64, positives per user float64) on the device."""
+        key = "pos:" + str(device)
+        if key not in self._dev:
+            self._dev[key] = (th.from_numpy(self.pos_keys).to(device),
+                              th.from_numpy(self.pos_len.astype(np.float64)).to(device))
+        return self._dev[key]
+
 
 _PLAN_CACHE = {}
 
@@ -111,6 +119,29 @@ def metrics_from_topk(topk: np.ndarray, plan: EvalPlan, K: int):
     return float(recall_u.sum() / n), float(ndcg_u.sum() / n), hits
 
 
+def metrics_from_topk_device(topk: th.Tensor, plan: EvalPlan, K: int):
+    """Same arithmetic as :func:`metrics_from_topk`, on the device in float64 (hit matching by binary
+    search in the sorted positive keys); only the two scalars travel to the host."""
+    dev = topk.device
+    pos_keys, pos_len = plan.device_positives(dev)
+    n = plan.n_users
+    keys = th.arange(n, dtype=th.int64, device=dev).unsqueeze(1) * plan.n_items + topk.to(th.int64)
+    if pos_keys.numel():
+        idx = th.searchsorted(pos_keys, keys.reshape(-1)).clamp_(max=pos_keys.numel() - 1)
+        hits = (pos_keys[idx] == keys.reshape(-1)).reshape(n, K).to(th.float64)          # metric.py:56-59
+    else:
+        hits = th.zeros(n, K, dtype=th.float64, device=dev)
+    n_hit = hits.sum(1)
+    recall_u = th.where(pos_len > 0, n_hit / pos_len.clamp(min=1.0), th.zeros_like(n_hit))  # metric.py:60-61
+    disc = 1.0 / th.log2(th.arange(2, K + 2, dtype=th.float64, device=dev))
+    dcg = (hits * disc).sum(1)
+    ideal = th.cat([th.zeros(1, dtype=th.float64, device=dev), th.cumsum(disc, 0)])[n_hit.to(th.int64)]
+    ndcg_u = th.where(ideal > 0, dcg / th.where(ideal > 0, ideal, th.ones_like(ideal)), th.zeros_like(dcg))
+    out = th.stack([recall_u.sum(), ndcg_u.sum()]) / n
+    rec, ndcg = out.tolist()
+    return rec, ndcg
+
+
 def topk_items(embedding, train_user_dict, test_user_dict, all_item_id_range, K, plan=None):
     """(n_eval_users, K) int32 device tensor of top-K positions into ``all_item_id_range``."""
     item_ids = th.as_tensor(all_item_id_range).reshape(-1)
@@ -128,6 +159,4 @@ def calc_recall_ndcg(embedding, train_user_dict, test_user_dict, all_item_id_ran
     compatibility; the embedding must live on the GPU (there is no CPU path)."""
     with th.no_grad():
         topk, plan = topk_items(embedding, train_user_dict, test_user_dict, all_item_id_range, K, plan)
-        topk = topk.cpu().numpy()
-    recall, ndcg, _ = metrics_from_topk(topk, plan, K)
-    return recall, ndcg
+        return metrics_from_topk_device(topk, plan, K)
