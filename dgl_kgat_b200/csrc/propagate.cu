@@ -56,13 +56,38 @@ __device__ __forceinline__ float4 gather_row(const int32_t* __restrict__ idx, co
     return across_groups_sum<LPE>(acc);
 }
 
+// Rows with more than LONG_ROW edges (hot entities of a power-law KG) are gathered by ALL warps of the
+// CTA: warp w takes the w-th contiguous slice (a multiple of 32 edges, so the summation order depends
+// on the row only), partials meet in shared memory and are added in warp order - deterministic.
+constexpr int LONG_ROW = 512;
+constexpr int COOP_FLOATS = WARPS * 32 * 4 + TM;      // float4 partial per lane per warp + row flags
+
+// CTA-uniform call; every lane of every warp returns the total (element group lane % (W/4))
+template <int W>
+__device__ __forceinline__ float4 gather_row_cta(const int32_t* __restrict__ idx, const float* __restrict__ wgt,
+                                                 int beg, int end, const float* __restrict__ feat, float4* sPart,
+                                                 int warp, int lane) {
+    const int per = (((end - beg) + WARPS - 1) / WARPS + 31) & ~31;
+    const int b = min(end, beg + warp * per), e = min(end, b + per);
+    sPart[warp * 32 + lane] = gather_row<W>(idx, wgt, b, e, feat, lane);
+    __syncthreads();
+    float4 t = sPart[lane];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) {
+        const float4 q = sPart[w * 32 + lane];
+        t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+    }
+    __syncthreads();
+    return t;
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
 template <int DIN, int DOUT>
 struct FwdSmem {
     static constexpr int LDW = DOUT + 1;
-    static constexpr size_t bytes = sizeof(float) * (DIN * LDW + TM * DIN + TM * DOUT) + 16;
+    static constexpr size_t bytes = sizeof(float) * (DIN * LDW + TM * DIN + TM * DOUT + COOP_FLOATS) + 16;
 };
 
 template <int DIN, int DOUT>
@@ -79,6 +104,8 @@ layer_fwd_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict_
     float* sZ = reinterpret_cast<float*>(smem_raw);          // [TM][DIN]   (16B aligned)
     float* sY = sZ + TM * DIN;                               // [TM][DOUT]
     float* sW = sY + TM * DOUT;                              // [DIN][LDW], sW[i][j] = W2[j][i]
+    float4* sPart = reinterpret_cast<float4*>(sW + DIN * LDW + ((4 - (DIN * LDW) % 4) % 4));   // 16B aligned
+    int* sLong = reinterpret_cast<int*>(sPart + WARPS * 32);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = row_begin + blockIdx.x * TM;
 
@@ -88,24 +115,42 @@ layer_fwd_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict_
     }
 
     // phase 1: aggregation, z tile
+    auto finish_row = [&](int row, int rl, const float4& hn) {
+        if (lane < LPI) {
+            const size_t o = static_cast<size_t>(row) * DIN + lane * 4;
+            const float4 x = ldg4(h_in + o);
+            *reinterpret_cast<float4*>(h_nb + o) = hn;
+            if (in_off >= 0)
+                *reinterpret_cast<float4*>(concat + static_cast<size_t>(row) * cstride + in_off + lane * 4) = x;
+            *reinterpret_cast<float4*>(sZ + rl * DIN + lane * 4) =
+                make_float4(x.x * hn.x, x.y * hn.y, x.z * hn.z, x.w * hn.w);
+        }
+    };
+    bool warp_long = false;
     for (int rl = warp; rl < TM; rl += WARPS) {
         const int row = row0 + rl;
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool is_long = false;
         if (row < row_end) {
             const int beg = __ldg(csr_ptr + row), end = __ldg(csr_ptr + row + 1);
-            const float4 hn = gather_row<DIN>(csr_src, w_csr, beg, end, h_in, lane);
-            if (lane < LPI) {
-                const size_t o = static_cast<size_t>(row) * DIN + lane * 4;
-                const float4 x = ldg4(h_in + o);
-                *reinterpret_cast<float4*>(h_nb + o) = hn;
-                if (in_off >= 0)
-                    *reinterpret_cast<float4*>(concat + static_cast<size_t>(row) * cstride + in_off + lane * 4) = x;
-                z = make_float4(x.x * hn.x, x.y * hn.y, x.z * hn.z, x.w * hn.w);
-            }
+            if (end - beg > LONG_ROW) is_long = true;
+            else finish_row(row, rl, gather_row<DIN>(csr_src, w_csr, beg, end, h_in, lane));
+        } else if (lane < LPI) {
+            *reinterpret_cast<float4*>(sZ + rl * DIN + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (lane < LPI) *reinterpret_cast<float4*>(sZ + rl * DIN + lane * 4) = z;
+        if (lane == 0) sLong[rl] = is_long ? 1 : 0;
+        warp_long |= is_long;
     }
-    __syncthreads();
+    // the barrier that ends phase 1 also tells every thread whether the tile holds a long row
+    if (__syncthreads_or(warp_long ? 1 : 0)) {
+        for (int rl = 0; rl < TM; ++rl) {
+            if (!sLong[rl]) continue;                     // CTA-uniform
+            const int row = row0 + rl;
+            const int beg = __ldg(csr_ptr + row), end = __ldg(csr_ptr + row + 1);
+            const float4 hn = gather_row_cta<DIN>(csr_src, w_csr, beg, end, h_in, sPart, warp, lane);
+            if (warp == rl % WARPS) finish_row(row, rl, hn);
+        }
+        __syncthreads();
+    }
 
     // phase 2: pre = z W2^T, LeakyReLU, dropout
     {
@@ -171,7 +216,7 @@ struct BwdCfg {
     static constexpr int BJ = (DOUT * DIN >= 4096) ? 4 : ((DOUT * DIN >= 2048) ? 2 : 1);
     static constexpr int NBLOCKS = DOUT * DIN / (4 * BJ);
     static constexpr int NB = (NBLOCKS + THREADS - 1) / THREADS;
-    static constexpr size_t bytes = sizeof(float) * (DOUT * DIN + TM * DOUT + TM * DIN) + 16;
+    static constexpr size_t bytes = sizeof(float) * (DOUT * DIN + TM * DOUT + TM * DIN + COOP_FLOATS) + 16;
 };
 
 template <int DIN, int DOUT>
@@ -192,6 +237,8 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
     float* sDP = reinterpret_cast<float*>(smem_raw);     // [TM][DOUT]
     float* sZ = sDP + TM * DOUT;                         // [TM][DIN]
     float* sW = sZ + TM * DIN;                           // [DOUT][DIN] as given
+    float4* sPart = reinterpret_cast<float4*>(sW + DOUT * DIN);
+    int* sLong = reinterpret_cast<int*>(sPart + WARPS * 32);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int idx = tid; idx < DOUT * DIN / 4; idx += THREADS)
@@ -210,16 +257,11 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
         __syncthreads();      // previous tile's readers are done with sDP / sZ (also orders the sW fill)
 
         // phase 1: dpre and z for every row of the tile
-        for (int rl = warp; rl < TM; rl += WARPS) {
-            const int row = row0 + rl;
+        // everything after the transposed aggregation: g = gathered next-layer term of this row
+        auto process_row = [&](int row, int rl, float4 g) {
             float4 dp = make_float4(0.f, 0.f, 0.f, 0.f), z = dp;
             if (row < row_end) {
                 const int lo = lane % LPO;
-                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (nxt_dh_nb) {
-                    const int beg = __ldg(csc_ptr + row), end = __ldg(csc_ptr + row + 1);
-                    g = gather_row<DOUT>(csc_dst, w_csc, beg, end, nxt_dh_nb, lane);
-                }
                 const size_t oo = static_cast<size_t>(row) * DOUT + lo * 4;
                 if (nxt_dx_direct) {
                     const float4 t = ldg4(nxt_dx_direct + oo);
@@ -268,8 +310,32 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
             }
             if (lane < LPO) *reinterpret_cast<float4*>(sDP + rl * DOUT + lane * 4) = dp;
             if (lane < LPI) *reinterpret_cast<float4*>(sZ + rl * DIN + lane * 4) = z;
+        };
+        bool warp_long = false;
+        for (int rl = warp; rl < TM; rl += WARPS) {
+            const int row = row0 + rl;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool is_long = false;
+            if (row < row_end && nxt_dh_nb) {
+                const int beg = __ldg(csc_ptr + row), end = __ldg(csc_ptr + row + 1);
+                if (end - beg > LONG_ROW) is_long = true;
+                else g = gather_row<DOUT>(csc_dst, w_csc, beg, end, nxt_dh_nb, lane);
+            }
+            if (!is_long) process_row(row, rl, g);
+            if (lane == 0) sLong[rl] = is_long ? 1 : 0;
+            warp_long |= is_long;
         }
-        __syncthreads();
+        // the barrier that ends phase 1 also tells every thread whether the tile holds a long row
+        if (__syncthreads_or(warp_long ? 1 : 0)) {
+            for (int rl = 0; rl < TM; ++rl) {
+                if (!sLong[rl]) continue;                 // CTA-uniform
+                const int row = row0 + rl;
+                const int beg = __ldg(csc_ptr + row), end = __ldg(csc_ptr + row + 1);
+                const float4 g = gather_row_cta<DOUT>(csc_dst, w_csc, beg, end, nxt_dh_nb, sPart, warp, lane);
+                if (warp == rl % WARPS) process_row(row, rl, g);
+            }
+            __syncthreads();
+        }
 
         // phase 2a: dW2 += dpre^T z
 #pragma unroll
