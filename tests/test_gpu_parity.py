@@ -601,3 +601,26 @@ def test_kgat_cli_one_epoch_on_synthetic(dev, tmp_path):
     assert any(f.startswith("log") and f.endswith(".log") for f in files)
     rows = open(__import__("os").path.join(args.save_dir, "valid%d.csv" % args.save_id)).read().strip().splitlines()
     assert rows[0] == "epoch,recall,ndcg,is_best" and len(rows) == 2
+
+
+@pytest.mark.parametrize("N,E", [(1, 0), (5, 3), (33, 40), (257, 1000)])
+def test_tiny_and_ragged_graphs(dev, N, E):
+    """Row counts that do not fill a 32-row tile, a graph without edges, a single node."""
+    rng = np.random.default_rng(N)
+    R = 3
+    trip = np.stack([rng.integers(0, N, E), rng.integers(0, R, E), rng.integers(0, N, E)], 1).astype(np.int32) \
+        if E else np.zeros((0, 3), np.int32)
+    m = make_model(N, R, dev)
+    g = CKGraph(N, trip, n_rel=R)
+    w = m.compute_attention(g)
+    assert tuple(w.shape) == (E, 1)
+    p64 = cpu_params(m)
+    if E:
+        w64 = kgat_ref.compute_attention(p64, trip, N).numpy()
+        assert elem_rel(w.cpu().numpy(), w64) < RTOL
+    ids = [th.as_tensor(rng.integers(0, N, 16)) for _ in range(3)]
+    emb, loss = run_cf_step(m, g, w, *[i.to(dev) for i in ids])
+    loss64, emb64, grads64 = kgat_ref.cf_step(p64, trip, w.cpu().double(), N, *ids, 1e-4)
+    assert max_rel(emb.cpu().numpy(), emb64.numpy()) < RTOL
+    assert abs(loss.item() - loss64.item()) < 1e-5 * abs(loss64.item())
+    assert max_rel(m.entity_embed.weight.grad.cpu().numpy(), grads64["entity_embed.weight"].numpy()) < RTOL
