@@ -305,8 +305,9 @@ extern "C" int kgat_segment_softmax(const kgat_graph_t* g, int64_t row_begin, in
 
 extern "C" int kgat_edge_weights_from_eid(const kgat_graph_t* g, const float* w_eid, float* w_csr,
                                           float* w_csc, kgat_stream_t stream) {
-    KGAT_REQUIRE(g && w_eid);
+    KGAT_REQUIRE(g);
     if (g->n_edges == 0) return KGAT_OK;
+    KGAT_REQUIRE(w_eid);
     const int64_t E = g->n_edges;
     const unsigned blocks = static_cast<unsigned>((E + 255) / 256);
     if (w_csr) {
