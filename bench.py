@@ -394,8 +394,9 @@ def run_ours(args):
         table[name] = {"ms": round(ms, 4), "alg_MB": None if b is None else round(b / 1e6, 2),
                        "GBps": None if b is None else round(b / (ms * 1e-3) / 1e9, 1)}
     roofline = None
-    if kernel_ms and not distributed:
-        top = max(kernel_ms, key=kernel_ms.get)
+    modelled = {k: v for k, v in kernel_ms.items() if alg.get(k) is not None}
+    if modelled and not distributed:
+        top = max(modelled, key=modelled.get)
         ach = alg[top] / (kernel_ms[top] * 1e-3) / 1e9
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": measured_traffic(top), "peak_source": peak_src, "launch_ms": kernel_ms[top],

@@ -30,7 +30,10 @@ class GraphedCFStep:
         if dev.type != "cuda":
             raise _lib.KgatError("a graphed step needs the model on a CUDA device")
         self.device = dev
-        self.ids = [th.zeros(batch_size, dtype=th.long, device=dev) for _ in range(3)]
+        # distinct ids for the warm-up / capture run (all-equal ids would serialise the compact-gradient
+        # accumulation of the loss head on one node)
+        n_rows = model.entity_embed.weight.shape[0]
+        self.ids = [(th.arange(batch_size, dtype=th.long, device=dev) * (k + 1)) % n_rows for k in range(3)]
         if _lib.RECORDER.enabled and _lib.RECORDER.time_kernels:
             raise _lib.KgatError("disable per-kernel event timing before capturing a graph")
         with th.cuda.device(dev):
