@@ -621,6 +621,11 @@ def test_tiny_and_ragged_graphs(dev, N, E):
     ids = [th.as_tensor(rng.integers(0, N, 16)) for _ in range(3)]
     emb, loss = run_cf_step(m, g, w, *[i.to(dev) for i in ids])
     loss64, emb64, grads64 = kgat_ref.cf_step(p64, trip, w.cpu().double(), N, *ids, 1e-4)
+    _, _, grads32 = kgat_ref.cf_step(cpu_params(m, th.float32), trip, w.cpu(), N, *ids, 1e-4)
     assert max_rel(emb.cpu().numpy(), emb64.numpy()) < RTOL
     assert abs(loss.item() - loss64.item()) < 1e-5 * abs(loss64.item())
-    assert max_rel(m.entity_embed.weight.grad.cpu().numpy(), grads64["entity_embed.weight"].numpy()) < RTOL
+    # on these degenerate graphs the BPR terms cancel almost exactly (every id hits the same few rows), so
+    # the fp32 reference itself is noisy against fp64: allow twice its own error, as elsewhere
+    k = "entity_embed.weight"
+    tol = max(RTOL, 2.0 * max_rel(grads32[k].numpy(), grads64[k].numpy()))
+    assert max_rel(m.entity_embed.weight.grad.cpu().numpy(), grads64[k].numpy()) < tol
