@@ -82,7 +82,9 @@ class EdgeBatchSampler:
             r = None if self.etype is None else self.etype[eid]
             corrupt = self.rng.integers(0, self.n_nodes, size=eid.shape[0])
             ns, nd = (corrupt, d) if self.mode == "head" else (s, corrupt)
-            false_neg = np.isin(self._edge_key(ns, nd, r), self._keys).astype(np.int64)
+            q = self._edge_key(ns, nd, r)                      # membership by binary search: _keys is sorted
+            pos = np.minimum(np.searchsorted(self._keys, q), self._keys.shape[0] - 1)
+            false_neg = (self._keys[pos] == q).astype(np.int64)
             yield s, d, r, ns, nd, false_neg
 
 
