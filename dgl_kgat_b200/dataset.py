@@ -184,6 +184,14 @@ class DataLoader(object):
         return info
 
     # ------------------------------------------------------------------ samplers (host side)
+    def _sampler(self, name, src, dst, etype, n_nodes, batch_size, mode):
+        """Samplers are kept across epochs (their sorted edge-key table is built once)."""
+        cache = self.__dict__.setdefault("_samplers", {})
+        key = (name, batch_size, mode)
+        if key not in cache:
+            cache[key] = EdgeBatchSampler(src, dst, etype, n_nodes, batch_size, mode, self._rng)
+        return cache[key]
+
     @staticmethod
     def _n_batch(batch_size, n):
         if batch_size < 0 or batch_size > n:
@@ -197,8 +205,8 @@ class DataLoader(object):
         if not (pos_mode == "uniform" and neg_mode == "tail"):
             raise NotImplementedError("only pos_mode='uniform', neg_mode='tail' (the mode kgat.py uses)")
         t = self.train_KG_triplet
-        sampler = EdgeBatchSampler(t[:, 2], t[:, 0], t[:, 1], self.n_KG_entity,
-                                   self._n_batch(batch_size, self.n_train_KG_triplet), "tail", self._rng)
+        sampler = self._sampler("kg", t[:, 2], t[:, 0], t[:, 1], self.n_KG_entity,
+                                self._n_batch(batch_size, self.n_train_KG_triplet), "tail")
         for s, d, r, _, nd, false_neg in sampler:
             yield s, r, d, nd, false_neg
 
@@ -210,7 +218,7 @@ class DataLoader(object):
         if not (pos_mode == "uniform" and neg_mode == "random"):
             raise NotImplementedError("only pos_mode='uniform', neg_mode='random' (the mode kgat.py uses)")
         t = self._train_uv_triplet
-        sampler = EdgeBatchSampler(t[:, 2], t[:, 0], None, self.n_users + self.n_items,
-                                   self._n_batch(batch_size, t.shape[0]), "head", self._rng)
+        sampler = self._sampler("cf", t[:, 2], t[:, 0], None, self.n_users + self.n_items,
+                                self._n_batch(batch_size, t.shape[0]), "head")
         for s, d, _, ns, _, false_neg in sampler:
             yield d, s, ns, false_neg
