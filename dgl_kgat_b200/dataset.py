@@ -88,6 +88,42 @@ class EdgeBatchSampler:
             yield s, d, r, ns, nd, false_neg
 
 
+class DeviceEdgeBatchSampler:
+    """:class:`EdgeBatchSampler` with the edge list, the shuffling, the corruption and the
+    false-negative lookup resident on one torch device: batches are
+    device tensors, so the training loop does no per-batch host->device copies (kgat.py:123-128,
+    :153-158) and the host does no sampling work.  Same batch contract, torch's RNG."""
+
+    def __init__(self, src, dst, etype, n_nodes, batch_size, negative_mode, device, generator=None):
+        import torch as th
+        self.th, self.device, self.gen = th, th.device(device), generator
+        self.src = th.as_tensor(np.asarray(src), dtype=th.long, device=self.device)
+        self.dst = th.as_tensor(np.asarray(dst), dtype=th.long, device=self.device)
+        self.etype = None if etype is None else th.as_tensor(np.asarray(etype), dtype=th.long, device=self.device)
+        self.n_nodes, self.batch_size, self.mode = int(n_nodes), int(batch_size), negative_mode
+        self._n_rel = 1 if self.etype is None else int(self.etype.max().item()) + 1
+        self._keys = th.unique(self._edge_key(self.src, self.dst, self.etype))      # sorted
+
+    def _edge_key(self, s, d, r):
+        k = s * self.n_nodes + d
+        return k if r is None else k * self._n_rel + r
+
+    def __iter__(self):
+        th = self.th
+        E = self.src.shape[0]
+        perm = th.randperm(E, device=self.device, generator=self.gen)
+        for b in range(0, E, self.batch_size):
+            eid = perm[b: b + self.batch_size]
+            s, d = self.src[eid], self.dst[eid]
+            r = None if self.etype is None else self.etype[eid]
+            corrupt = th.randint(0, self.n_nodes, (eid.shape[0],), device=self.device, generator=self.gen)
+            ns, nd = (corrupt, d) if self.mode == "head" else (s, corrupt)
+            q = self._edge_key(ns, nd, r)
+            pos = th.searchsorted(self._keys, q).clamp_(max=self._keys.shape[0] - 1)
+            false_neg = (self._keys[pos] == q).to(th.long)
+            yield s, d, r, ns, nd, false_neg
+
+
 class DataLoader(object):
     def __init__(self, data_name, symmetric=True, as_continuous_ids=True, add_uv2KG=True, seed=1234,
                  data_dir=None, _frames=None):
@@ -147,14 +183,14 @@ class DataLoader(object):
     # ------------------------------------------------------------------ construction helpers
     @classmethod
     def from_synthetic(cls, config="tiny", seed=1234, skew=False):
-        """Same object from a synthetic CKG of a BASELINE.json shape; the held-out pairs
-        serve as both the validation and the test split."""
+        """Same object from a synthetic CKG of a BASELINE.json shape."""
         ck = synth.synth_ckg(config, seed=seed, skew=skew)
         U = ck.cfg.n_users
         frame = lambda p: pd.DataFrame({"u": p[:, 0].astype(np.int32), "v": (p[:, 1] - U).astype(np.int32)})
         kg = pd.DataFrame({"h": ck.kg[:, 0] - U, "r": ck.kg[:, 1], "t": ck.kg[:, 2] - U}, dtype=np.int32)
+        half = ck.valid_pairs.shape[0] // 2            # held-out pairs: first half validation, second half test
         return cls("synthetic-" + ck.cfg.name, seed=seed,
-                   _frames=(frame(ck.train_pairs), frame(ck.valid_pairs), frame(ck.valid_pairs), kg))
+                   _frames=(frame(ck.train_pairs), frame(ck.valid_pairs[:half]), frame(ck.valid_pairs[half:]), kg))
 
     @staticmethod
     def _uv2triplet(pairs, offset_rel, symmetric=True):
@@ -184,12 +220,22 @@ class DataLoader(object):
         return info
 
     # ------------------------------------------------------------------ samplers (host side)
+    def use_device_samplers(self, device):
+        """Make KG_sampler / CF_pair_sampler yield DEVICE tensors produced on `device`
+        (None switches back to the numpy samplers)."""
+        self._sampler_device = device
+        self.__dict__.pop("_samplers", None)
+
     def _sampler(self, name, src, dst, etype, n_nodes, batch_size, mode):
         """Samplers are kept across epochs (their sorted edge-key table is built once)."""
         cache = self.__dict__.setdefault("_samplers", {})
-        key = (name, batch_size, mode)
+        dev = self.__dict__.get("_sampler_device")
+        key = (name, batch_size, mode, str(dev))
         if key not in cache:
-            cache[key] = EdgeBatchSampler(src, dst, etype, n_nodes, batch_size, mode, self._rng)
+            if dev is None:
+                cache[key] = EdgeBatchSampler(src, dst, etype, n_nodes, batch_size, mode, self._rng)
+            else:
+                cache[key] = DeviceEdgeBatchSampler(src, dst, etype, n_nodes, batch_size, mode, dev)
         return cache[key]
 
     @staticmethod

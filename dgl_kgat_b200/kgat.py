@@ -10,7 +10,8 @@ BPR loss + backward per batch of ``--batch_size``; (4) every ``--evaluate_every`
 Recall@20 / NDCG@20 on the validation users (train graph) and the test users (test graph),
 logged to ``log/<cfg>/valid{id}.csv`` and ``test{id}.csv``.  Additions (all off by default):
 ``--synthetic`` builds the inputs from :mod:`synth`; ``--max_kg_iters`` / ``--max_cf_iters``
-cap the phases for smoke runs.
+cap the phases for smoke runs; batches come from the device-resident sampler unless
+``--host_sampler`` is given.
 """
 from __future__ import annotations
 
@@ -54,6 +55,8 @@ def parse_args(argv=None):
     p.add_argument('--max_kg_iters', type=int, default=-1, help='cap on KG batches per epoch (-1: all)')
     p.add_argument('--max_cf_iters', type=int, default=-1, help='cap on CF batches per epoch (-1: all)')
     p.add_argument('--log_root', type=str, default='log')
+    p.add_argument('--host_sampler', action='store_true',
+                   help='sample batches with numpy on the host (default: device-resident sampler)')
     args = p.parse_args(argv)
     name = args.data_name if args.synthetic is None else "synthetic-" + args.synthetic
     save_dir = "{}_d{}_l{}_dp{}_lr{}_bz{}_kgbz{}_att{}_seed{}".format(
@@ -90,6 +93,8 @@ def train_eval(args):
     else:
         dataset = DataLoader(data_name=args.data_name, seed=args.seed)
     print(dataset)
+    if not args.host_sampler:
+        dataset.use_device_samplers(dev)
     model = Model(use_KG=True, input_node_dim=args.entity_embed_dim, gnn_model=args.gnn_model,
                   num_gnn_layers=args.gnn_num_layer, n_hidden=args.gnn_hidden_size, dropout=args.dropout_rate,
                   n_entities=dataset.n_KG_entity, n_relations=dataset.n_KG_relation,

@@ -127,8 +127,9 @@ def test_dataloader_tsv_roundtrip(tmp_path):
     va = ck.valid_pairs.copy(); va[:, 1] -= U
     kg = ck.kg.copy(); kg[:, 0] -= U; kg[:, 2] -= U
     dump("uv_train.pd", ["u", "v"], tr)
-    dump("uv_val.pd", ["u", "v"], va)
-    dump("uv_test.pd", ["u", "v"], va)
+    half = va.shape[0] // 2                     # from_synthetic: first half validation, second half test
+    dump("uv_val.pd", ["u", "v"], va[:half])
+    dump("uv_test.pd", ["u", "v"], va[half:])
     dump("kg_item.pd", ["h", "r", "t"], kg)
     a = dataset.DataLoader("toy", data_dir=str(d))
     b = dataset.DataLoader.from_synthetic("tiny")
@@ -170,6 +171,27 @@ def test_samplers_semantics():
         tot += len(users)
         assert len(users) <= 10240 and neg.max() < dl.n_users + dl.n_items
     assert tot == 2 * dl.n_train
+
+
+def test_device_sampler_same_contract_as_host_sampler():
+    """dataset.DeviceEdgeBatchSampler (run on the CPU device here) keeps the batch contract."""
+    dl = dataset.DataLoader.from_synthetic("tiny")
+    dl.use_device_samplers("cpu")
+    t = dl.train_KG_triplet
+    edges = set(map(tuple, t[:, [2, 0, 1]].tolist()))
+    seen = 0
+    for h, r, pos_t, neg_t, fn in dl.KG_sampler(batch_size=30000):
+        assert all(isinstance(x, th.Tensor) and x.dtype == th.long for x in (h, r, pos_t, neg_t, fn))
+        seen += len(h)
+        assert all((int(a), int(b), int(c)) in edges for a, b, c in zip(h[:50], pos_t[:50], r[:50]))
+        chk = [(int(a), int(b), int(c)) in edges for a, b, c in zip(h[:200], neg_t[:200], r[:200])]
+        assert chk == [bool(x) for x in fn[:200]]
+        assert int(neg_t.min()) >= 0 and int(neg_t.max()) < dl.n_KG_entity
+    assert seen == dl.n_train_KG_triplet
+    tot = sum(len(u) for u, p, n, fn in dl.CF_pair_sampler(batch_size=10240))
+    assert tot == 2 * dl.n_train
+    dl.use_device_samplers(None)
+    assert isinstance(next(iter(dl.KG_sampler(2048)))[0], np.ndarray)
 
 
 def test_metric_helpers_and_plan(golden_g3, golden_eval, golden_small):
