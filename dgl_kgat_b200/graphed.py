@@ -94,3 +94,49 @@ class GraphedDistCFStep(GraphedCFStep):
         loss = dk.get_loss(emb, *self.ids)
         loss.backward()
         return loss
+
+
+class GraphedKGStep:
+    """One TransR iteration of the reference loop (kgat.py:117-131) - ``model.transR(h, r, pos_t, neg_t)``
+    and ``loss.backward()`` - as a CUDA graph for a FIXED batch size (the ~40 small torch kernels of
+    the TransR head are launch-bound otherwise).  Call it with device or pinned-host int64 ids; a
+    batch of another size (the last, partial one) must go through the eager calls."""
+
+    def __init__(self, model, batch_size, warmup=3):
+        self.model = model
+        dev = model.entity_embed.weight.device
+        if dev.type != "cuda":
+            raise _lib.KgatError("a graphed step needs the model on a CUDA device")
+        n_ent, n_rel = model.entity_embed.weight.shape[0], model.relation_embed.weight.shape[0]
+        ar = th.arange(batch_size, dtype=th.long, device=dev)
+        self.batch_size = batch_size
+        self.ids = [ar % n_ent, ar % n_rel, (ar * 3 + 1) % n_ent, (ar * 7 + 2) % n_ent]
+        with th.cuda.device(dev):
+            side = th.cuda.Stream()
+            side.wait_stream(th.cuda.current_stream())
+            with th.cuda.stream(side):
+                for _ in range(max(warmup, 1)):
+                    self._body()
+            th.cuda.current_stream().wait_stream(side)
+            th.cuda.synchronize()
+            for p in model.parameters():
+                p.grad = None
+            self.graph = th.cuda.CUDAGraph()
+            with th.cuda.graph(self.graph):
+                self.loss = self._body()
+            self._grads = [(p, p.grad) for p in model.parameters() if p.grad is not None]
+
+    def _body(self):
+        for p in self.model.parameters():
+            p.grad = None
+        loss = self.model.transR(*self.ids)
+        loss.backward()
+        return loss
+
+    def __call__(self, h, r, pos_t, neg_t):
+        for dst, src in zip(self.ids, (h, r, pos_t, neg_t)):
+            dst.copy_(th.as_tensor(src), non_blocking=True)
+        self.graph.replay()
+        for p, g in self._grads:
+            p.grad = g
+        return self.loss

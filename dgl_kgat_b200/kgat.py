@@ -11,7 +11,9 @@ Recall@20 / NDCG@20 on the validation users (train graph) and the test users (te
 logged to ``log/<cfg>/valid{id}.csv`` and ``test{id}.csv``.  Additions (all off by default):
 ``--synthetic`` builds the inputs from :mod:`synth`; ``--max_kg_iters`` / ``--max_cf_iters``
 cap the phases for smoke runs; batches come from the device-resident sampler unless
-``--host_sampler`` is given.
+``--host_sampler`` is given; the KG and CF iterations run as CUDA graphs (``graphed.py``) unless
+``--eager``; Adam is torch's fused multi-tensor kernel; ``--save_every`` / ``--resume`` write and read
+checkpoints (the reference has none, kgat.py:190).
 """
 from __future__ import annotations
 
@@ -57,6 +59,10 @@ def parse_args(argv=None):
     p.add_argument('--log_root', type=str, default='log')
     p.add_argument('--host_sampler', action='store_true',
                    help='sample batches with numpy on the host (default: device-resident sampler)')
+    p.add_argument('--eager', action='store_true',
+                   help='do not capture the KG / CF iterations as CUDA graphs')
+    p.add_argument('--save_every', type=int, default=0, help='write a checkpoint every N epochs (0: never)')
+    p.add_argument('--resume', type=str, default=None, help='checkpoint file to resume from')
     args = p.parse_args(argv)
     name = args.data_name if args.synthetic is None else "synthetic-" + args.synthetic
     save_dir = "{}_d{}_l{}_dp{}_lr{}_bz{}_kgbz{}_att{}_seed{}".format(
@@ -100,7 +106,14 @@ def train_eval(args):
                   n_entities=dataset.n_KG_entity, n_relations=dataset.n_KG_relation,
                   relation_dim=args.relation_embed_dim, reg_lambda_kg=args.regs, reg_lambda_gnn=args.regs).to(dev)
     logging.info(model)
-    optimizer = optim.Adam(model.parameters(), lr=args.lr)
+    optimizer = optim.Adam(model.parameters(), lr=args.lr, fused=True)      # one multi-tensor kernel per step
+    start_epoch = 1
+    if args.resume:
+        ckpt = th.load(args.resume, map_location=dev)
+        model.load_state_dict(ckpt["state_dict"])
+        optimizer.load_state_dict(ckpt["optimizer"])
+        start_epoch = int(ckpt["epoch"]) + 1
+        logging.info("resumed from %s (epoch %d)", args.resume, ckpt["epoch"])
     valid_log = MetricLogger(['epoch', 'recall', 'ndcg', 'is_best'], ['%d', '%.5f', '%.5f', '%d'],
                              os.path.join(args.save_dir, 'valid{:d}.csv'.format(args.save_id)))
     test_log = MetricLogger(['epoch', 'recall', 'ndcg'], ['%d', '%.5f', '%.5f'],
@@ -115,7 +128,8 @@ def train_eval(args):
     item_id_range = th.as_tensor(dataset.item_id_range, dtype=th.long, device=dev)
     as_ids = lambda a: th.as_tensor(a, dtype=th.long).to(dev, non_blocking=True)
 
-    for epoch in range(1, args.max_epoch + 1):
+    kg_graph = cf_graph = None
+    for epoch in range(start_epoch, args.max_epoch + 1):
         # phase 1: TransR on the KG (kgat.py:116-136)
         t0, it, total = time(), 0, 0.0
         model.train()
@@ -123,8 +137,14 @@ def train_eval(args):
             if 0 <= args.max_kg_iters <= it:
                 break
             it += 1
-            loss = model.transR(as_ids(h), as_ids(r), as_ids(pos_t), as_ids(neg_t))
-            loss.backward()
+            if not args.eager and len(h) == args.batch_size_kg:
+                if kg_graph is None:
+                    from .graphed import GraphedKGStep
+                    kg_graph = GraphedKGStep(model, args.batch_size_kg)
+                loss = kg_graph(h, r, pos_t, neg_t)
+            else:
+                loss = model.transR(as_ids(h), as_ids(r), as_ids(pos_t), as_ids(neg_t))
+                loss.backward()
             optimizer.step()
             optimizer.zero_grad()
             total += loss.item()
@@ -147,9 +167,15 @@ def train_eval(args):
             if 0 <= args.max_cf_iters <= it:
                 break
             it += 1
-            embedding = model.gnn(train_g, train_g.ndata['id'])
-            loss = model.get_loss(embedding, as_ids(user_ids), as_ids(item_pos_ids), as_ids(item_neg_ids))
-            loss.backward()
+            if not args.eager and len(user_ids) == args.batch_size:
+                if cf_graph is None:
+                    from .graphed import GraphedCFStep
+                    cf_graph = GraphedCFStep(model, train_g, args.batch_size, refresh_attention=False)
+                loss = cf_graph(user_ids, item_pos_ids, item_neg_ids)
+            else:
+                embedding = model.gnn(train_g, train_g.ndata['id'])
+                loss = model.get_loss(embedding, as_ids(user_ids), as_ids(item_pos_ids), as_ids(item_neg_ids))
+                loss.backward()
             optimizer.step()
             optimizer.zero_grad()
             total += loss.item()
@@ -172,6 +198,10 @@ def train_eval(args):
                 test_log.log(epoch=epoch, recall=test_recall, ndcg=test_ndcg)
             info += "\t[{:.1f}s] test recall:{:.5f}, test ndcg:{:.5f}".format(time() - t0, test_recall, test_ndcg)
             logging.info(info)
+        if args.save_every > 0 and epoch % args.save_every == 0:
+            path = os.path.join(args.save_dir, 'ckpt{:d}.pt'.format(args.save_id))
+            th.save({'state_dict': model.state_dict(), 'optimizer': optimizer.state_dict(), 'epoch': epoch}, path)
+            logging.info("checkpoint written to %s", path)
 
     logging.info("Final test recall:{:.5f}, test ndcg:{:.5f}, best epoch:{}".format(test_recall, test_ndcg, best_epoch))
     return test_recall, test_ndcg, best_epoch

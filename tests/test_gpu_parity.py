@@ -591,8 +591,9 @@ def test_graphed_cf_step_matches_eager(dev):
 def test_kgat_cli_one_epoch_on_synthetic(dev, tmp_path):
     """The kgat.py-compatible driver end to end: KG phase, attention refresh, CF phase, eval, CSV logs."""
     from dgl_kgat_b200 import kgat
-    args = kgat.parse_args(["--synthetic", "tiny", "--max_epoch", "1", "--max_kg_iters", "3", "--max_cf_iters", "3",
-                            "--batch_size", "4096", "--batch_size_kg", "1024", "--log_root", str(tmp_path)])
+    args = kgat.parse_args(["--synthetic", "tiny", "--max_epoch", "1", "--max_kg_iters", "5", "--max_cf_iters", "5",
+                            "--batch_size", "4096", "--batch_size_kg", "1024", "--log_root", str(tmp_path),
+                            "--save_every", "1"])
     assert (args.entity_embed_dim, args.gnn_num_layer, args.dropout_rate, args.lr) == (64, 3, 0.1, 0.001)
     test_recall, test_ndcg, best_epoch = kgat.train_eval(args)
     assert 0.0 <= test_recall <= 1.0 and 0.0 <= test_ndcg <= 1.0
@@ -601,6 +602,13 @@ def test_kgat_cli_one_epoch_on_synthetic(dev, tmp_path):
     assert any(f.startswith("log") and f.endswith(".log") for f in files)
     rows = open(__import__("os").path.join(args.save_dir, "valid%d.csv" % args.save_id)).read().strip().splitlines()
     assert rows[0] == "epoch,recall,ndcg,is_best" and len(rows) == 2
+    # resume from the checkpoint for one more epoch, eager this time
+    ckpt = __import__("os").path.join(args.save_dir, "ckpt%d.pt" % args.save_id)
+    args2 = kgat.parse_args(["--synthetic", "tiny", "--max_epoch", "2", "--max_kg_iters", "2", "--max_cf_iters", "2",
+                             "--batch_size", "4096", "--batch_size_kg", "1024", "--log_root", str(tmp_path),
+                             "--resume", ckpt, "--eager", "--host_sampler"])
+    r2, n2, _ = kgat.train_eval(args2)
+    assert 0.0 <= r2 <= 1.0
 
 
 @pytest.mark.parametrize("N,E", [(1, 0), (5, 3), (33, 40), (257, 1000)])
