@@ -249,11 +249,16 @@ using namespace kgat;
 
 int kgat_launch_att_logits_umma(const kgat_graph_t* g, const float* entity, const float* rel_emb, const float* W_R,
                                 float* logits_csr, cudaStream_t st);
+int kgat_launch_att_logits_umma16(const kgat_graph_t* g, const float* entity, const float* rel_emb,
+                                  const float* W_R, float* logits_csr, cudaStream_t st);
 
-// KGAT_ATT_IMPL=ffma selects the fp32 FFMA tile kernel instead of the tcgen05 3xTF32 kernel (A/B runs).
-static bool use_umma() {
+// KGAT_ATT_IMPL selects the kernel for d = rd = 64 (A/B runs): "f16" (default) tcgen05 split-fp16,
+// "tf32" tcgen05 3xTF32, "ffma" fp32 FFMA tiles.
+static int att_impl() {
     const char* e = std::getenv("KGAT_ATT_IMPL");
-    return !(e && std::strcmp(e, "ffma") == 0);
+    if (e && std::strcmp(e, "ffma") == 0) return 0;
+    if (e && std::strcmp(e, "tf32") == 0) return 1;
+    return 2;
 }
 
 extern "C" int kgat_attention_logits(const kgat_graph_t* g, const float* entity, const float* rel_emb,
@@ -265,7 +270,10 @@ extern "C" int kgat_attention_logits(const kgat_graph_t* g, const float* entity,
     if (g->n_edges == 0) return KGAT_OK;
     cudaStream_t st = as_stream(stream);
     const int64_t E = g->n_edges;
-    if (d == 64 && rd == 64 && g->n_rel <= 1024 && use_umma()) {
+    const int impl = att_impl();
+    if (d == 64 && rd == 64 && g->n_rel <= 1024 && impl == 2) {
+        return kgat_launch_att_logits_umma16(g, entity, rel_emb, W_R, logits_csr, st);
+    } else if (d == 64 && rd == 64 && g->n_rel <= 1024 && impl == 1) {
         return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, st);
     } else if (d == 64 && rd == 64) {
         using S = AttSmem<64, 64>;

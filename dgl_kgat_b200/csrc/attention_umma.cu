@@ -13,17 +13,19 @@
 //            features = one 128-byte row per edge) of a tile: 4 arrays x 16 KB; two stages ring.  Loads for the next stage are in
 //            flight while the current one is split and stored.  W_r is staged as B = [W_hi | W_lo]
 //            (N = 128) once per relation.
-//   MMA      (warp 12, one lane) per stage: T_hi x [W_hi|W_lo] (N=128), T_lo x W_hi (N=64) and the same
-//            for the head rows -> hi*hi + lo*hi in TMEM columns 0..63, hi*lo in 64..127; fp32
-//            accumulation in TMEM, two accumulator buffers (2 x 256 columns).  tcgen05.commit releases
-//            the shared-memory stage and, after the second K-half, publishes the accumulator.
-//   epilogue (warps 8-11, one TMEM lane quarter each) tcgen05.ld, t = c[0:64] + c[64:128],
+//   MMA      (warp 12, one lane) per stage: T_hi x W_hi, T_hi x W_lo, T_lo x W_hi (N=64 each) accumulate
+//            into the SAME 64 TMEM columns, and the same for the head rows; fp32 accumulation in TMEM,
+//            two accumulator buffers (2 x 128 columns).  tcgen05.commit releases the shared-memory
+//            stage and, after the second K-half, publishes the accumulator.
+//   epilogue (warps 8-11, one TMEM lane quarter each) tcgen05.ld,
 //            logit = sum_c t_r[c] * tanh(h_r[c] + e_r[c]), scattered to the edge's CSR position; runs
 //            while the tensor core works on the next tile.
 // Neither projection ever exists in HBM.  3xTF32 keeps the result inside the 1e-5 relative bar
 // (a single TF32 pass is ~4e-4).
 #include "common.cuh"
 #include "umma.cuh"
+
+#include <cstdlib>
 
 namespace kgat {
 namespace {
@@ -39,7 +41,7 @@ constexpr int MAX_REL = 1024;
 constexpr uint32_t ARR_BYTES = TILE * KH * 4;        // 16 KB: one operand array of one stage
 constexpr uint32_t STAGE_BYTES = 4 * ARR_BYTES;      // T_hi, T_lo, H_hi, H_lo
 constexpr uint32_t B_HALF_BYTES = 128 * KH * 4;      // 16 KB: [W_hi | W_lo] rows for one K-half
-constexpr uint32_t TMEM_COLS = 512;                  // 2 buffers x (T: 128 + H: 128)
+constexpr uint32_t TMEM_COLS = 512;
 
 struct Smem {
     unsigned char B[2][B_HALF_BYTES];                // per K-half: rows 0..63 W_hi^T, rows 64..127 W_lo^T
@@ -70,6 +72,7 @@ __device__ __forceinline__ TileInfo tile_info(const int* prefix, const int32_t* 
     return t;
 }
 
+template <int EPI_W, int WIDE>
 __global__ void __launch_bounds__(THREADS, 1)
 att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int32_t* __restrict__ bk_head,
                        const int32_t* __restrict__ bk_tail, const int32_t* __restrict__ bk_pos,
@@ -209,12 +212,12 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
     } else if (warp == MMA_WARP) {
         // =========================================================== MMA issuer
         if (lane == 0) {
-            const uint32_t idesc128 = umma::make_idesc_tf32(TILE, 128), idesc64 = umma::make_idesc_tf32(TILE, 64);
+            const uint32_t idesc = umma::make_idesc_tf32(TILE, D), idesc128 = umma::make_idesc_tf32(TILE, 128);
             for (int tile = t0; tile < t1 && !s.abort_flag; ++tile) {
                 const int it = tile - t0, buf = it & 1;
                 if (!umma::mbar_wait(&s.acc_empty[buf], ((it >> 1) & 1) ^ 1)) s.abort_flag = 1;
                 umma::fence_after_sync();
-                const uint32_t tT = tmem + buf * 256, tH = tT + 128;
+                const uint32_t tT = tmem + buf * 256, tH = tT + (WIDE ? 128 : 64);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if (!umma::mbar_wait(&s.full[h], it & 1)) s.abort_flag = 1;
@@ -224,12 +227,24 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
 #pragma unroll
                     for (int ks = 0; ks < KH / 8; ++ks) {
                         const uint32_t off = ks * 32;                 // K = 8 fp32 inside the 128-byte row
-                        const uint64_t dB = umma::make_smem_desc_sw128(bW + off);
+                        const uint64_t dWhi = umma::make_smem_desc_sw128(bW + off);                // rows 0..63
+                        const uint64_t dWlo = umma::make_smem_desc_sw128(bW + 64 * 128 + off);     // rows 64..127
+                        const uint64_t dThi = umma::make_smem_desc_sw128(aT + off);
+                        const uint64_t dHhi = umma::make_smem_desc_sw128(aH + off);
                         const uint32_t acc = (h | ks) != 0;
-                        umma::mma_tf32(tT, umma::make_smem_desc_sw128(aT + off), dB, idesc128, acc);
-                        umma::mma_tf32(tT, umma::make_smem_desc_sw128(aT + ARR_BYTES + off), dB, idesc64, 1);
-                        umma::mma_tf32(tH, umma::make_smem_desc_sw128(aH + off), dB, idesc128, acc);
-                        umma::mma_tf32(tH, umma::make_smem_desc_sw128(aH + ARR_BYTES + off), dB, idesc64, 1);
+                        if constexpr (WIDE) {
+                            umma::mma_tf32(tT, dThi, dWhi, idesc128, acc);
+                            umma::mma_tf32(tT, umma::make_smem_desc_sw128(aT + ARR_BYTES + off), dWhi, idesc, 1);
+                            umma::mma_tf32(tH, dHhi, dWhi, idesc128, acc);
+                            umma::mma_tf32(tH, umma::make_smem_desc_sw128(aH + ARR_BYTES + off), dWhi, idesc, 1);
+                        } else {
+                            umma::mma_tf32(tT, dThi, dWhi, idesc, acc);
+                            umma::mma_tf32(tT, dThi, dWlo, idesc, 1);
+                            umma::mma_tf32(tT, umma::make_smem_desc_sw128(aT + ARR_BYTES + off), dWhi, idesc, 1);
+                            umma::mma_tf32(tH, dHhi, dWhi, idesc, acc);
+                            umma::mma_tf32(tH, dHhi, dWlo, idesc, 1);
+                            umma::mma_tf32(tH, umma::make_smem_desc_sw128(aH + ARR_BYTES + off), dWhi, idesc, 1);
+                        }
                     }
                     umma::mma_commit(&s.empty[h]);                   // stage h may be refilled once these finish
                 }
@@ -254,17 +269,33 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
             if (s.epi_abort) break;
             const uint32_t ta = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
             float p = 0.f;
+            if constexpr (WIDE) {
 #pragma unroll
-            for (int c0 = 0; c0 < D; c0 += 16) {
-                float a[16], b[16], c[16], d[16];
-                umma::tmem_ld16(ta + c0, a);                 // T: hi*hi + lo*hi
-                umma::tmem_ld16(ta + 64 + c0, b);            // T: hi*lo
-                umma::tmem_ld16(ta + 128 + c0, c);           // H: hi*hi + lo*hi
-                umma::tmem_ld16(ta + 192 + c0, d);           // H: hi*lo
+                for (int c0 = 0; c0 < D; c0 += 16) {
+                    float a[16], b[16], c[16], d[16];
+                    umma::tmem_ld16(ta + c0, a);                 // T: hi*hi + lo*hi
+                    umma::tmem_ld16(ta + 64 + c0, b);            // T: hi*lo
+                    umma::tmem_ld16(ta + 128 + c0, c);           // H: hi*hi + lo*hi
+                    umma::tmem_ld16(ta + 192 + c0, d);           // H: hi*lo
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        p = fmaf(a[i] + b[i], tanh_fast(c[i] + d[i] + s.er[buf][c0 + i]), p);
+                }
+            } else
+#pragma unroll
+            for (int c0 = 0; c0 < D; c0 += EPI_W) {
+                float a[EPI_W], c[EPI_W];
+                if constexpr (EPI_W == 32) {
+                    umma::tmem_ld32(ta + c0, a);             // e_t W_r
+                    umma::tmem_ld32(ta + 64 + c0, c);        // e_h W_r
+                } else {
+                    umma::tmem_ld16(ta + c0, a);
+                    umma::tmem_ld16(ta + 64 + c0, c);
+                }
                 umma::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    p = fmaf(a[i] + b[i], tanh_fast(c[i] + d[i] + s.er[buf][c0 + i]), p);
+                for (int i = 0; i < EPI_W; ++i) p = fmaf(a[i], tanh_fast(c[i] + s.er[buf][c0 + i]), p);
             }
             umma::fence_before_sync();
             umma::mbar_arrive(&s.acc_empty[buf]);                     // TMEM buffer may be overwritten
@@ -288,6 +319,13 @@ using namespace kgat;
 
 int kgat_eval_umma_error_take();
 
+// device address of the shared tensor-core error word (attention_umma16.cu reports through it too)
+int* kgat_umma_error_word() {
+    int* p = nullptr;
+    if (cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_umma_error) != cudaSuccess) return nullptr;
+    return p;
+}
+
 extern "C" int kgat_umma_error_flag(void) {
     int v = 0, zero = 0;
     if (cudaMemcpyFromSymbol(&v, g_umma_error, sizeof(int)) != cudaSuccess) return KGAT_ERR_CUDA;
@@ -302,17 +340,22 @@ int kgat_launch_att_logits_umma(const kgat_graph_t* g, const float* entity, cons
                                 float* logits_csr, cudaStream_t st) {
     static int* err_flag = nullptr;
     static bool configured = false;
+    static int epi_w = 32;
     if (!configured) {
         KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&err_flag), g_umma_error));
-        KGAT_CUDA(cudaFuncSetAttribute(att_logits_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        KGAT_CUDA(cudaFuncSetAttribute(att_logits_umma_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
+        KGAT_CUDA(cudaFuncSetAttribute(att_logits_umma_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(Smem)));
+        const char* e = std::getenv("KGAT_ATT_EPI");
+        if (e && std::atoi(e) == 16) epi_w = 16;
         configured = true;
     }
     const int64_t max_tiles = g->n_edges / TILE + g->n_rel;
     const int grid = static_cast<int>(max_tiles < num_sms() ? max_tiles : num_sms());
-    att_logits_umma_kernel<<<grid, THREADS, sizeof(Smem), st>>>(
-        g->rel_ptr, static_cast<int>(g->n_rel), g->bk_head, g->bk_tail, g->bk_pos, entity, rel_emb, W_R, logits_csr,
-        err_flag);
+    auto kern = epi_w == 16 ? att_logits_umma_kernel<16, 1> : att_logits_umma_kernel<32, 0>;
+    kern<<<grid, THREADS, sizeof(Smem), st>>>(g->rel_ptr, static_cast<int>(g->n_rel), g->bk_head, g->bk_tail,
+                                              g->bk_pos, entity, rel_emb, W_R, logits_csr, err_flag);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }

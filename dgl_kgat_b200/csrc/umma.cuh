@@ -109,6 +109,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 8 consecutive fp32 columns of this thread's TMEM lane (no wait)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors
@@ -172,12 +183,13 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 // ---------------------------------------------------------------- 3xTF32 split
-// x = hi + lo with hi the round-to-nearest TF32 of x; lo is exact in fp32 and is itself truncated to
-// TF32 by the tensor core.  hi*hi + hi*lo + lo*hi (+ lo*lo) recovers ~fp32 accuracy.
+// x = hi + lo with hi the round-to-nearest (ties away) TF32 of x; lo is exact in fp32 and is itself
+// truncated to TF32 by the tensor core.  hi*hi + hi*lo + lo*hi (+ lo*lo) recovers ~fp32 accuracy.
+// The rounding is done on the bit pattern (add half an ulp of the 10-bit mantissa, clear the low 13
+// bits): identical to cvt.rna.tf32.f32 for finite values below the overflow threshold, and 2 integer
+// instructions instead of the 5 (add, |x| < inf test, select, mask) ptxas emits for the cvt.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
     lo = x - hi;
 }
 
