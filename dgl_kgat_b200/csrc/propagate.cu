@@ -408,19 +408,42 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
 }
 
 // dW2[idx] = sum_p partials[p][idx], fixed order, accumulated in fp64 (the per-CTA partials are
-// fp32 sums over a few hundred rows; the cross-CTA sum must not add its own rounding on top);
-// 8 threads per element, combined by shuffle
+// fp32 sums over a few hundred rows; the cross-CTA sum must not add its own rounding on top).
+// One CTA per 32 consecutive elements (one 128-byte line of every partial): lane = (partial slot
+// lane / 8, float4 lane % 8), warp w and slot g take partials p = 4 w + g (mod 32), so every load
+// instruction reads four full lines and a thread walks n_partials / 32 of them; slots meet by shuffle,
+// warps in shared memory, always in the same order.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int n_elem, float* __restrict__ out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int idx = t >> 3, part = t & 7;
-    double s = 0.0;
-    if (idx < n_elem)
-        for (int p = part; p < n_partials; p += 8)
-            s += static_cast<double>(__ldg(partials + static_cast<size_t>(p) * n_elem + idx));
+    __shared__ double sAcc[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e4 = lane & 7, slot = lane >> 3;
+    const int idx = blockIdx.x * 32 + e4 * 4;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (idx < n_elem) {
+#pragma unroll 4
+        for (int p = warp * 4 + slot; p < n_partials; p += 32) {
+            const float4 v = ldg4(partials + static_cast<size_t>(p) * n_elem + idx);
+            s0 += static_cast<double>(v.x); s1 += static_cast<double>(v.y);
+            s2 += static_cast<double>(v.z); s3 += static_cast<double>(v.w);
+        }
+    }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
-    if (idx < n_elem && part == 0) out[idx] = static_cast<float>(s);
+    for (int o = 8; o < 32; o <<= 1) {
+        s0 += __shfl_xor_sync(FULL_MASK, s0, o); s1 += __shfl_xor_sync(FULL_MASK, s1, o);
+        s2 += __shfl_xor_sync(FULL_MASK, s2, o); s3 += __shfl_xor_sync(FULL_MASK, s3, o);
+    }
+    if (slot == 0) {
+        sAcc[warp][e4 * 4 + 0] = s0; sAcc[warp][e4 * 4 + 1] = s1;
+        sAcc[warp][e4 * 4 + 2] = s2; sAcc[warp][e4 * 4 + 3] = s3;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && blockIdx.x * 32 + threadIdx.x < n_elem) {
+        double t = sAcc[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t += sAcc[w][threadIdx.x];
+        out[blockIdx.x * 32 + threadIdx.x] = static_cast<float>(t);
+    }
 }
 
 // d_entity[v] = d_concat[v, in_off:+D] + dx_direct[v] + sum_{k in CSC row v} w[k] * dh_nb[dst[k]]
@@ -511,7 +534,7 @@ int launch_bwd(const BwdArgs& a) {
         a.dh_nb, a.partials);
     KGAT_LAUNCH_CHECK();
     const int n_elem = DIN * DOUT;
-    reduce_partials_kernel<<<(n_elem * 8 + 255) / 256, 256, 0, a.st>>>(a.partials, grid, n_elem, a.dW2);
+    reduce_partials_kernel<<<(n_elem + 31) / 32, 256, 0, a.st>>>(a.partials, grid, n_elem, a.dW2);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }
