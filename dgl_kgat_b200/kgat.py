@@ -131,7 +131,7 @@ def train_eval(args):
     kg_graph = cf_graph = None
     for epoch in range(start_epoch, args.max_epoch + 1):
         # phase 1: TransR on the KG (kgat.py:116-136)
-        t0, it, total = time(), 0, 0.0
+        t0, it, total = time(), 0, th.zeros((), dtype=th.float64, device=dev)
         model.train()
         for h, r, pos_t, neg_t, _ in dataset.KG_sampler(batch_size=args.batch_size_kg):
             if 0 <= args.max_kg_iters <= it:
@@ -147,10 +147,10 @@ def train_eval(args):
                 loss.backward()
             optimizer.step()
             optimizer.zero_grad()
-            total += loss.item()
+            total += loss.detach().double()         # summed on the device: no host sync per iteration
             if it % args.print_every == 0 or it == 1:
-                logging.info("Epoch {:04d} Iter {:04d} | Loss {:.4f} ".format(epoch, it, total / it))
-        logging.info('Time for KGE: {:.1f}s, loss {:.4f}'.format(time() - t0, total / max(it, 1)))
+                logging.info("Epoch {:04d} Iter {:04d} | Loss {:.4f} ".format(epoch, it, total.item() / it))
+        logging.info('Time for KGE: {:.1f}s, loss {:.4f}'.format(time() - t0, total.item() / max(it, 1)))
 
         # phase 2: attention refresh (kgat.py:139-145)
         if args.use_attention:
@@ -162,7 +162,7 @@ def train_eval(args):
             logging.info("Time for attention: {:.3f}s".format(time() - t0))
 
         # phase 3: CF (kgat.py:146-168)
-        t0, it, total = time(), 0, 0.0
+        t0, it, total = time(), 0, th.zeros((), dtype=th.float64, device=dev)
         for user_ids, item_pos_ids, item_neg_ids, _ in dataset.CF_pair_sampler(batch_size=args.batch_size):
             if 0 <= args.max_cf_iters <= it:
                 break
@@ -178,10 +178,10 @@ def train_eval(args):
                 loss.backward()
             optimizer.step()
             optimizer.zero_grad()
-            total += loss.item()
+            total += loss.detach().double()         # summed on the device: no host sync per iteration
             if it % args.print_every == 0 or it == 1:
-                logging.info("Epoch {:04d} Iter {:04d} | Loss {:.4f} ".format(epoch, it, total / it))
-        logging.info('Time for GNN: {:.1f}s, loss {:.4f}'.format(time() - t0, total / max(it, 1)))
+                logging.info("Epoch {:04d} Iter {:04d} | Loss {:.4f} ".format(epoch, it, total.item() / it))
+        logging.info('Time for GNN: {:.1f}s, loss {:.4f}'.format(time() - t0, total.item() / max(it, 1)))
 
         if epoch % args.evaluate_every == 0:                 # kgat.py:171-196
             t0 = time()

@@ -115,7 +115,13 @@ class Model(nn.Module):
 
     # ------------------------------------------------------------------ KG-embedding mode
     def transR(self, h, r, pos_t, neg_t):
-        """TransR pairwise ranking loss on L2-normalised projections (models.py:114-133)."""
+        """TransR pairwise ranking loss on L2-normalised projections (models.py:114-133).  On the GPU,
+        for 64-wide embeddings, loss and gradients come from one relation-grouped library call
+        (``ops.TransRLoss``); the plain formula below is the same arithmetic for every other shape."""
+        if h.dim() == 1 and ops.transr_supported(self.entity_embed.weight, self.relation_embed.weight, self.W_R,
+                                                 h.numel()):
+            return ops.transr_loss(self.entity_embed.weight, self.relation_embed.weight, self.W_R, h, r, pos_t,
+                                   neg_t, self._reg_lambda_kg)
         h_embed = self.entity_embed(h)
         r_embed = self.relation_embed(r)
         pos_t_embed = self.entity_embed(pos_t)

@@ -341,3 +341,48 @@ def score_topk(emb: th.Tensor, user_ids: th.Tensor, item_ids: th.Tensor, mask_pt
                                            _lib.ptr(mask_items) if mask_items is not None and mask_items.numel() else None,
                                            K, topk.data_ptr(), _lib.ptr(scores), _lib.stream_ptr()), "kgat_score_topk")
     return (topk, scores) if want_scores else topk
+
+
+# --------------------------------------------------------------------------- TransR step
+def transr_supported(entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Tensor, batch: int) -> bool:
+    """Shapes ``kgat_transr_fwd_bwd`` covers (anything else goes through the plain torch formula)."""
+    return (entity.is_cuda and entity.dtype == th.float32 and entity.shape[1] == 64 and rel_emb.shape[1] == 64
+            and W_R.shape[0] <= 1024 and 0 < 3 * batch <= 16384)
+
+
+class TransRLoss(th.autograd.Function):
+    """Model.transR (reference models.py:114-133) with loss and all three parameter gradients
+    produced by one library call in ``forward``; ``backward`` scales them by the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, entity, rel_emb, W_R, h, r, pos_t, neg_t, reg_lambda):
+        lib = _lib.load()
+        dev = entity.device
+        ent, rel, W = (_f32c(t.detach(), dev) for t in (entity, rel_emb, W_R))
+        ids = [t.to(device=dev, dtype=th.long).contiguous() for t in (h, r, pos_t, neg_t)]
+        B, R = ids[0].numel(), rel.shape[0]
+        ws_bytes = lib.kgat_transr_workspace_bytes(B, R)
+        ws = th.empty(ws_bytes, dtype=th.uint8, device=dev)
+        loss = th.empty((), dtype=th.float32, device=dev)
+        d_ent, d_rel, d_W = th.empty_like(ent), th.empty_like(rel), th.empty_like(W)
+        with th.cuda.device(dev):
+            with _lib.record("transr_fwd_bwd", 5):
+                _lib.check(lib.kgat_transr_fwd_bwd(ent.data_ptr(), ent.shape[0], rel.data_ptr(), W.data_ptr(), R,
+                                                   ent.shape[1], rel.shape[1], ids[0].data_ptr(), ids[1].data_ptr(),
+                                                   ids[2].data_ptr(), ids[3].data_ptr(), B, float(reg_lambda),
+                                                   loss.data_ptr(), d_ent.data_ptr(), d_rel.data_ptr(), d_W.data_ptr(),
+                                                   ws.data_ptr(), ws_bytes, _lib.stream_ptr()), "kgat_transr_fwd_bwd")
+        ctx.save_for_backward(d_ent, d_rel, d_W)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        d_ent, d_rel, d_W = ctx.saved_tensors
+        g = grad_loss.to(d_ent.dtype)
+        need = ctx.needs_input_grad
+        return (d_ent * g if need[0] else None, d_rel * g if need[1] else None, d_W * g if need[2] else None,
+                None, None, None, None, None)
+
+
+def transr_loss(entity, rel_emb, W_R, h, r, pos_t, neg_t, reg_lambda):
+    return TransRLoss.apply(entity, rel_emb, W_R, h, r, pos_t, neg_t, reg_lambda)

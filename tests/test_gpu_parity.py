@@ -637,3 +637,77 @@ def test_tiny_and_ragged_graphs(dev, N, E):
     k = "entity_embed.weight"
     tol = max(RTOL, 2.0 * max_rel(grads32[k].numpy(), grads64[k].numpy()))
     assert max_rel(m.entity_embed.weight.grad.cpu().numpy(), grads64[k].numpy()) < tol
+
+
+# --------------------------------------------------------------------------- TransR step
+def _transr_oracle(m, ids, lam, dtype):
+    p = {k: v.detach().clone().requires_grad_(k in ("entity_embed.weight", "relation_embed.weight", "W_R"))
+         for k, v in cpu_params(m, dtype).items()}
+    loss = kgat_ref.transr_loss(p, *ids, lam)
+    loss.backward()
+    return loss.detach(), {k: p[k].grad for k in ("entity_embed.weight", "relation_embed.weight", "W_R")}
+
+
+@pytest.mark.parametrize("B", [2, 33, 300, 2048, 5461])
+def test_transr_fused_step_vs_fp64_oracle(dev, B):
+    """Loss and the three dense gradients of the relation-grouped TransR call against autograd through
+    the oracle's per-sample formulation: ragged chunks, duplicate entities, relations without samples."""
+    ck = synth_ckg("tiny")
+    N, R = ck.cfg.n_nodes, ck.cfg.n_relations
+    m = make_model(N, R, dev)
+    rng = np.random.default_rng(B)
+    rels = rng.choice(R, size=max(1, R - 3), replace=False)            # some relations stay empty
+    ids = [th.as_tensor(rng.integers(0, N // 20 + 1, B)), th.as_tensor(rng.choice(rels, B)),
+           th.as_tensor(rng.integers(0, N, B)), th.as_tensor(rng.integers(0, N // 20 + 1, B))]
+    assert ops.transr_supported(m.entity_embed.weight, m.relation_embed.weight, m.W_R, B)
+    loss = m.transR(*[i.to(dev) for i in ids])
+    loss.backward()
+    loss64, g64 = _transr_oracle(m, ids, m._reg_lambda_kg, th.float64)
+    _, g32 = _transr_oracle(m, ids, m._reg_lambda_kg, th.float32)
+    assert abs(loss.item() - loss64.item()) < 1e-5 * abs(loss64.item())
+    got = {"entity_embed.weight": m.entity_embed.weight.grad, "relation_embed.weight": m.relation_embed.weight.grad,
+           "W_R": m.W_R.grad}
+    for k, g in got.items():
+        bound = max(RTOL, 2.0 * max_rel(g32[k].numpy(), g64[k].numpy()))
+        assert max_rel(g.cpu().numpy(), g64[k].numpy()) < bound, k
+    # rows of entities outside the batch are exactly zero; relations without samples too
+    touched = np.zeros(N, bool)
+    for t in (ids[0], ids[2], ids[3]):
+        touched[t.numpy()] = True
+    assert np.all(got["entity_embed.weight"].cpu().numpy()[~touched] == 0)
+    empty = np.setdiff1d(np.arange(R), ids[1].numpy())
+    assert np.all(got["W_R"].cpu().numpy()[empty] == 0) and np.all(got["relation_embed.weight"].cpu().numpy()[empty] == 0)
+
+
+def test_transr_fused_is_deterministic_and_scales_with_upstream_gradient(dev):
+    ck = synth_ckg("tiny")
+    N, R = ck.cfg.n_nodes, ck.cfg.n_relations
+    m = make_model(N, R, dev)
+    rng = np.random.default_rng(3)
+    ids = [th.as_tensor(rng.integers(0, 50, 1000)).to(dev), th.as_tensor(rng.integers(0, R, 1000)).to(dev),
+           th.as_tensor(rng.integers(0, 50, 1000)).to(dev), th.as_tensor(rng.integers(0, 50, 1000)).to(dev)]
+    grads = []
+    for scale in (1.0, 1.0, 3.0):
+        m.zero_grad(set_to_none=True)
+        (m.transR(*ids) * scale).backward()
+        grads.append([p.grad.clone() for p in (m.entity_embed.weight, m.relation_embed.weight, m.W_R)])
+    for a, b, c in zip(*grads):
+        assert th.equal(a, b)                                      # bit-identical run to run
+        assert th.allclose(c, 3.0 * a, rtol=1e-6, atol=0)
+
+
+def test_transr_unsupported_shapes_use_the_plain_formula(dev):
+    ck = synth_ckg("tiny")
+    N, R = ck.cfg.n_nodes, ck.cfg.n_relations
+    m = make_model(N, R, dev, d=32, hidden=32, layers=1, rd=32)
+    ids = [th.zeros(8, dtype=th.long, device=dev)] * 4
+    assert not ops.transr_supported(m.entity_embed.weight, m.relation_embed.weight, m.W_R, 8)
+    m.transR(*ids).backward()
+    assert m.W_R.grad is not None
+    # and the library itself refuses rather than guessing
+    lib = _lib.load()
+    z = th.zeros(64, device=dev)
+    rc = lib.kgat_transr_fwd_bwd(z.data_ptr(), 1, z.data_ptr(), z.data_ptr(), 1, 32, 32, ids[0].data_ptr(),
+                                 ids[0].data_ptr(), ids[0].data_ptr(), ids[0].data_ptr(), 8, 0.0, z.data_ptr(),
+                                 z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1 << 20, _lib.stream_ptr())
+    assert rc == -2
