@@ -6,14 +6,18 @@
 //        + lambda * mean over the batch of (|v_h|^2 + |r_v|^2 + |v_p|^2 + |v_n|^2) / 2
 // The reference gathers W_R[r] per sample (a (B, d, rd) tensor, models.py:46-47) and runs three bmm;
 // here the batch is grouped by relation so W_r is staged once per 32-sample chunk:
-//   plan     (one CTA) bitonic sort of (relation, sample) -> chunk table; bitonic sort of
-//            (node, gradient row) for the 3B entity rows -> the order their gradients are summed in;
+//   plan     (one CTA) stable partition of the samples by relation (per-warp match/ballot counts) ->
+//            chunk table; bitonic sort of (node, gradient row) for the 3B entity rows -> the order
+//            their gradients are summed in;
 //   main     one CTA per chunk: gather the 96 entity rows, V = E W_r, per-sample normalise / scores /
 //            loss / gradient of the projections, dE = G W_r^T (rows written per sample),
-//            dW_r partial = E^T G, d e_r partial, loss partial;
-//   reduce   per relation, partials added in chunk order (fp64) -> d_W, d_rel; loss;
-//   scatter  one warp per distinct node adds its gradient rows in sorted order -> d_entity.
-// Deterministic: no atomics, every sum has a fixed order.  d = rd = 64, 3 * batch <= 16384.
+//            dW_r partial = E^T G, d e_r partial, loss partial; the last CTA to finish adds the loss
+//            partials in chunk order;
+//   reduce   (backward) per relation, partials added in chunk order (fp64), times the upstream
+//            gradient -> d_W, d_rel;
+//   scatter  (backward) one warp per distinct node adds its gradient rows in sorted order -> d_entity.
+// Deterministic: every sum has a fixed order (the one atomic is the CTA-completion counter).
+// d = rd = 64, 3 * batch <= 16384.
 #include "common.cuh"
 
 namespace kgat {
@@ -28,6 +32,7 @@ constexpr int MAX_ROWS = 16384;         // 3 * batch, bitonic-sorted in shared m
 
 struct Ws {
     int32_t *order_rel, *chunk_rel, *chunk_start, *chunk_cnt, *rel_chunk0, *n_chunks, *ent_node, *ent_row;
+    unsigned* done;
     float *dE_rows, *dW_part, *drel_part;
     double* loss_part;
     size_t bytes;
@@ -47,6 +52,7 @@ Ws carve(void* base, int64_t B, int64_t R) {
     w.chunk_cnt = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * maxc));
     w.rel_chunk0 = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (R + 1)));
     w.n_chunks = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
+    w.done = reinterpret_cast<unsigned*>(take(sizeof(unsigned)));
     w.ent_node = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * P));
     w.ent_row = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * P));
     w.dE_rows = reinterpret_cast<float*>(take(sizeof(float) * P * D));
@@ -60,63 +66,129 @@ Ws carve(void* base, int64_t B, int64_t R) {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-__device__ void bitonic_sort(unsigned long long* keys, int n) {      // n: power of two, whole CTA
+constexpr int PLAN_THREADS = 1024;
+constexpr int PLAN_WARPS = PLAN_THREADS / 32;
+constexpr int MAX_ROUNDS = (MAX_ROWS / 3 + PLAN_THREADS - 1) / PLAN_THREADS;     // samples per plan thread
+
+// Bitonic sort of n (power of two, >= 32 * ... handled below) DISTINCT keys in shared memory by the whole
+// CTA.  Compare-exchange distances below 32 stay inside a warp: those steps run on registers with
+// shuffles (element e lives in thread e % 1024, slot e / 1024), so only the long distances pay a
+// __syncthreads; the shared-memory steps enumerate PAIRS, so no thread idles.
+template <typename K>
+__device__ __forceinline__ K shfl_xor_key(K v, int j) {
+    if constexpr (sizeof(K) == 8) {
+        const unsigned lo = __shfl_xor_sync(FULL_MASK, static_cast<unsigned>(v), j);
+        const unsigned hi = __shfl_xor_sync(FULL_MASK, static_cast<unsigned>(v >> 32), j);
+        return (static_cast<K>(hi) << 32) | lo;
+    } else {
+        return __shfl_xor_sync(FULL_MASK, v, j);
+    }
+}
+
+template <typename K>
+__device__ void bitonic_sort(K* keys, int n) {
+    const int tid = threadIdx.x;
     for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const int x = i ^ j;
-                if (x > i) {
-                    const unsigned long long a = keys[i], b = keys[x];
-                    if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[x] = a; }
-                }
+        int j = k >> 1;
+        for (; j >= 32; j >>= 1) {                       // long distances: shared memory, one pair per step
+            for (int t = tid; t < (n >> 1); t += PLAN_THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), x = i | j;
+                const K a = keys[i], b = keys[x];
+                if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[x] = a; }
             }
             __syncthreads();
         }
+        // distances 16..1 (or k/2..1 for the first stages): registers + shuffles
+        for (int e = tid; e < n; e += PLAN_THREADS) {
+            K v = keys[e];
+            const bool up = (e & k) == 0;
+            for (int jj = j; jj > 0; jj >>= 1) {
+                const K o = shfl_xor_key<K>(v, jj);
+                const bool lower = (e & jj) == 0;
+                v = (lower == up) ? (v < o ? v : o) : (v < o ? o : v);
+            }
+            keys[e] = v;
+        }
+        __syncthreads();
     }
 }
 
-__device__ __forceinline__ int lower_bound_key(const unsigned long long* keys, int n, unsigned long long v) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (keys[mid] < v) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-__global__ void __launch_bounds__(1024)
+// Shared memory is used twice: first as the per-warp relation counters of the stable partition, then as
+// the key array of the entity-row sort.
+template <typename K>
+__global__ void __launch_bounds__(PLAN_THREADS)
 transr_plan_kernel(const int64_t* __restrict__ h, const int64_t* __restrict__ r, const int64_t* __restrict__ pos,
-                   const int64_t* __restrict__ neg, int B, int R, int n2_rel, int n2_ent,
+                   const int64_t* __restrict__ neg, int B, int R, int n2_ent, int idx_bits,
                    int32_t* __restrict__ order_rel, int32_t* __restrict__ chunk_rel,
                    int32_t* __restrict__ chunk_start, int32_t* __restrict__ chunk_cnt,
-                   int32_t* __restrict__ rel_chunk0, int32_t* __restrict__ n_chunks,
+                   int32_t* __restrict__ rel_chunk0, int32_t* __restrict__ n_chunks, unsigned* __restrict__ done,
                    int32_t* __restrict__ ent_node, int32_t* __restrict__ ent_row) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
-    __shared__ int sStart[MAX_REL + 1], sC0[MAX_REL + 1];
-    const int tid = threadIdx.x;
+    __shared__ int sStart[MAX_REL + 1], sC0[MAX_REL + 1], sTot[MAX_REL];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) *done = 0;
 
-    // samples by (relation, index)
-    for (int i = tid; i < n2_rel; i += blockDim.x)
-        keys[i] = i < B ? (static_cast<unsigned long long>(r[i]) << 32) | static_cast<unsigned>(i) : ~0ull;
+    // ---- samples grouped by relation, original order kept inside a relation (stable partition):
+    // warp w owns the contiguous samples [w * per, (w + 1) * per); cnt[w][rel] counts what it has seen.
+    int* cnt = reinterpret_cast<int*>(smem_raw);
+    for (int i = tid; i < PLAN_WARPS * R; i += PLAN_THREADS) cnt[i] = 0;
     __syncthreads();
-    bitonic_sort(keys, n2_rel);
-    for (int i = tid; i < B; i += blockDim.x) order_rel[i] = static_cast<int32_t>(keys[i] & 0xffffffffu);
-    for (int rr = tid; rr <= R; rr += blockDim.x)
-        sStart[rr] = lower_bound_key(keys, B, static_cast<unsigned long long>(rr) << 32);
-    __syncthreads();
-    if (tid == 0) {
-        int c = 0;
-        for (int rr = 0; rr < R; ++rr) {
-            sC0[rr] = c;
-            c += (sStart[rr + 1] - sStart[rr] + T - 1) / T;
-        }
-        sC0[R] = c;
-        *n_chunks = c;
+    const int per = ((B + PLAN_WARPS - 1) / PLAN_WARPS + 31) & ~31;
+    const int wbeg = warp * per, wend = min(B, wbeg + per);
+    int my_rel[MAX_ROUNDS], my_pref[MAX_ROUNDS];
+#pragma unroll
+    for (int rd = 0; rd < MAX_ROUNDS; ++rd) {
+        const int i = wbeg + rd * 32 + lane;
+        const bool valid = rd * 32 < per && i < wend;
+        const int rel = valid ? static_cast<int>(r[i]) : -1;
+        const unsigned m = __match_any_sync(FULL_MASK, rel);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        int prev = 0;
+        if (valid) prev = cnt[warp * R + rel];
+        __syncwarp();
+        if (valid && rank == 0) cnt[warp * R + rel] = prev + __popc(m);
+        __syncwarp();
+        my_rel[rd] = rel;
+        my_pref[rd] = prev + rank;
     }
     __syncthreads();
-    for (int rr = tid; rr <= R; rr += blockDim.x) rel_chunk0[rr] = sC0[rr];
-    for (int rr = tid; rr < R; rr += blockDim.x) {
+    for (int rr = tid; rr < R; rr += PLAN_THREADS) {     // exclusive scan over the warps, per relation
+        int run = 0;
+        for (int w = 0; w < PLAN_WARPS; ++w) {
+            const int t = cnt[w * R + rr];
+            cnt[w * R + rr] = run;
+            run += t;
+        }
+        sTot[rr] = run;
+    }
+    __syncthreads();
+    if (warp == 0) {                                     // scan over relations: lane l takes a contiguous block
+        const int blk = (R + 31) / 32, b0 = min(R, lane * blk), b1 = min(R, b0 + blk);
+        int tot = 0, totc = 0;
+        for (int rr = b0; rr < b1; ++rr) { tot += sTot[rr]; totc += (sTot[rr] + T - 1) / T; }
+        int inc = tot, incc = totc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL_MASK, inc, o), vc = __shfl_up_sync(FULL_MASK, incc, o);
+            if (lane >= o) { inc += v; incc += vc; }
+        }
+        int run = inc - tot, runc = incc - totc;
+        for (int rr = b0; rr < b1; ++rr) {
+            sStart[rr] = run;
+            sC0[rr] = runc;
+            run += sTot[rr];
+            runc += (sTot[rr] + T - 1) / T;
+        }
+        if (lane == 31) { sStart[R] = inc; sC0[R] = incc; *n_chunks = incc; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rd = 0; rd < MAX_ROUNDS; ++rd) {
+        const int i = wbeg + rd * 32 + lane;
+        if (my_rel[rd] >= 0) order_rel[sStart[my_rel[rd]] + cnt[warp * R + my_rel[rd]] + my_pref[rd]] = i;
+    }
+    for (int rr = tid; rr <= R; rr += PLAN_THREADS) rel_chunk0[rr] = sC0[rr];
+    for (int rr = tid; rr < R; rr += PLAN_THREADS) {
         const int s = sStart[rr], e = sStart[rr + 1];
         for (int c = sC0[rr], b = s; b < e; ++c, b += T) {
             chunk_rel[c] = rr;
@@ -126,21 +198,23 @@ transr_plan_kernel(const int64_t* __restrict__ h, const int64_t* __restrict__ r,
     }
     __syncthreads();
 
-    // entity gradient rows by (node, row): row = set * B + sample
+    // ---- entity gradient rows by (node, row): row = set * B + sample
+    K* keys = reinterpret_cast<K*>(smem_raw);
     const int P = 3 * B;
-    for (int i = tid; i < n2_ent; i += blockDim.x) {
-        unsigned long long k = ~0ull;
+    for (int i = tid; i < n2_ent; i += PLAN_THREADS) {
+        K k = ~static_cast<K>(0);
         if (i < P) {
             const int64_t node = i < B ? h[i] : (i < 2 * B ? pos[i - B] : neg[i - 2 * B]);
-            k = (static_cast<unsigned long long>(node) << 32) | static_cast<unsigned>(i);
+            k = (static_cast<K>(node) << idx_bits) | static_cast<K>(i);
         }
         keys[i] = k;
     }
     __syncthreads();
-    bitonic_sort(keys, n2_ent);
-    for (int i = tid; i < P; i += blockDim.x) {
-        ent_node[i] = static_cast<int32_t>(keys[i] >> 32);
-        ent_row[i] = static_cast<int32_t>(keys[i] & 0xffffffffu);
+    bitonic_sort<K>(keys, n2_ent);
+    const K idx_mask = (static_cast<K>(1) << idx_bits) - 1;
+    for (int i = tid; i < P; i += PLAN_THREADS) {
+        ent_node[i] = static_cast<int32_t>(keys[i] >> idx_bits);
+        ent_row[i] = static_cast<int32_t>(keys[i] & idx_mask);
     }
 }
 
@@ -173,10 +247,12 @@ transr_main_kernel(const float* __restrict__ entity, const float* __restrict__ r
                    const int64_t* __restrict__ neg, int B, float lambda,
                    const int32_t* __restrict__ order_rel, const int32_t* __restrict__ chunk_rel,
                    const int32_t* __restrict__ chunk_start, const int32_t* __restrict__ chunk_cnt,
-                   const int32_t* __restrict__ n_chunks, float* __restrict__ dE_rows,
-                   float* __restrict__ dW_part, float* __restrict__ drel_part, double* __restrict__ loss_part) {
+                   const int32_t* __restrict__ n_chunks, unsigned* __restrict__ done, float* __restrict__ dE_rows,
+                   float* __restrict__ dW_part, float* __restrict__ drel_part, double* __restrict__ loss_part,
+                   float* __restrict__ loss) {
     const int c = blockIdx.x;
-    if (c >= *n_chunks) return;
+    const int nc = *n_chunks;
+    if (c >= nc) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MainSmem& s = *reinterpret_cast<MainSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -343,18 +419,37 @@ transr_main_kernel(const float* __restrict__ entity, const float* __restrict__ r
         for (int a = 0; a < 4; ++a)
             *reinterpret_cast<float4*>(out + (k0 + a) * D + n0) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
     }
+
+    // ---- the last chunk to finish adds the loss partials, always in chunk order
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(done, 1u) == static_cast<unsigned>(nc - 1);
+    __syncthreads();
+    if (is_last && warp == 0) {
+        __threadfence();
+        double a = 0.0;
+        for (int c0 = 0; c0 < nc; c0 += 32) {            // 32 partials per pass, combined in a fixed tree
+            double v = c0 + lane < nc ? __ldcg(loss_part + c0 + lane) : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+            a += v;
+        }
+        if (lane == 0) *loss = static_cast<float>(a / static_cast<double>(B));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// reduce: grid (R, 4); CTA (rel, quarter) sums its quarter of d_W[rel] over the relation's chunks
+// backward.  reduce: grid (R, 4); CTA (rel, quarter) sums its quarter of d_W[rel] over the relation's
+// chunks.  grad: device scalar, the upstream gradient of the loss (null = 1).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-transr_reduce_kernel(const int32_t* __restrict__ rel_chunk0, const int32_t* __restrict__ n_chunks,
-                     const float* __restrict__ dW_part, const float* __restrict__ drel_part,
-                     const double* __restrict__ loss_part, int B, float* __restrict__ d_W,
-                     float* __restrict__ d_rel, float* __restrict__ loss) {
+transr_reduce_kernel(const int32_t* __restrict__ rel_chunk0, const float* __restrict__ dW_part,
+                     const float* __restrict__ drel_part, const float* __restrict__ grad,
+                     float* __restrict__ d_W, float* __restrict__ d_rel) {
     const int rel = blockIdx.x, quarter = blockIdx.y, tid = threadIdx.x;
     const int c0 = rel_chunk0[rel], c1 = rel_chunk0[rel + 1];
+    const double g = grad ? static_cast<double>(*grad) : 1.0;
     const int e = quarter * 1024 + tid * 4;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     for (int c = c0; c < c1; ++c) {
@@ -362,37 +457,32 @@ transr_reduce_kernel(const int32_t* __restrict__ rel_chunk0, const int32_t* __re
         a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
     }
     *reinterpret_cast<float4*>(d_W + static_cast<size_t>(rel) * D * D + e) =
-        make_float4(static_cast<float>(a0), static_cast<float>(a1), static_cast<float>(a2), static_cast<float>(a3));
+        make_float4(static_cast<float>(a0 * g), static_cast<float>(a1 * g), static_cast<float>(a2 * g),
+                    static_cast<float>(a3 * g));
     if (quarter == 0 && tid < D) {
         double a = 0.0;
         for (int c = c0; c < c1; ++c) a += drel_part[static_cast<size_t>(c) * D + tid];
-        d_rel[static_cast<size_t>(rel) * D + tid] = static_cast<float>(a);
-    }
-    if (rel == 0 && quarter == 1 && tid == 0) {
-        double a = 0.0;
-        const int nc = *n_chunks;
-        for (int c = 0; c < nc; ++c) a += loss_part[c];
-        *loss = static_cast<float>(a / static_cast<double>(B));
+        d_rel[static_cast<size_t>(rel) * D + tid] = static_cast<float>(a * g);
     }
 }
 
-// ------------------------------------------------------------------------------------------------
 // scatter: one warp per sorted position that starts a run of equal nodes
-// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 transr_scatter_kernel(const int32_t* __restrict__ ent_node, const int32_t* __restrict__ ent_row, int P,
-                      const float* __restrict__ dE_rows, float* __restrict__ d_entity) {
+                      const float* __restrict__ dE_rows, const float* __restrict__ grad,
+                      float* __restrict__ d_entity) {
     const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (p >= P) return;
     const int node = ent_node[p];
     if (p > 0 && ent_node[p - 1] == node) return;
+    const float g = grad ? *grad : 1.0f;
     float2 acc = make_float2(0.f, 0.f);
     for (int q = p; q < P && ent_node[q] == node; ++q) {
         const float2 v = *reinterpret_cast<const float2*>(dE_rows + static_cast<size_t>(ent_row[q]) * D + lane * 2);
         acc.x += v.x;
         acc.y += v.y;
     }
-    *reinterpret_cast<float2*>(d_entity + static_cast<size_t>(node) * D + lane * 2) = acc;
+    *reinterpret_cast<float2*>(d_entity + static_cast<size_t>(node) * D + lane * 2) = make_float2(acc.x * g, acc.y * g);
 }
 
 int next_pow2(int64_t n) {
@@ -411,44 +501,73 @@ extern "C" size_t kgat_transr_workspace_bytes(int64_t batch, int64_t n_rel) {
     return carve(nullptr, batch, n_rel).bytes;
 }
 
-extern "C" int kgat_transr_fwd_bwd(const float* entity, int64_t n_nodes, const float* rel_emb, const float* W_R,
-                                   int64_t n_rel, int d, int rd, const int64_t* h, const int64_t* r,
-                                   const int64_t* pos_t, const int64_t* neg_t, int64_t batch, float reg_lambda,
-                                   float* loss, float* d_entity, float* d_rel, float* d_W, void* workspace,
-                                   size_t workspace_bytes, kgat_stream_t stream) {
-    KGAT_REQUIRE(entity && rel_emb && W_R && h && r && pos_t && neg_t && loss && d_entity && d_rel && d_W);
+static int transr_check(int64_t n_nodes, int64_t n_rel, int d, int rd, int64_t batch) {
     KGAT_REQUIRE(n_nodes > 0 && n_rel > 0 && batch > 0);
-    KGAT_REQUIRE(aligned16(entity) && aligned16(rel_emb) && aligned16(W_R) && aligned16(d_entity) &&
-                 aligned16(d_rel) && aligned16(d_W) && aligned16(workspace));
     if (d != D || rd != D || n_rel > MAX_REL || 3 * batch > MAX_ROWS) return KGAT_ERR_UNSUPPORTED_DIM;
+    return KGAT_OK;
+}
+
+extern "C" int kgat_transr_fwd(const float* entity, int64_t n_nodes, const float* rel_emb, const float* W_R,
+                               int64_t n_rel, int d, int rd, const int64_t* h, const int64_t* r,
+                               const int64_t* pos_t, const int64_t* neg_t, int64_t batch, float reg_lambda,
+                               float* loss, void* workspace, size_t workspace_bytes, kgat_stream_t stream) {
+    KGAT_REQUIRE(entity && rel_emb && W_R && h && r && pos_t && neg_t && loss);
+    KGAT_REQUIRE(aligned16(entity) && aligned16(rel_emb) && aligned16(W_R) && aligned16(workspace));
+    if (const int rc = transr_check(n_nodes, n_rel, d, rd, batch)) return rc;
     const Ws w = carve(workspace, batch, n_rel);
     if (!workspace || workspace_bytes < w.bytes) return KGAT_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
     const int B = static_cast<int>(batch), R = static_cast<int>(n_rel), P = 3 * B;
-    const int n2_rel = next_pow2(B), n2_ent = next_pow2(P);
+    const int n2_ent = next_pow2(P) < PLAN_THREADS ? PLAN_THREADS : next_pow2(P);
+    int idx_bits = 0;
+    while ((1 << idx_bits) < n2_ent) ++idx_bits;
+    const bool narrow = n_nodes < (static_cast<int64_t>(1) << (32 - idx_bits));      // (node, row) fits 32 bits
+    const size_t key_bytes = static_cast<size_t>(n2_ent) * (narrow ? 4 : 8);
+    const size_t cnt_bytes = sizeof(int) * PLAN_WARPS * static_cast<size_t>(R);
+    const size_t plan_smem = key_bytes > cnt_bytes ? key_bytes : cnt_bytes;
 
     static bool configured = false;
     if (!configured) {
-        KGAT_CUDA(cudaFuncSetAttribute(transr_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       MAX_ROWS * (int)sizeof(unsigned long long)));
+        const int plan_max = MAX_ROWS * (int)sizeof(unsigned long long);
+        KGAT_CUDA(cudaFuncSetAttribute(transr_plan_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       plan_max));
+        KGAT_CUDA(cudaFuncSetAttribute(transr_plan_kernel<unsigned long long>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, plan_max));
         KGAT_CUDA(cudaFuncSetAttribute(transr_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(MainSmem)));
         configured = true;
     }
-    KGAT_CUDA(cudaMemsetAsync(d_entity, 0, sizeof(float) * static_cast<size_t>(n_nodes) * D, st));
-    transr_plan_kernel<<<1, 1024, sizeof(unsigned long long) * n2_ent, st>>>(
-        h, r, pos_t, neg_t, B, R, n2_rel, n2_ent, w.order_rel, w.chunk_rel, w.chunk_start, w.chunk_cnt, w.rel_chunk0,
-        w.n_chunks, w.ent_node, w.ent_row);
+    if (narrow)
+        transr_plan_kernel<uint32_t><<<1, PLAN_THREADS, plan_smem, st>>>(
+            h, r, pos_t, neg_t, B, R, n2_ent, idx_bits, w.order_rel, w.chunk_rel, w.chunk_start, w.chunk_cnt,
+            w.rel_chunk0, w.n_chunks, w.done, w.ent_node, w.ent_row);
+    else
+        transr_plan_kernel<unsigned long long><<<1, PLAN_THREADS, plan_smem, st>>>(
+            h, r, pos_t, neg_t, B, R, n2_ent, idx_bits, w.order_rel, w.chunk_rel, w.chunk_start, w.chunk_cnt,
+            w.rel_chunk0, w.n_chunks, w.done, w.ent_node, w.ent_row);
     KGAT_LAUNCH_CHECK();
     const int max_chunks = B / T + R;
     transr_main_kernel<<<max_chunks, THREADS, sizeof(MainSmem), st>>>(
         entity, rel_emb, W_R, h, pos_t, neg_t, B, reg_lambda, w.order_rel, w.chunk_rel, w.chunk_start, w.chunk_cnt,
-        w.n_chunks, w.dE_rows, w.dW_part, w.drel_part, w.loss_part);
+        w.n_chunks, w.done, w.dE_rows, w.dW_part, w.drel_part, w.loss_part, loss);
     KGAT_LAUNCH_CHECK();
-    transr_reduce_kernel<<<dim3(R, 4), 256, 0, st>>>(w.rel_chunk0, w.n_chunks, w.dW_part, w.drel_part, w.loss_part, B,
-                                                     d_W, d_rel, loss);
+    return KGAT_OK;
+}
+
+extern "C" int kgat_transr_bwd(const float* grad_loss, int64_t n_nodes, int64_t n_rel, int d, int rd, int64_t batch,
+                               float* d_entity, float* d_rel, float* d_W, const void* workspace,
+                               size_t workspace_bytes, kgat_stream_t stream) {
+    KGAT_REQUIRE(d_entity && d_rel && d_W);
+    KGAT_REQUIRE(aligned16(d_entity) && aligned16(d_rel) && aligned16(d_W) && aligned16(workspace));
+    if (const int rc = transr_check(n_nodes, n_rel, d, rd, batch)) return rc;
+    const Ws w = carve(const_cast<void*>(workspace), batch, n_rel);
+    if (!workspace || workspace_bytes < w.bytes) return KGAT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    const int R = static_cast<int>(n_rel), P = 3 * static_cast<int>(batch);
+    KGAT_CUDA(cudaMemsetAsync(d_entity, 0, sizeof(float) * static_cast<size_t>(n_nodes) * D, st));
+    transr_reduce_kernel<<<dim3(R, 4), 256, 0, st>>>(w.rel_chunk0, w.dW_part, w.drel_part, grad_loss, d_W, d_rel);
     KGAT_LAUNCH_CHECK();
-    transr_scatter_kernel<<<(P + 7) / 8, 256, 0, st>>>(w.ent_node, w.ent_row, P, w.dE_rows, d_entity);
+    transr_scatter_kernel<<<(P + 7) / 8, 256, 0, st>>>(w.ent_node, w.ent_row, P, w.dE_rows, grad_loss, d_entity);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }

@@ -108,12 +108,17 @@ class DeviceEdgeBatchSampler:
         k = s * self.n_nodes + d
         return k if r is None else k * self._n_rel + r
 
+    # batches are drawn SUPER at a time (a handful of kernels over SUPER * batch_size edges) and handed
+    # out as views, so an iteration of the training loop costs no sampling launches of its own
+    SUPER = 64
+
     def __iter__(self):
         th = self.th
         E = self.src.shape[0]
         perm = th.randperm(E, device=self.device, generator=self.gen)
-        for b in range(0, E, self.batch_size):
-            eid = perm[b: b + self.batch_size]
+        span = self.batch_size * self.SUPER
+        for c in range(0, E, span):
+            eid = perm[c: c + span]
             s, d = self.src[eid], self.dst[eid]
             r = None if self.etype is None else self.etype[eid]
             corrupt = th.randint(0, self.n_nodes, (eid.shape[0],), device=self.device, generator=self.gen)
@@ -121,7 +126,9 @@ class DeviceEdgeBatchSampler:
             q = self._edge_key(ns, nd, r)
             pos = th.searchsorted(self._keys, q).clamp_(max=self._keys.shape[0] - 1)
             false_neg = (self._keys[pos] == q).to(th.long)
-            yield s, d, r, ns, nd, false_neg
+            for b in range(0, eid.shape[0], self.batch_size):
+                e = b + self.batch_size
+                yield (s[b:e], d[b:e], None if r is None else r[b:e], ns[b:e], nd[b:e], false_neg[b:e])
 
 
 class DataLoader(object):

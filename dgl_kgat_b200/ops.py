@@ -351,8 +351,9 @@ def transr_supported(entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Tensor, batc
 
 
 class TransRLoss(th.autograd.Function):
-    """Model.transR (reference models.py:114-133) with loss and all three parameter gradients
-    produced by one library call in ``forward``; ``backward`` scales them by the upstream gradient."""
+    """Model.transR (reference models.py:114-133): ``forward`` runs the relation-grouped pass that
+    yields the loss and leaves every gradient piece in the workspace; ``backward`` turns them into the
+    three dense gradients, scaled by the upstream gradient on the device."""
 
     @staticmethod
     def forward(ctx, entity, rel_emb, W_R, h, r, pos_t, neg_t, reg_lambda):
@@ -364,24 +365,33 @@ class TransRLoss(th.autograd.Function):
         ws_bytes = lib.kgat_transr_workspace_bytes(B, R)
         ws = th.empty(ws_bytes, dtype=th.uint8, device=dev)
         loss = th.empty((), dtype=th.float32, device=dev)
-        d_ent, d_rel, d_W = th.empty_like(ent), th.empty_like(rel), th.empty_like(W)
         with th.cuda.device(dev):
-            with _lib.record("transr_fwd_bwd", 5):
-                _lib.check(lib.kgat_transr_fwd_bwd(ent.data_ptr(), ent.shape[0], rel.data_ptr(), W.data_ptr(), R,
-                                                   ent.shape[1], rel.shape[1], ids[0].data_ptr(), ids[1].data_ptr(),
-                                                   ids[2].data_ptr(), ids[3].data_ptr(), B, float(reg_lambda),
-                                                   loss.data_ptr(), d_ent.data_ptr(), d_rel.data_ptr(), d_W.data_ptr(),
-                                                   ws.data_ptr(), ws_bytes, _lib.stream_ptr()), "kgat_transr_fwd_bwd")
-        ctx.save_for_backward(d_ent, d_rel, d_W)
+            with _lib.record("transr_fwd", 2):
+                _lib.check(lib.kgat_transr_fwd(ent.data_ptr(), ent.shape[0], rel.data_ptr(), W.data_ptr(), R,
+                                               ent.shape[1], rel.shape[1], ids[0].data_ptr(), ids[1].data_ptr(),
+                                               ids[2].data_ptr(), ids[3].data_ptr(), B, float(reg_lambda),
+                                               loss.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()),
+                           "kgat_transr_fwd")
+        ctx.save_for_backward(ws)
+        ctx.shapes = (tuple(ent.shape), tuple(rel.shape), tuple(W.shape), B)
         return loss
 
     @staticmethod
     def backward(ctx, grad_loss):
-        d_ent, d_rel, d_W = ctx.saved_tensors
-        g = grad_loss.to(d_ent.dtype)
-        need = ctx.needs_input_grad
-        return (d_ent * g if need[0] else None, d_rel * g if need[1] else None, d_W * g if need[2] else None,
-                None, None, None, None, None)
+        lib = _lib.load()
+        (ws,) = ctx.saved_tensors
+        es, rs, Ws_, B = ctx.shapes
+        dev = ws.device
+        g = grad_loss.to(device=dev, dtype=th.float32).contiguous()
+        d_ent = th.empty(es, dtype=th.float32, device=dev)
+        d_rel = th.empty(rs, dtype=th.float32, device=dev)
+        d_W = th.empty(Ws_, dtype=th.float32, device=dev)
+        with th.cuda.device(dev):
+            with _lib.record("transr_bwd", 3):
+                _lib.check(lib.kgat_transr_bwd(g.data_ptr(), es[0], rs[0], es[1], rs[1], B, d_ent.data_ptr(),
+                                               d_rel.data_ptr(), d_W.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               _lib.stream_ptr()), "kgat_transr_bwd")
+        return d_ent, d_rel, d_W, None, None, None, None, None
 
 
 def transr_loss(entity, rel_emb, W_R, h, r, pos_t, neg_t, reg_lambda):

@@ -189,23 +189,27 @@ KGAT_API int kgat_bpr_loss_bwd(const float* emb, int64_t emb_stride, int dim, co
                       float* rows, int32_t* rows_node, int32_t* row_slot,
                       void* workspace, size_t workspace_bytes, kgat_stream_t stream);
 
-/* (6) TransR step of the KG phase -- replaces Model.transR (models.py:114-133, :46-47) AND its
- *     autograd in one call:
+/* (6) TransR step of the KG phase -- replaces Model.transR (models.py:114-133, :46-47) and its
+ *     autograd:
  *       v_x  = normalize(e_x W_R[r]) for x in {h, pos_t, neg_t};  r_v = normalize(rel_emb[r])
  *       loss = mean(-logsigmoid(|v_h + r_v - v_n|^2 - |v_h + r_v - v_p|^2))
  *            + reg_lambda * mean_b((|v_h|^2 + |r_v|^2 + |v_p|^2 + |v_n|^2) / 2)
- *     Writes the scalar loss and the DENSE gradients the reference's optimizer sees:
+ *     fwd writes the scalar loss and leaves the per-sample / per-chunk gradient pieces in the
+ *     workspace; bwd (same workspace, untouched in between) scales them by the upstream gradient
+ *     (device scalar, null = 1) and writes the DENSE gradients the reference's optimizer sees:
  *     d_entity (n_nodes, d) in full (zero rows for entities not in the batch), d_rel (n_rel, rd),
  *     d_W (n_rel, d, rd).  int64 ids as kgat.py:117-126 produces them, in range like nn.Embedding
  *     requires.  The batch is grouped by relation so W_R[r] is staged once per 32 samples instead of
- *     gathered per sample.  Deterministic (sorted, fixed-order sums; no atomics).
+ *     gathered per sample.  Deterministic (sorted, fixed-order sums).
  *     d = rd = 64, n_rel <= 1024 and 3 * batch <= 16384, else KGAT_ERR_UNSUPPORTED_DIM. */
 KGAT_API size_t kgat_transr_workspace_bytes(int64_t batch, int64_t n_rel);
-KGAT_API int kgat_transr_fwd_bwd(const float* entity, int64_t n_nodes, const float* rel_emb, const float* W_R,
-                        int64_t n_rel, int d, int rd, const int64_t* h, const int64_t* r,
-                        const int64_t* pos_t, const int64_t* neg_t, int64_t batch, float reg_lambda,
-                        float* loss, float* d_entity, float* d_rel, float* d_W,
-                        void* workspace, size_t workspace_bytes, kgat_stream_t stream);
+KGAT_API int kgat_transr_fwd(const float* entity, int64_t n_nodes, const float* rel_emb, const float* W_R,
+                    int64_t n_rel, int d, int rd, const int64_t* h, const int64_t* r,
+                    const int64_t* pos_t, const int64_t* neg_t, int64_t batch, float reg_lambda,
+                    float* loss, void* workspace, size_t workspace_bytes, kgat_stream_t stream);
+KGAT_API int kgat_transr_bwd(const float* grad_loss, int64_t n_nodes, int64_t n_rel, int d, int rd, int64_t batch,
+                    float* d_entity, float* d_rel, float* d_W, const void* workspace,
+                    size_t workspace_bytes, kgat_stream_t stream);
 
 /* (5) full-rank scoring with fused per-row top-K -- replaces the per-user loop of
  *     metric.calc_recall_ndcg (metric.py:44-51): for eval user j,

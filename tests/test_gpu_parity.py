@@ -707,7 +707,7 @@ def test_transr_unsupported_shapes_use_the_plain_formula(dev):
     # and the library itself refuses rather than guessing
     lib = _lib.load()
     z = th.zeros(64, device=dev)
-    rc = lib.kgat_transr_fwd_bwd(z.data_ptr(), 1, z.data_ptr(), z.data_ptr(), 1, 32, 32, ids[0].data_ptr(),
-                                 ids[0].data_ptr(), ids[0].data_ptr(), ids[0].data_ptr(), 8, 0.0, z.data_ptr(),
-                                 z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1 << 20, _lib.stream_ptr())
+    rc = lib.kgat_transr_fwd(z.data_ptr(), 1, z.data_ptr(), z.data_ptr(), 1, 32, 32, ids[0].data_ptr(),
+                             ids[0].data_ptr(), ids[0].data_ptr(), ids[0].data_ptr(), 8, 0.0, z.data_ptr(),
+                             z.data_ptr(), 1 << 20, _lib.stream_ptr())
     assert rc == -2
