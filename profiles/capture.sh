@@ -12,6 +12,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
     --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
 # 2) full counter set for our kernels, second step onwards
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:"att_logits|layer_fwd|layer_bwd|input_bwd|segment_softmax|score_topk" -s 10 -c 11 \
+    -k regex:"att_logits|layer_fwd|layer_bwd|input_bwd|segment_softmax|score_topk|transr_" -s 10 -c 11 \
     -o $OUT/prof_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
 ls -la $OUT

@@ -79,4 +79,37 @@ if os.path.exists(rep):
                 else:
                     cells.append((r[i] + " " + units[i]).strip())
             f.write("| " + " | ".join(cells) + " |\n")
-print("wrote", [p for p in os.listdir(out) if tag in p])
+    # measured DRAM traffic per launch of the step kernels (first profiled launch of each) -> the table
+    # bench.py reads for roofline.traffic
+    import json
+
+    def bench_key(name):
+        m = re.search(r"layer_(fwd|bwd)_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", name)
+        if m:
+            return "layer_%s_%sx%s" % m.groups()
+        m = re.search(r"input_bwd_kernel<\(?(?:int\))?(\d+)>", name)
+        if m:
+            return "input_bwd_%s" % m.group(1)
+        if "att_logits" in name:
+            return "attention_logits"
+        if "segment_softmax" in name:
+            return "segment_softmax"
+        return None
+
+    def num(r, col, scale_units):
+        i = hdr.index(col)
+        v = float(r[i].replace(",", ""))
+        return v * scale_units.get(units[i], 1.0)
+
+    byte_units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    time_units = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}
+    ki = hdr.index("Kernel Name")
+    kernels = collections.OrderedDict()
+    for r in data:
+        k = bench_key(r[ki])
+        if k and k not in kernels:
+            kernels[k] = {"dram_bytes": num(r, "dram__bytes_read.sum", byte_units) + num(r, "dram__bytes_write.sum", byte_units),
+                          "ncu_time_us": num(r, "gpu__time_duration.sum", time_units)}
+    json.dump({"source": "ncu --set full --clock-control none, profiles/capture.sh %s (amazon-book shape)" % tag,
+               "kernels": kernels}, open(os.path.join(out, "traffic_r1.json"), "w"), indent=1)
+print("wrote", [p for p in os.listdir(out) if tag in p], "+ traffic_r1.json")
