@@ -59,6 +59,8 @@ SIGNATURES = {
                                   C.c_size_t, C.c_void_p]),
     "kgat_transr_bwd": (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64, c_f32p, c_f32p, c_f32p,
                                   C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kgat_adam_step": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]),
     "kgat_umma_error_flag": (C.c_int, []),
     "kgat_selftest_umma": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p]),

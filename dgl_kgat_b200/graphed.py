@@ -134,8 +134,12 @@ class GraphedKGStep:
         return loss
 
     def __call__(self, h, r, pos_t, neg_t):
-        for dst, src in zip(self.ids, (h, r, pos_t, neg_t)):
-            dst.copy_(th.as_tensor(src), non_blocking=True)
+        src = (h, r, pos_t, neg_t)
+        if all(isinstance(t, th.Tensor) and t.is_cuda and t.dtype == th.long for t in src):
+            th._foreach_copy_(self.ids, list(src))                 # one multi-tensor launch
+        else:
+            for dst, t in zip(self.ids, src):
+                dst.copy_(th.as_tensor(t), non_blocking=True)
         self.graph.replay()
         for p, g in self._grads:
             p.grad = g

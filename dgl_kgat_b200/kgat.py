@@ -12,7 +12,7 @@ logged to ``log/<cfg>/valid{id}.csv`` and ``test{id}.csv``.  Additions (all off 
 ``--synthetic`` builds the inputs from :mod:`synth`; ``--max_kg_iters`` / ``--max_cf_iters``
 cap the phases for smoke runs; batches come from the device-resident sampler unless
 ``--host_sampler`` is given; the KG and CF iterations run as CUDA graphs (``graphed.py``) unless
-``--eager``; Adam is torch's fused multi-tensor kernel; ``--save_every`` / ``--resume`` write and read
+``--eager``; Adam is one library launch per step (``optim.FusedAdam``); ``--save_every`` / ``--resume`` write and read
 checkpoints (the reference has none, kgat.py:190).
 """
 from __future__ import annotations
@@ -28,6 +28,7 @@ import torch.optim as optim
 from . import metric
 from .dataset import DataLoader
 from .models import Model
+from .optim import FusedAdam
 from .utils import MetricLogger, creat_log_id, logging_config
 
 
@@ -106,7 +107,7 @@ def train_eval(args):
                   n_entities=dataset.n_KG_entity, n_relations=dataset.n_KG_relation,
                   relation_dim=args.relation_embed_dim, reg_lambda_kg=args.regs, reg_lambda_gnn=args.regs).to(dev)
     logging.info(model)
-    optimizer = optim.Adam(model.parameters(), lr=args.lr, fused=True)      # one multi-tensor kernel per step
+    optimizer = FusedAdam(model.parameters(), lr=args.lr)     # optim.Adam's rule, one library launch per step
     start_epoch = 1
     if args.resume:
         ckpt = th.load(args.resume, map_location=dev)
@@ -147,7 +148,7 @@ def train_eval(args):
                 loss.backward()
             optimizer.step()
             optimizer.zero_grad()
-            total += loss.detach().double()         # summed on the device: no host sync per iteration
+            total.add_(loss.detach())               # summed on the device: no host sync per iteration
             if it % args.print_every == 0 or it == 1:
                 logging.info("Epoch {:04d} Iter {:04d} | Loss {:.4f} ".format(epoch, it, total.item() / it))
         logging.info('Time for KGE: {:.1f}s, loss {:.4f}'.format(time() - t0, total.item() / max(it, 1)))
@@ -178,7 +179,7 @@ def train_eval(args):
                 loss.backward()
             optimizer.step()
             optimizer.zero_grad()
-            total += loss.detach().double()         # summed on the device: no host sync per iteration
+            total.add_(loss.detach())               # summed on the device: no host sync per iteration
             if it % args.print_every == 0 or it == 1:
                 logging.info("Epoch {:04d} Iter {:04d} | Loss {:.4f} ".format(epoch, it, total.item() / it))
         logging.info('Time for GNN: {:.1f}s, loss {:.4f}'.format(time() - t0, total.item() / max(it, 1)))

@@ -211,6 +211,16 @@ KGAT_API int kgat_transr_bwd(const float* grad_loss, int64_t n_nodes, int64_t n_
                     float* d_entity, float* d_rel, float* d_W, const void* workspace,
                     size_t workspace_bytes, kgat_stream_t stream);
 
+/* (7) Adam step over a list of fp32 tensors in one launch -- replaces optimizer.step() of
+ *     torch.optim.Adam as the reference configures it (kgat.py:101; no amsgrad):
+ *       m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *       p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)      (g += weight_decay * p first)
+ *     params/grads/exp_avg/exp_avg_sq: HOST arrays of n_tensors device pointers (16-byte aligned),
+ *     numel their element counts; step counts from 1.  At most 16 tensors per call. */
+KGAT_API int kgat_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2,
+                   double eps, double weight_decay, int64_t step, kgat_stream_t stream);
+
 /* (5) full-rank scoring with fused per-row top-K -- replaces the per-user loop of
  *     metric.calc_recall_ndcg (metric.py:44-51): for eval user j,
  *       score[i] = <emb[user_ids[j]], emb[item_ids[i]]>,

@@ -15,7 +15,8 @@ dl = DataLoader.from_synthetic("amazon-book")
 dl.use_device_samplers(dev)
 m = models.Model(True, 64, "kgat", 3, 64, 0.1, n_entities=dl.n_KG_entity, n_relations=dl.n_KG_relation,
                  relation_dim=64).to(dev)
-opt = th.optim.Adam(m.parameters(), lr=1e-3, fused=True)
+from dgl_kgat_b200.optim import FusedAdam
+opt = FusedAdam(m.parameters(), lr=1e-3)
 B = 2048
 
 

@@ -711,3 +711,34 @@ def test_transr_unsupported_shapes_use_the_plain_formula(dev):
                              ids[0].data_ptr(), ids[0].data_ptr(), ids[0].data_ptr(), 8, 0.0, z.data_ptr(),
                              z.data_ptr(), 1 << 20, _lib.stream_ptr())
     assert rc == -2
+
+
+# --------------------------------------------------------------------------- Adam step
+def test_fused_adam_matches_torch_adam(dev):
+    from dgl_kgat_b200.optim import FusedAdam
+    th.manual_seed(0)
+    shapes = [(1000, 64), (41, 64), (41, 64, 64), (64, 128), (7,), (4099,), (1,)]      # incl. sizes not divisible by 4
+    a = [th.nn.Parameter(th.randn(s, device=dev) * 0.1) for s in shapes]
+    b = [th.nn.Parameter(p.detach().clone()) for p in a]
+    oa, ob = FusedAdam(a, lr=1e-3), th.optim.Adam(b, lr=1e-3)
+    for step in range(6):
+        for p, q in zip(a, b):
+            g = th.randn_like(p) * (10.0 ** (-step))
+            p.grad, q.grad = g.clone(), g.clone()
+        if step == 3:                      # a parameter without a gradient is skipped, like torch does
+            a[1].grad = b[1].grad = None
+        oa.step()
+        ob.step()
+    for p, q in zip(a, b):
+        assert th.allclose(p, q, rtol=2e-6, atol=1e-9), float((p - q).abs().max())
+    for p, q in zip(a, b):
+        assert th.allclose(oa.state[p]["exp_avg_sq"], ob.state[q]["exp_avg_sq"], rtol=1e-6, atol=0)
+    assert oa.state[a[1]]["step"] == 5 and oa.state[a[0]]["step"] == 6
+    # state round trip
+    oc = FusedAdam(a, lr=1e-3)
+    oc.load_state_dict(oa.state_dict())
+    assert int(oc.state[a[0]]["step"]) == 6
+    cpu_p = th.nn.Parameter(th.zeros(4))
+    cpu_p.grad = th.zeros(4)
+    with pytest.raises(_lib.KgatError):
+        FusedAdam([cpu_p], lr=1e-3).step()
