@@ -128,13 +128,15 @@ def measured_traffic(kernel):
         return None
 
 
-def workload_config(cfg, world=1, work_mb=None):
+def workload_config(cfg, world=1, work_mb=None, exchange=None):
     c = {"workload": cfg.name + "-shaped synthetic CKG, 1 attention + 1 gnn fwd+bwd per step",
          "nodes": cfg.n_nodes, "edges": cfg.n_edges, "relations": cfg.n_relations, "layers": "64-32-16",
          "batch": BATCH}
     if work_mb is not None:
         c["l2_policy"] = "inputs larger than L2 (%.0f MB touched per step vs 126 MB L2)" % work_mb
         c["parallelism"] = "dst-partition x%d" % world if world > 1 else "single GPU"
+        if world > 1 and exchange is not None:
+            c["exchange"] = exchange
     return c
 
 
@@ -335,14 +337,15 @@ def run_ours(args):
 
     # ---- value: inputs resident in HBM.  Single GPU: the step replayed as one CUDA graph
     # (graphed.GraphedCFStep = the public call sequence, captured), ids already in its device buffers.
-    # Multi-GPU: the eager DistKGAT calls.  (KGAT_BENCH_GRAPH_DIST=1 opts into the experimental
-    # graphed.GraphedDistCFStep, which also captures the NCCL collectives; measured gain at N=2 was
-    # marginal and process teardown after capturing NCCL work was unreliable, so it is off by default.)
+    # Multi-GPU, peer exchange (default): the partitioned step - push kernels + device-side barriers, no
+    # NCCL call in it - replayed as one CUDA graph per rank (graphed.GraphedDistCFStep).
+    # Multi-GPU, KGAT_DIST_EXCHANGE=nccl: the eager DistKGAT calls (KGAT_BENCH_GRAPH_DIST=1 captures the
+    # NCCL collectives too; the gain at N=2 was marginal and teardown after capturing NCCL work unreliable).
     graphed = None
     if not distributed:
         from dgl_kgat_b200.graphed import GraphedCFStep
         graphed = GraphedCFStep(model, g, BATCH, refresh_attention=True)
-    elif os.environ.get("KGAT_BENCH_GRAPH_DIST", "0") == "1":
+    elif os.environ.get("KGAT_BENCH_GRAPH_DIST", "1" if dk.peer is not None else "0") == "1":
         from dgl_kgat_b200.graphed import GraphedDistCFStep
         graphed = GraphedDistCFStep(dk, BATCH)
     if graphed is not None:
@@ -382,8 +385,8 @@ def run_ours(args):
     e2e = {"value": E / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 3 * BATCH * 8,
            "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": loss_val,
            "api": "dist.DistKGAT (eager)" if graphed is None else
-                  ("graphed.GraphedDistCFStep (CUDA graph incl. NCCL collectives)" if distributed
-                   else "graphed.GraphedCFStep (CUDA graph of the public calls)")}
+                  ("graphed.GraphedDistCFStep (CUDA graph of the partitioned step, %s exchange)" % dk.exchange
+                   if distributed else "graphed.GraphedCFStep (CUDA graph of the public calls)")}
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peak, peak_src = measured_peaks()
@@ -448,13 +451,18 @@ def run_ours(args):
         if not args.no_eval:
             cpu["eval_users_per_s"] = cpu_port_eval(ck, 128)
 
+    if distributed and dk.peer is not None:
+        # a barrier that timed out (a rank fell out of step) invalidates every number above
+        peer_err = max_over_ranks(float(dk.peer.error()))
+        if peer_err:
+            raise SystemExit("peer barrier timed out (waiting for rank %d): no result" % (int(peer_err) - 1))
     if rank == 0:
         work_mb = (N * 4 * (176 + 2 * (64 + 64 + 32) + 64 + 32 + 16) + E * 4 * 12) / 1e6
         line = {
             "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cfg, world, work_mb),
+            "config": workload_config(cfg, world, work_mb, dk.exchange if distributed else None),
             "e2e": e2e, "gpu_launches": launches, "eager_ms_per_step": ms_eager,
             "value_path": "eager dist.DistKGAT step" if graphed is None else
                           "CUDA-graph replay of the step, ids resident (eager instrumented pass: eager_ms_per_step)",
@@ -463,6 +471,8 @@ def run_ours(args):
         }
         print(json.dumps(line))
     if distributed:
+        graphed = None
+        dk.close()
         tdist.barrier()
         tdist.destroy_process_group()
 

@@ -26,8 +26,20 @@ class KgatGraph(C.Structure):
 
 GRAPH_ARRAYS = [name for name, _ in KgatGraph._fields_[3:]]
 
+MAX_RANKS = 8                   # KGAT_MAX_RANKS
+PEER_HEADER_BYTES = 1024        # KGAT_PEER_HEADER_BYTES
+IPC_HANDLE_BYTES = 64           # KGAT_IPC_HANDLE_BYTES
+
+
+class KgatPeerGroup(C.Structure):
+    """Mirror of ``kgat_peer_group_t``."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("arena_bytes", C.c_uint64),
+                ("arena", C.c_void_p * MAX_RANKS)]
+
+
 # name -> (restype, argtypes); must list every KGAT_API symbol of the header
 _GP = C.POINTER(KgatGraph)
+_PG = C.POINTER(KgatPeerGroup)
 SIGNATURES = {
     "kgat_version": (C.c_int, []),
     "kgat_error_string": (C.c_char_p, [C.c_int]),
@@ -61,6 +73,25 @@ SIGNATURES = {
                                   C.c_void_p, C.c_size_t, C.c_void_p]),
     "kgat_adam_step": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                  C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]),
+    "kgat_peer_arena_create": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "kgat_peer_arena_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "kgat_peer_arena_close": (C.c_int, [C.c_void_p]),
+    "kgat_peer_arena_destroy": (C.c_int, [C.c_void_p]),
+    "kgat_peer_barrier": (C.c_int, [_PG, C.c_int, C.c_void_p]),
+    "kgat_peer_error": (C.c_int, [_PG]),
+    "kgat_segment_softmax_push": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, _PG, C.c_void_p]),
+    "kgat_layer_fwd_push": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int,
+                                      C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int64,
+                                      _PG, C.c_void_p]),
+    "kgat_layer_bwd_push": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_i32p, C.c_int64, C.c_int64, c_f32p, c_f32p,
+                                      c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int,
+                                      C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, _PG, C.c_void_p]),
+    "kgat_input_bwd_push": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_i32p, C.c_int64, C.c_int64, c_f32p, c_f32p,
+                                      c_f32p, C.c_int, c_f32p, _PG, C.c_void_p]),
+    "kgat_peer_gather_rows_push": (C.c_int, [c_f32p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                             c_f32p, _PG, C.c_void_p]),
+    "kgat_peer_push_slot": (C.c_int, [c_f32p, C.c_int64, c_f32p, _PG, C.c_void_p]),
+    "kgat_peer_sum_slots": (C.c_int, [c_f32p, C.c_int64, C.c_int, c_f32p, C.c_void_p]),
     "kgat_umma_error_flag": (C.c_int, []),
     "kgat_selftest_umma": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p]),

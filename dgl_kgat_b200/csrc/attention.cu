@@ -9,7 +9,7 @@
 //
 // Softmax: one warp per destination row of the CSR, max and sum by warp shuffles, exp(x - max) / sum
 // like DGL's edge_softmax (reference models.py:153).
-#include "common.cuh"
+#include "peer.cuh"
 
 namespace kgat {
 namespace {
@@ -201,7 +201,7 @@ __global__ void att_logits_generic_kernel(const int32_t* __restrict__ csr_src, c
 __global__ void __launch_bounds__(256)
 segment_softmax_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict__ csr_eid,
                        int64_t row_begin, int64_t row_end, const float* __restrict__ logits,
-                       float* __restrict__ w_csr, float* __restrict__ w_eid) {
+                       float* __restrict__ w_csr, float* __restrict__ w_eid, PeerOut po) {
     const int64_t row = row_begin + ((blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= row_end) return;
@@ -216,6 +216,7 @@ segment_softmax_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __res
         if (ok) {
             const float w = ex / den;
             w_csr[c] = w;
+            peer_store(po, c, w);            // multi-GPU: the peers' copies (peer.cuh)
             if (w_eid) w_eid[csr_eid[c]] = w;
         }
         return;
@@ -229,6 +230,7 @@ segment_softmax_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __res
     for (int c = beg + lane; c < end; c += 32) {
         const float w = expf(logits[c] - m) / den;
         w_csr[c] = w;
+        peer_store(po, c, w);
         if (w_eid) w_eid[csr_eid[c]] = w;
     }
 }
@@ -297,18 +299,26 @@ extern "C" int kgat_attention_logits(const kgat_graph_t* g, const float* entity,
     return KGAT_OK;
 }
 
-extern "C" int kgat_segment_softmax(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
-                                    const float* logits_csr, float* w_csr, float* w_eid,
-                                    kgat_stream_t stream) {
+extern "C" int kgat_segment_softmax_push(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                                         const float* logits_csr, float* w_csr, float* w_eid,
+                                         const kgat_peer_group_t* pg, kgat_stream_t stream) {
     KGAT_REQUIRE(g && logits_csr && w_csr);
     KGAT_REQUIRE(row_begin >= 0 && row_end <= g->n_nodes && row_begin <= row_end);
+    PeerOut po = no_peers();
+    if (pg && g->n_edges > 0) KGAT_REQUIRE(peer_aliases(pg, w_csr, sizeof(float) * g->n_edges, &po));
     if (row_begin == row_end || g->n_edges == 0) return KGAT_OK;
     const int64_t rows = row_end - row_begin;
     const int64_t blocks = (rows * 32 + 255) / 256;
     segment_softmax_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
-        g->csr_ptr, g->csr_eid, row_begin, row_end, logits_csr, w_csr, w_eid);
+        g->csr_ptr, g->csr_eid, row_begin, row_end, logits_csr, w_csr, w_eid, po);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
+}
+
+extern "C" int kgat_segment_softmax(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                                    const float* logits_csr, float* w_csr, float* w_eid,
+                                    kgat_stream_t stream) {
+    return kgat_segment_softmax_push(g, row_begin, row_end, logits_csr, w_csr, w_eid, nullptr, stream);
 }
 
 extern "C" int kgat_edge_weights_from_eid(const kgat_graph_t* g, const float* w_eid, float* w_csr,

@@ -14,7 +14,11 @@
 //            deterministic), then dropout / LeakyReLU backward -> dpre tile in shared memory;
 //   phase 2  dW2 += dpre^T z in registers (4xBJ blocks per thread, one partial per CTA, reduced by a
 //            second kernel in fixed order), dz = dpre W2, dx_direct = dz (.) h_nb, dh_nb = dz (.) h_in.
-#include "common.cuh"
+//
+// Multi-GPU (peer.cuh): the PUSH instantiations store every owned row of the exchanged output (h_out,
+// dh_nb, d_entity) into the peers' arenas right next to the local store, so the all-gather of the
+// destination-partitioned step rides on the kernel that produces the rows.
+#include "peer.cuh"
 
 namespace kgat {
 namespace {
@@ -90,14 +94,14 @@ struct FwdSmem {
     static constexpr size_t bytes = sizeof(float) * (DIN * LDW + TM * DIN + TM * DOUT + COOP_FLOATS) + 16;
 };
 
-template <int DIN, int DOUT>
+template <int DIN, int DOUT, bool PUSH>
 __global__ void __launch_bounds__(THREADS)
 layer_fwd_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict__ csr_src,
                  const float* __restrict__ w_csr, int row_begin, int row_end,
                  const float* __restrict__ h_in, const float* __restrict__ W2,
                  const float* __restrict__ drop_mask, float slope, float* __restrict__ h_nb,
                  float* __restrict__ act, float* __restrict__ h_out, float* __restrict__ concat,
-                 int64_t cstride, int64_t out_off, int64_t in_off) {
+                 int64_t cstride, int64_t out_off, int64_t in_off, PeerOut po) {
     constexpr int LDW = DOUT + 1;
     constexpr int LPI = DIN / 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -203,6 +207,7 @@ layer_fwd_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict_
         for (int j = lane; j < DOUT; j += 32) {
             const float v = sY[rl * DOUT + j];
             h_out[static_cast<size_t>(row) * DOUT + j] = v;
+            if (PUSH) peer_store(po, static_cast<size_t>(row) * DOUT + j, v);
             if (concat) concat[static_cast<size_t>(row) * cstride + out_off + j] = v / denom;
         }
     }
@@ -219,7 +224,7 @@ struct BwdCfg {
     static constexpr size_t bytes = sizeof(float) * (DOUT * DIN + TM * DOUT + TM * DIN + COOP_FLOATS) + 16;
 };
 
-template <int DIN, int DOUT>
+template <int DIN, int DOUT, bool PUSH>
 __global__ void __launch_bounds__(THREADS)
 layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
                  const float* __restrict__ w_csc, int row_begin, int row_end, int n_tiles,
@@ -229,7 +234,8 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                  const float* __restrict__ h_in, const float* __restrict__ h_nb,
                  const float* __restrict__ act, const float* __restrict__ h_out,
                  const float* __restrict__ drop_mask, const float* __restrict__ W2, float slope,
-                 float* __restrict__ dx_direct, float* __restrict__ dh_nb, float* __restrict__ partials) {
+                 float* __restrict__ dx_direct, float* __restrict__ dh_nb, float* __restrict__ partials,
+                 PeerOut po) {
     using C = BwdCfg<DIN, DOUT>;
     constexpr int BJ = C::BJ, NBLOCKS = C::NBLOCKS, NB = C::NB;
     constexpr int LPI = DIN / 4, LPO = DOUT / 4;
@@ -386,7 +392,9 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                 if (row < row_end) {
                     const size_t o = static_cast<size_t>(row) * DIN + i;
                     dx_direct[o] = dz[k] * __ldg(h_nb + o);
-                    dh_nb[o] = dz[k] * __ldg(h_in + o);
+                    const float dh = dz[k] * __ldg(h_in + o);
+                    dh_nb[o] = dh;
+                    if (PUSH) peer_store(po, o, dh);
                 }
             }
         }
@@ -447,13 +455,13 @@ reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int n
 }
 
 // d_entity[v] = d_concat[v, in_off:+D] + dx_direct[v] + sum_{k in CSC row v} w[k] * dh_nb[dst[k]]
-template <int D>
+template <int D, bool PUSH>
 __global__ void __launch_bounds__(THREADS)
 input_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
                  const float* __restrict__ w_csc, int row_begin, int row_end,
                  const float* __restrict__ d_concat, const int32_t* __restrict__ dc_slot, int64_t cstride,
                  int64_t in_off, const float* __restrict__ dx_direct, const float* __restrict__ dh_nb,
-                 float* __restrict__ d_entity) {
+                 float* __restrict__ d_entity, PeerOut po) {
     constexpr int LP = D / 4;
     const int lane = threadIdx.x & 31;
     const int row = row_begin + blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -476,6 +484,7 @@ input_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
             g.x += c.x; g.y += c.y; g.z += c.z; g.w += c.w;
         }
         *reinterpret_cast<float4*>(d_entity + o) = g;
+        if (PUSH) peer_store(po, o, g);
     }
 }
 
@@ -486,24 +495,30 @@ struct FwdArgs {
     const kgat_graph_t* g; int row_begin, row_end;
     const float *h_in, *w_csr, *W2, *drop_mask; float slope;
     float *h_nb, *act, *h_out, *concat; int64_t cstride, out_off, in_off; cudaStream_t st;
+    bool push; PeerOut po;
 };
 
-template <int DIN, int DOUT>
-int launch_fwd(const FwdArgs& a) {
+template <int DIN, int DOUT, bool PUSH>
+int launch_fwd_t(const FwdArgs& a) {
     constexpr size_t smem = FwdSmem<DIN, DOUT>::bytes;
     static bool configured = false;
     if (!configured) {
-        KGAT_CUDA(cudaFuncSetAttribute(layer_fwd_kernel<DIN, DOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        KGAT_CUDA(cudaFuncSetAttribute(layer_fwd_kernel<DIN, DOUT, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         configured = true;
     }
     const int rows = a.row_end - a.row_begin;
     const unsigned grid = (rows + TM - 1) / TM;
-    layer_fwd_kernel<DIN, DOUT><<<grid, THREADS, smem, a.st>>>(
+    layer_fwd_kernel<DIN, DOUT, PUSH><<<grid, THREADS, smem, a.st>>>(
         a.g->csr_ptr, a.g->csr_src, a.w_csr, a.row_begin, a.row_end, a.h_in, a.W2, a.drop_mask, a.slope,
-        a.h_nb, a.act, a.h_out, a.concat, a.cstride, a.out_off, a.in_off);
+        a.h_nb, a.act, a.h_out, a.concat, a.cstride, a.out_off, a.in_off, a.po);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
+}
+
+template <int DIN, int DOUT>
+int launch_fwd(const FwdArgs& a) {
+    return a.push ? launch_fwd_t<DIN, DOUT, true>(a) : launch_fwd_t<DIN, DOUT, false>(a);
 }
 
 struct BwdArgs {
@@ -511,32 +526,38 @@ struct BwdArgs {
     const float* d_concat; const int32_t* dc_slot; int64_t cstride, out_off;
     const float *nxt_dx_direct, *nxt_dh_nb, *w_csc, *h_in, *h_nb, *act, *h_out, *drop_mask, *W2; float slope;
     float *dx_direct, *dh_nb, *dW2, *partials; cudaStream_t st;
+    bool push; PeerOut po;
 };
 
 inline int bwd_max_ctas() { return 4 * num_sms(); }
 
-template <int DIN, int DOUT>
-int launch_bwd(const BwdArgs& a) {
+template <int DIN, int DOUT, bool PUSH>
+int launch_bwd_t(const BwdArgs& a) {
     constexpr size_t smem = BwdCfg<DIN, DOUT>::bytes;
     static bool configured = false;
     if (!configured) {
-        KGAT_CUDA(cudaFuncSetAttribute(layer_bwd_kernel<DIN, DOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        KGAT_CUDA(cudaFuncSetAttribute(layer_bwd_kernel<DIN, DOUT, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         configured = true;
     }
     const int rows = a.row_end - a.row_begin;
     const int n_tiles = (rows + TM - 1) / TM;
     const int grid = n_tiles < bwd_max_ctas() ? n_tiles : bwd_max_ctas();
-    layer_bwd_kernel<DIN, DOUT><<<grid, THREADS, smem, a.st>>>(
+    layer_bwd_kernel<DIN, DOUT, PUSH><<<grid, THREADS, smem, a.st>>>(
         a.g->csc_ptr, a.g->csc_dst, a.w_csc, a.row_begin, a.row_end, n_tiles, a.d_concat, a.dc_slot, a.cstride,
         a.out_off,
         a.nxt_dx_direct, a.nxt_dh_nb, a.h_in, a.h_nb, a.act, a.h_out, a.drop_mask, a.W2, a.slope, a.dx_direct,
-        a.dh_nb, a.partials);
+        a.dh_nb, a.partials, a.po);
     KGAT_LAUNCH_CHECK();
     const int n_elem = DIN * DOUT;
     reduce_partials_kernel<<<(n_elem + 31) / 32, 256, 0, a.st>>>(a.partials, grid, n_elem, a.dW2);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
+}
+
+template <int DIN, int DOUT>
+int launch_bwd(const BwdArgs& a) {
+    return a.push ? launch_bwd_t<DIN, DOUT, true>(a) : launch_bwd_t<DIN, DOUT, false>(a);
 }
 
 #define KGAT_DIM_PAIRS(X) \
@@ -547,12 +568,13 @@ int launch_bwd(const BwdArgs& a) {
 
 using namespace kgat;
 
-extern "C" int kgat_layer_fwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
-                              const float* h_in, const float* w_csr, const float* W2,
-                              const float* drop_mask, int d_in, int d_out, float slope,
-                              float* h_nb, float* act, float* h_out, float* concat,
-                              int64_t concat_stride, int64_t out_off, int64_t in_off,
-                              kgat_stream_t stream) {
+// pg == nullptr: the single-GPU entry points; otherwise the exchanged output must lie in the own arena
+extern "C" int kgat_layer_fwd_push(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                                   const float* h_in, const float* w_csr, const float* W2,
+                                   const float* drop_mask, int d_in, int d_out, float slope,
+                                   float* h_nb, float* act, float* h_out, float* concat,
+                                   int64_t concat_stride, int64_t out_off, int64_t in_off,
+                                   const kgat_peer_group_t* pg, kgat_stream_t stream) {
     KGAT_REQUIRE(g && h_in && W2 && h_nb && h_out);
     KGAT_REQUIRE(g->n_edges == 0 || w_csr);
     KGAT_REQUIRE(row_begin >= 0 && row_end <= g->n_nodes && row_begin <= row_end);
@@ -564,16 +586,58 @@ extern "C" int kgat_layer_fwd(const kgat_graph_t* g, int64_t row_begin, int64_t 
     } else {
         in_off = -1;
     }
+    PeerOut po = no_peers();
+    if (pg) KGAT_REQUIRE(d_out > 0 && peer_aliases(pg, h_out, sizeof(float) * g->n_nodes * d_out, &po));
     if (row_begin == row_end) return KGAT_OK;
     FwdArgs a{g, (int)row_begin, (int)row_end, h_in, w_csr, W2, drop_mask, slope, h_nb, act, h_out, concat,
-              concat_stride, out_off, in_off, as_stream(stream)};
+              concat_stride, out_off, in_off, as_stream(stream), pg != nullptr, po};
 #define X(DI, DO) if (d_in == DI && d_out == DO) return launch_fwd<DI, DO>(a);
     KGAT_DIM_PAIRS(X)
 #undef X
     return KGAT_ERR_UNSUPPORTED_DIM;
 }
 
+extern "C" int kgat_layer_fwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                              const float* h_in, const float* w_csr, const float* W2,
+                              const float* drop_mask, int d_in, int d_out, float slope,
+                              float* h_nb, float* act, float* h_out, float* concat,
+                              int64_t concat_stride, int64_t out_off, int64_t in_off,
+                              kgat_stream_t stream) {
+    return kgat_layer_fwd_push(g, row_begin, row_end, h_in, w_csr, W2, drop_mask, d_in, d_out, slope, h_nb, act, h_out,
+                               concat, concat_stride, out_off, in_off, nullptr, stream);
+}
+
 extern "C" int kgat_layer_bwd_partials(void) { return bwd_max_ctas(); }
+
+extern "C" int kgat_layer_bwd_push(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                                   const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride,
+                                   int64_t out_off, const float* nxt_dx_direct, const float* nxt_dh_nb,
+                                   const float* w_csc, const float* h_in, const float* h_nb, const float* act,
+                                   const float* h_out, const float* drop_mask, const float* W2, int d_in, int d_out,
+                                   float slope, float* dx_direct, float* dh_nb, float* dW2, float* dW2_partials,
+                                   const kgat_peer_group_t* pg, kgat_stream_t stream) {
+    KGAT_REQUIRE(g && h_in && h_nb && h_out && W2 && dx_direct && dh_nb && dW2 && dW2_partials);
+    KGAT_REQUIRE(row_begin >= 0 && row_end <= g->n_nodes && row_begin <= row_end);
+    KGAT_REQUIRE(!nxt_dh_nb || g->n_edges == 0 || w_csc);
+    KGAT_REQUIRE(!drop_mask || act);
+    KGAT_REQUIRE(aligned16(h_in) && aligned16(h_nb) && aligned16(h_out) && aligned16(W2) && aligned16(dx_direct) &&
+                 aligned16(dh_nb) && aligned16(dW2_partials));
+    if (d_concat) KGAT_REQUIRE(aligned16(d_concat) && concat_stride % 4 == 0 && out_off % 4 == 0 && out_off >= 0);
+    PeerOut po = no_peers();
+    if (pg) KGAT_REQUIRE(d_in > 0 && peer_aliases(pg, dh_nb, sizeof(float) * g->n_nodes * d_in, &po));
+    cudaStream_t st = as_stream(stream);
+    if (row_begin == row_end) {
+        KGAT_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * d_in * d_out, st));
+        return KGAT_OK;
+    }
+    KGAT_REQUIRE(!dc_row_slot || d_concat);
+    BwdArgs a{g, (int)row_begin, (int)row_end, d_concat, dc_row_slot, concat_stride, out_off, nxt_dx_direct, nxt_dh_nb, w_csc,
+              h_in, h_nb, act, h_out, drop_mask, W2, slope, dx_direct, dh_nb, dW2, dW2_partials, st, pg != nullptr, po};
+#define X(DI, DO) if (d_in == DI && d_out == DO) return launch_bwd<DI, DO>(a);
+    KGAT_DIM_PAIRS(X)
+#undef X
+    return KGAT_ERR_UNSUPPORTED_DIM;
+}
 
 extern "C" int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
                               const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride,
@@ -582,24 +646,39 @@ extern "C" int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t 
                               const float* drop_mask, const float* W2, int d_in, int d_out, float slope,
                               float* dx_direct, float* dh_nb, float* dW2, float* dW2_partials,
                               kgat_stream_t stream) {
-    KGAT_REQUIRE(g && h_in && h_nb && h_out && W2 && dx_direct && dh_nb && dW2 && dW2_partials);
+    return kgat_layer_bwd_push(g, row_begin, row_end, d_concat, dc_row_slot, concat_stride, out_off, nxt_dx_direct,
+                               nxt_dh_nb, w_csc, h_in, h_nb, act, h_out, drop_mask, W2, d_in, d_out, slope, dx_direct,
+                               dh_nb, dW2, dW2_partials, nullptr, stream);
+}
+
+extern "C" int kgat_input_bwd_push(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                                   const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride,
+                                   int64_t in_off, const float* dx_direct, const float* dh_nb, const float* w_csc,
+                                   int d, float* d_entity, const kgat_peer_group_t* pg, kgat_stream_t stream) {
+    KGAT_REQUIRE(g && dx_direct && dh_nb && d_entity);
+    KGAT_REQUIRE(g->n_edges == 0 || w_csc);
     KGAT_REQUIRE(row_begin >= 0 && row_end <= g->n_nodes && row_begin <= row_end);
-    KGAT_REQUIRE(!nxt_dh_nb || g->n_edges == 0 || w_csc);
-    KGAT_REQUIRE(!drop_mask || act);
-    KGAT_REQUIRE(aligned16(h_in) && aligned16(h_nb) && aligned16(h_out) && aligned16(W2) && aligned16(dx_direct) &&
-                 aligned16(dh_nb) && aligned16(dW2_partials));
-    if (d_concat) KGAT_REQUIRE(aligned16(d_concat) && concat_stride % 4 == 0 && out_off % 4 == 0 && out_off >= 0);
+    KGAT_REQUIRE(aligned16(dx_direct) && aligned16(dh_nb) && aligned16(d_entity));
+    if (d_concat) KGAT_REQUIRE(aligned16(d_concat) && concat_stride % 4 == 0 && in_off % 4 == 0 && in_off >= 0);
+    PeerOut po = no_peers();
+    if (pg) KGAT_REQUIRE(d > 0 && peer_aliases(pg, d_entity, sizeof(float) * g->n_nodes * d, &po));
+    if (row_begin == row_end) return KGAT_OK;
+    const int rows = static_cast<int>(row_end - row_begin);
+    const unsigned grid = (rows + WARPS - 1) / WARPS;
     cudaStream_t st = as_stream(stream);
-    if (row_begin == row_end) {
-        KGAT_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * d_in * d_out, st));
-        return KGAT_OK;
+#define LAUNCH_T(D, P)                                                                                     \
+    input_bwd_kernel<D, P><<<grid, THREADS, 0, st>>>(g->csc_ptr, g->csc_dst, w_csc, (int)row_begin,        \
+                                                     (int)row_end, d_concat, dc_row_slot, concat_stride,   \
+                                                     in_off, dx_direct, dh_nb, d_entity, po)
+#define LAUNCH(D)                                                                                          \
+    if (d == D) {                                                                                          \
+        if (pg) LAUNCH_T(D, true); else LAUNCH_T(D, false);                                                \
+        KGAT_LAUNCH_CHECK();                                                                               \
+        return KGAT_OK;                                                                                    \
     }
-    KGAT_REQUIRE(!dc_row_slot || d_concat);
-    BwdArgs a{g, (int)row_begin, (int)row_end, d_concat, dc_row_slot, concat_stride, out_off, nxt_dx_direct, nxt_dh_nb, w_csc,
-              h_in, h_nb, act, h_out, drop_mask, W2, slope, dx_direct, dh_nb, dW2, dW2_partials, st};
-#define X(DI, DO) if (d_in == DI && d_out == DO) return launch_bwd<DI, DO>(a);
-    KGAT_DIM_PAIRS(X)
-#undef X
+    LAUNCH(128) LAUNCH(64) LAUNCH(32) LAUNCH(16) LAUNCH(8)
+#undef LAUNCH
+#undef LAUNCH_T
     return KGAT_ERR_UNSUPPORTED_DIM;
 }
 
@@ -607,25 +686,6 @@ extern "C" int kgat_input_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t 
                               const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride,
                               int64_t in_off, const float* dx_direct, const float* dh_nb, const float* w_csc, int d,
                               float* d_entity, kgat_stream_t stream) {
-    KGAT_REQUIRE(g && dx_direct && dh_nb && d_entity);
-    KGAT_REQUIRE(g->n_edges == 0 || w_csc);
-    KGAT_REQUIRE(row_begin >= 0 && row_end <= g->n_nodes && row_begin <= row_end);
-    KGAT_REQUIRE(aligned16(dx_direct) && aligned16(dh_nb) && aligned16(d_entity));
-    if (d_concat) KGAT_REQUIRE(aligned16(d_concat) && concat_stride % 4 == 0 && in_off % 4 == 0 && in_off >= 0);
-    if (row_begin == row_end) return KGAT_OK;
-    const int rows = static_cast<int>(row_end - row_begin);
-    const unsigned grid = (rows + WARPS - 1) / WARPS;
-    cudaStream_t st = as_stream(stream);
-#define LAUNCH(D)                                                                                          \
-    if (d == D) {                                                                                          \
-        input_bwd_kernel<D><<<grid, THREADS, 0, st>>>(g->csc_ptr, g->csc_dst, w_csc, (int)row_begin,       \
-                                                      (int)row_end, d_concat, dc_row_slot, concat_stride,  \
-                                                      in_off,                                              \
-                                                      dx_direct, dh_nb, d_entity);                         \
-        KGAT_LAUNCH_CHECK();                                                                               \
-        return KGAT_OK;                                                                                    \
-    }
-    LAUNCH(128) LAUNCH(64) LAUNCH(32) LAUNCH(16) LAUNCH(8)
-#undef LAUNCH
-    return KGAT_ERR_UNSUPPORTED_DIM;
+    return kgat_input_bwd_push(g, row_begin, row_end, d_concat, dc_row_slot, concat_stride, in_off, dx_direct, dh_nb,
+                               w_csc, d, d_entity, nullptr, stream);
 }

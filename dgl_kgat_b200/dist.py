@@ -4,7 +4,16 @@ New capability (the reference is single-GPU, kgat.py:14,69-71).  Every rank hold
 parameters, the CSR of the in-edges of its own contiguous destination range (forward, attention)
 and the CSC of the out-edges of the same range (backward).  Ranges are balanced by edge count.
 
-Exchange steps (``torch.distributed``; NCCL over NVLink on the GPUs, gloo in the CPU tests):
+Two exchange implementations (``DistKGAT(..., exchange=...)``, default from ``KGAT_DIST_EXCHANGE``):
+
+``"peer"``  every rank owns an arena that all other ranks map over NVLink / NVSwitch (cudaIpc).  The
+            kernels that PRODUCE exchanged rows (softmax, layer forward, layer backward, entity
+            gradient, loss-row gather) store each owned row into the own arena and into every peer's
+            arena in the same instruction stream, so the all-gather rides on the compute kernel; what
+            remains of each collective is one device-side barrier (``kgat_peer_barrier``, ~5 us, no host,
+            no NCCL).  8 barriers per step, the whole step is CUDA-graph capturable
+            (``graphed.GraphedDistCFStep``).  ``torch.distributed`` only carries the 64-byte IPC handles.
+``"nccl"``  the same algorithm with NCCL collectives between unchanged single-GPU kernels:
   attention   all-reduce(sum) of the zero-filled (E,) weight vector - each edge is written by
               exactly one rank, so the sum is exact;
   forward     after layers 0 .. L-2: all-gather of the owned rows of the (N, d_l) layer output;
@@ -22,8 +31,109 @@ import numpy as np
 import torch as th
 import torch.distributed as tdist
 
-from . import metric, ops
+import ctypes
+import os
+
+from . import _lib, metric, ops
 from .graph import CKGraph
+
+
+class _RawCuda:
+    """``__cuda_array_interface__`` view of a piece of device memory (fp32) for ``torch.as_tensor``."""
+
+    def __init__(self, ptr, shape, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f4",
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class PeerArena:
+    """This rank's arena plus the mapped arenas of all peers (include/kgat_b200.h section 8).
+
+    ``buf(name, shape)`` carves a persistent fp32 tensor out of the own arena; every rank must request
+    the same names and shapes in the same order so a buffer has the SAME offset in every arena - that
+    offset is how the ``*_push`` kernels find the peers' copies.  ``barrier()`` enqueues the device-side
+    barrier on the current stream; every rank must enqueue the same sequence."""
+
+    def __init__(self, payload_bytes, device, group=None, timeout_ms=0):
+        lib = _lib.load()
+        self.device, self.group = th.device(device), group
+        self.rank, self.world = tdist.get_rank(group), tdist.get_world_size(group)
+        if self.world > _lib.MAX_RANKS:
+            raise _lib.KgatError("peer exchange supports at most %d ranks (one NVLink box)" % _lib.MAX_RANKS)
+        self.nbytes = (_lib.PEER_HEADER_BYTES + int(payload_bytes) + 255) // 256 * 256
+        self.timeout_ms = int(timeout_ms) or int(os.environ.get("KGAT_PEER_TIMEOUT_MS", "0"))
+        self.generation = 0
+        self._bufs, self._top, self._closed = {}, _lib.PEER_HEADER_BYTES, False
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        self._pg = _lib.KgatPeerGroup()
+        self._pg.world, self._pg.rank, self._pg.arena_bytes = self.world, self.rank, self.nbytes
+        self._mapped = []
+        with th.cuda.device(self.device):
+            _lib.check(lib.kgat_peer_arena_create(self.nbytes, ctypes.byref(own), handle), "kgat_peer_arena_create")
+            self._own = own.value
+            infos = [None] * self.world
+            tdist.all_gather_object(infos, (bytes(handle.raw), self.nbytes), group=group)
+            if any(n != self.nbytes for _, n in infos):
+                raise _lib.KgatError("peer arenas differ in size across ranks: %s" % [n for _, n in infos])
+            for k, (h, _) in enumerate(infos):
+                if k == self.rank:
+                    self._pg.arena[k] = self._own
+                    continue
+                p = ctypes.c_void_p()
+                _lib.check(lib.kgat_peer_arena_open(h, ctypes.byref(p)), "kgat_peer_arena_open (rank %d)" % k)
+                self._pg.arena[k] = p.value
+                self._mapped.append(p.value)
+            self.ref = ctypes.byref(self._pg)
+            tdist.barrier(group=group)       # nobody pushes before every rank has mapped every arena
+
+    def buf(self, name, shape):
+        t = self._bufs.get(name)
+        shape = tuple(int(x) for x in shape)
+        if t is not None:
+            if tuple(t.shape) != shape:
+                raise _lib.KgatError("arena buffer %r has shape %s, requested %s" % (name, tuple(t.shape), shape))
+            return t
+        n = 4
+        for x in shape:
+            n *= x
+        off = self._top
+        if off + n > self.nbytes:
+            raise _lib.KgatError("peer arena exhausted (%d bytes): buffer %r needs %d more; raise max_batch / "
+                                 "arena size in DistKGAT" % (self.nbytes, name, n))
+        self._top = (off + n + 255) // 256 * 256
+        t = th.as_tensor(_RawCuda(self._own + off, shape, self), device=self.device)
+        if t.data_ptr() != self._own + off or t.dtype != th.float32:
+            raise _lib.KgatError("could not alias arena memory as a torch tensor")
+        self._bufs[name] = t
+        return t
+
+    def barrier(self):
+        with th.cuda.device(self.device):
+            with _lib.record("peer_barrier"):
+                _lib.check(_lib.load().kgat_peer_barrier(self.ref, self.timeout_ms, _lib.stream_ptr()),
+                           "kgat_peer_barrier")
+
+    def error(self):
+        """0, or 1 + the rank that did not reach a barrier in time (synchronises the device)."""
+        with th.cuda.device(self.device):
+            return int(_lib.load().kgat_peer_error(self.ref))
+
+    def close(self):
+        """Collective: unmap the peers' arenas, then free the own one."""
+        if self._closed:
+            return
+        self._closed = True
+        lib = _lib.load()
+        with th.cuda.device(self.device):
+            th.cuda.synchronize()
+            tdist.barrier(group=self.group)
+            self._bufs.clear()
+            for p in self._mapped:
+                lib.kgat_peer_arena_close(p)
+            tdist.barrier(group=self.group)
+            lib.kgat_peer_arena_destroy(self._own)
 
 
 def partition_rows(indegree: np.ndarray, n_parts: int) -> np.ndarray:
@@ -111,10 +221,29 @@ class _BatchRows(th.autograd.Function):
 class DistKGAT:
     """Drives a replicated :class:`models.Model` over a destination-partitioned graph."""
 
-    def __init__(self, model, n_nodes, triplets, n_rel, device, group=None):
+    def __init__(self, model, n_nodes, triplets, n_rel, device, group=None, exchange=None, max_batch=16384):
         self.model, self.device, self.group = model, th.device(device), group
         self.rank, self.world = tdist.get_rank(group), tdist.get_world_size(group)
+        exchange = exchange or os.environ.get("KGAT_DIST_EXCHANGE", "peer")
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl', got %r" % (exchange,))
+        self.exchange = exchange
         self.part = Partition(n_nodes, triplets, n_rel, self.rank, self.world)
+        self.peer = None
+        if exchange == "peer":
+            dims = [model.entity_embed.weight.shape[1]] + [l.res_fc_2.weight.shape[0] for l in model.layers]
+            N, E, L = int(n_nodes), self.part.n_edges, len(dims) - 1
+            floats = E + N * sum(dims[1:L]) + N * sum(dims[:L]) + N * dims[0] \
+                + self.world * sum(dims[l] * dims[l + 1] for l in range(L)) + 3 * int(max_batch) * sum(dims)
+            self.peer = PeerArena(4 * floats + 256 * (2 * L + 8), self.device, group)
+            # fixed allocation order = identical offsets on every rank
+            self.peer.buf(("w",), (max(E, 1),))
+            for l in range(L - 1):
+                self.peer.buf(("h", l), (N, dims[l + 1]))
+            for l in range(L):
+                self.peer.buf(("dh", l), (N, dims[l]))
+            self.peer.buf(("d_entity",), (N, dims[0]))
+            self.peer.buf(("dW2",), (self.world, sum(dims[l] * dims[l + 1] for l in range(L))))
         self.dg_in = self.part.g_in.device_graph(self.device)
         self.dg_out = self.part.g_out.device_graph(self.device)
         p = self.part
@@ -131,20 +260,33 @@ class DistKGAT:
         """Attention refresh (models.py:146-154) on the partitioned graph; ``attention_weights()``
         returns the (E, 1) tensor in original edge order when the caller wants it."""
         m, p = self.model, self.part
+        e0, e1 = int(p.edge_bounds[self.rank]), int(p.edge_bounds[self.rank + 1])
         with th.no_grad():
-            _, w_csr = ops.attention(self.dg_in, m.entity_embed.weight, m.relation_embed.weight, m.W_R,
-                                     rows=(p.r0, p.r1), want_eid=False)
-            # one uneven all-gather assembles the weights of ALL edges in global CSR order
-            w_glob = th.empty(p.n_edges, dtype=th.float32, device=self.device)
-            w_glob[int(p.edge_bounds[self.rank]): int(p.edge_bounds[self.rank + 1])] = w_csr[: self.dg_in.n_edges]
-            exchange_rows(w_glob, p.edge_bounds, self.group)
+            if self.peer is not None:
+                # the softmax kernel writes this rank's slice of the all-edges vector (global CSR order)
+                # into every arena; after the barrier every rank holds the weights of ALL edges
+                w_glob = self.peer.buf(("w",), (max(p.n_edges, 1),))[: p.n_edges]
+                _, w_csr = ops.attention(self.dg_in, m.entity_embed.weight, m.relation_embed.weight, m.W_R,
+                                         rows=(p.r0, p.r1), want_eid=False, w_csr_out=w_glob[e0:e1], peer=self.peer)
+                self.peer.barrier()
+            else:
+                _, w_csr = ops.attention(self.dg_in, m.entity_embed.weight, m.relation_embed.weight, m.W_R,
+                                         rows=(p.r0, p.r1), want_eid=False)
+                # one uneven all-gather assembles the weights of ALL edges in global CSR order
+                w_glob = th.empty(p.n_edges, dtype=th.float32, device=self.device)
+                w_glob[e0:e1] = w_csr[: self.dg_in.n_edges]
+                exchange_rows(w_glob, p.edge_bounds, self.group)
             _, w_csc = self.dg_out.edge_weights(w_glob[self._out_rank])
         self._w_glob = w_glob
         self.w_full = None
-        self._plan = ops.PropagatePlan(
-            self.dg_in, w_csr, w_csc, dg_bwd=self.dg_out, rows=(p.r0, p.r1),
-            exchange=lambda t: exchange_rows(t, p.bounds, self.group),
-            reduce=self._reduce_weight_grads)
+        if self.peer is not None:
+            self._plan = ops.PropagatePlan(self.dg_in, w_csr, w_csc, dg_bwd=self.dg_out, rows=(p.r0, p.r1),
+                                           peer=self.peer)
+        else:
+            self._plan = ops.PropagatePlan(
+                self.dg_in, w_csr, w_csc, dg_bwd=self.dg_out, rows=(p.r0, p.r1),
+                exchange=lambda t: exchange_rows(t, p.bounds, self.group),
+                reduce=self._reduce_weight_grads)
         return self
 
     def attention_weights(self):
@@ -164,7 +306,8 @@ class DistKGAT:
 
     # CF-embedding mode -------------------------------------------------------------------
     def gnn(self, drop_masks=None):
-        """(N, sum d) embedding whose OWNED rows are valid (others zero); differentiable."""
+        """(N, sum d) embedding whose OWNED rows are valid (the others are zero with the NCCL exchange
+        and undefined with the peer exchange; ``full_embedding`` fills them); differentiable."""
         if self._plan is None:
             raise RuntimeError("call compute_attention() first")
         m = self.model
@@ -177,7 +320,13 @@ class DistKGAT:
         gradient stays compact and local (ops.DistBprLoss)."""
         return ops.DistBprLoss.apply(embedding, src_ids, pos_dst_ids, neg_dst_ids, self.model._reg_lambda_gnn,
                                      getattr(embedding, "_kgat_channel", None), (self.part.r0, self.part.r1),
-                                     self.group)
+                                     self.group, self.peer)
+
+    def close(self):
+        """Collective teardown of the peer arenas (no-op for the NCCL exchange)."""
+        if self.peer is not None:
+            self._plan = None
+            self.peer.close()
 
     def full_embedding(self, embedding):
         with th.no_grad():

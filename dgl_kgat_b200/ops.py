@@ -21,11 +21,14 @@ def _f32c(t: th.Tensor, device) -> th.Tensor:
     return t.contiguous()
 
 
-def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Tensor, rows=None, want_eid=True):
+def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Tensor, rows=None, want_eid=True,
+              w_csr_out=None, peer=None):
     """Logits + per-destination softmax (reference models.py:146-154).
 
     Returns ``(w_eid, w_csr)``: ``w_eid`` is the (E, 1) tensor ``compute_attention``
     returns (original edge order); ``w_csr`` the same weights in CSR order.
+    Multi-GPU (``peer`` = dist.PeerArena): ``w_csr_out`` is this rank's slice of the all-edges weight
+    vector inside the arena and the softmax kernel stores every weight to the peers' copies as well.
     """
     lib = _lib.load()
     dev = dg.device
@@ -35,7 +38,12 @@ def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Te
         raise _lib.KgatError("attention: parameter shapes do not match the graph (N=%d, R=%d)" % (dg.n_nodes, dg.n_rel))
     E = max(dg.n_edges, 1)
     logits = th.empty(E, dtype=th.float32, device=dev)
-    w_csr = th.empty(E, dtype=th.float32, device=dev)
+    if w_csr_out is not None:
+        if w_csr_out.dtype != th.float32 or w_csr_out.numel() != dg.n_edges or not w_csr_out.is_contiguous():
+            raise _lib.KgatError("attention: w_csr_out must be a contiguous fp32 vector of %d weights" % dg.n_edges)
+        w_csr = w_csr_out
+    else:
+        w_csr = th.empty(E, dtype=th.float32, device=dev)
     w_eid = None
     if want_eid:
         w_eid = th.zeros(dg.n_edges, 1, dtype=th.float32, device=dev) if rows is not None else \
@@ -47,9 +55,13 @@ def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Te
             _lib.check(lib.kgat_attention_logits(dg.ref, entity.data_ptr(), rel_emb.data_ptr(), W_R.data_ptr(),
                                                  d, rd, logits.data_ptr(), st), "kgat_attention_logits")
         with _lib.record("segment_softmax"):
-            _lib.check(lib.kgat_segment_softmax(dg.ref, r0, r1, logits.data_ptr(), w_csr.data_ptr(),
-                                                w_eid.data_ptr() if (want_eid and dg.n_edges) else None, st),
-                       "kgat_segment_softmax")
+            we = w_eid.data_ptr() if (want_eid and dg.n_edges) else None
+            if peer is not None:
+                _lib.check(lib.kgat_segment_softmax_push(dg.ref, r0, r1, logits.data_ptr(), w_csr.data_ptr(), we,
+                                                         peer.ref, st), "kgat_segment_softmax_push")
+            else:
+                _lib.check(lib.kgat_segment_softmax(dg.ref, r0, r1, logits.data_ptr(), w_csr.data_ptr(), we, st),
+                           "kgat_segment_softmax")
     return w_eid, w_csr
 
 
@@ -69,17 +81,19 @@ class PropagatePlan:
     Single GPU: one DeviceGraph, all rows.  Multi-GPU (dist.py): ``dg_fwd`` holds the CSR of the
     in-edges of the owned destination rows ``[r0, r1)``, ``dg_bwd`` the CSC of the out-edges of the
     same rows, and ``exchange(t)`` all-gathers the owned rows of a full-size (N, d) buffer in place;
-    ``reduce(t)`` sums a small replicated tensor over ranks."""
+    ``reduce(t)`` sums a small replicated tensor over ranks.  With ``peer`` (a dist.PeerArena) neither
+    is called: the exchanged buffers live in the arena, the ``*_push`` kernels store every owned row to
+    all peers while they compute, and only a device-side barrier follows."""
 
-    def __init__(self, dg_fwd, w_csr, w_csc, dg_bwd=None, rows=None, exchange=None, reduce=None):
+    def __init__(self, dg_fwd, w_csr, w_csc, dg_bwd=None, rows=None, exchange=None, reduce=None, peer=None):
         self.dg_fwd, self.dg_bwd = dg_fwd, dg_bwd if dg_bwd is not None else dg_fwd
         self.w_csr, self.w_csc = w_csr, w_csc
         self.r0, self.r1 = (0, dg_fwd.n_nodes) if rows is None else rows
-        self.exchange, self.reduce = exchange, reduce
+        self.exchange, self.reduce, self.peer = exchange, reduce, peer
 
     @property
     def distributed(self):
-        return self.exchange is not None
+        return self.exchange is not None or self.peer is not None
 
 
 class GradChannel:
@@ -122,7 +136,11 @@ class Propagate(th.autograd.Function):
             if w.shape[1] != dims[l]:
                 raise _lib.KgatError("layer %d weight is %s, expected (*, %d)" % (l, tuple(w.shape), dims[l]))
         masks = [None] * L if masks is None else [None if m is None else _f32c(m, dev) for m in masks]
-        alloc = th.zeros if plan.distributed else th.empty      # rows of other ranks stay defined
+        peer = plan.peer
+        # NCCL exchange: rows of other ranks are zero until exchanged; peer push: every row is written by its owner
+        alloc = th.zeros if (plan.distributed and peer is None) else th.empty
+        if peer is not None:
+            peer.generation += 1
         concat = None if single_layer else alloc(N, sum(dims), dtype=th.float32, device=dev)
         cstride = 0 if concat is None else concat.shape[1]
         saved = []
@@ -132,20 +150,27 @@ class Propagate(th.autograd.Function):
             for l in range(L):
                 d_in, d_out = dims[l], dims[l + 1]
                 h_nb = th.empty(N, d_in, dtype=th.float32, device=dev)
-                h_out = alloc(N, d_out, dtype=th.float32, device=dev)
+                push = peer is not None and l + 1 < L       # the next layer gathers rows owned by other ranks
+                h_out = peer.buf(("h", l), (N, d_out)) if push else alloc(N, d_out, dtype=th.float32, device=dev)
                 act = th.empty(N, d_out, dtype=th.float32, device=dev) if masks[l] is not None else None
                 with _lib.record("layer_fwd_%dx%d" % (d_in, d_out)):
-                    _lib.check(lib.kgat_layer_fwd(
-                        dg.ref, plan.r0, plan.r1, h.data_ptr(), plan.w_csr.data_ptr(), weights[l].data_ptr(),
-                        _lib.ptr(masks[l]), d_in, d_out, LEAKY_SLOPE, h_nb.data_ptr(), _lib.ptr(act),
-                        h_out.data_ptr(), _lib.ptr(concat), cstride, off,
-                        0 if (l == 0 and concat is not None) else -1, st), "kgat_layer_fwd")
-                if plan.distributed and l + 1 < L:
-                    plan.exchange(h_out)                # the next layer gathers rows owned by other ranks
+                    args = (dg.ref, plan.r0, plan.r1, h.data_ptr(), plan.w_csr.data_ptr(), weights[l].data_ptr(),
+                            _lib.ptr(masks[l]), d_in, d_out, LEAKY_SLOPE, h_nb.data_ptr(), _lib.ptr(act),
+                            h_out.data_ptr(), _lib.ptr(concat), cstride, off,
+                            0 if (l == 0 and concat is not None) else -1)
+                    if push:
+                        _lib.check(lib.kgat_layer_fwd_push(*args, peer.ref, st), "kgat_layer_fwd_push")
+                    else:
+                        _lib.check(lib.kgat_layer_fwd(*args, st), "kgat_layer_fwd")
+                if push:
+                    peer.barrier()
+                elif plan.distributed and l + 1 < L:
+                    plan.exchange(h_out)
                 saved.append((h, h_nb, act, h_out))
                 h, off = h_out, off + d_out
         ctx.plan, ctx.masks, ctx.dims, ctx.single = plan, masks, dims, single_layer
         ctx.saved, ctx.weights, ctx.channel = saved, weights, channel
+        ctx.generation = peer.generation if peer is not None else 0
         return h if single_layer else concat
 
     @staticmethod
@@ -175,15 +200,25 @@ class Propagate(th.autograd.Function):
             offs.append(offs[-1] + d)
         d_weights = [None] * L
         nxt_dx, nxt_dh = None, None
-        alloc = th.zeros if plan.distributed else th.empty
+        peer = plan.peer
+        if peer is not None and ctx.generation != peer.generation:
+            raise _lib.KgatError("the exchanged activations of this forward pass were overwritten by a later "
+                                 "gnn() call on the same DistKGAT; run backward before the next forward")
+        alloc = th.zeros if (plan.distributed and peer is None) else th.empty
+        w_off = [0]
+        for l in range(L):
+            w_off.append(w_off[-1] + dims[l] * dims[l + 1])
         with th.cuda.device(dev):
             st = _lib.stream_ptr()
+            # peer exchange: every layer's dW2 is a view of one flat buffer that travels as one slot
+            dw_flat = th.empty(w_off[-1], dtype=th.float32, device=dev) if peer is not None else None
             for l in reversed(range(L)):
                 d_in, d_out = dims[l], dims[l + 1]
                 h_in, h_nb, act, h_out = ctx.saved[l]
                 dx = th.empty(N, d_in, dtype=th.float32, device=dev)
-                dh = alloc(N, d_in, dtype=th.float32, device=dev)
-                dW = th.empty(d_out, d_in, dtype=th.float32, device=dev)
+                dh = peer.buf(("dh", l), (N, d_in)) if peer is not None else alloc(N, d_in, dtype=th.float32, device=dev)
+                dW = dw_flat[w_off[l]: w_off[l + 1]].view(d_out, d_in) if peer is not None else \
+                    th.empty(d_out, d_in, dtype=th.float32, device=dev)
                 part = th.empty(n_part * d_out * d_in, dtype=th.float32, device=dev)
                 if ctx.single:
                     # bare KGATConv: the incoming gradient IS the gradient of the layer output
@@ -191,26 +226,51 @@ class Propagate(th.autograd.Function):
                 else:
                     up_dx, up_dh = nxt_dx, nxt_dh
                 with _lib.record("layer_bwd_%dx%d" % (d_in, d_out), 2):
-                    _lib.check(lib.kgat_layer_bwd(
-                        dg.ref, plan.r0, plan.r1, _lib.ptr(d_concat), _lib.ptr(dc_slot), cstride, offs[l + 1],
-                        _lib.ptr(up_dx), _lib.ptr(up_dh), plan.w_csc.data_ptr(),
-                        h_in.data_ptr(), h_nb.data_ptr(), _lib.ptr(act), h_out.data_ptr(), _lib.ptr(ctx.masks[l]),
-                        ctx.weights[l].data_ptr(), d_in, d_out, LEAKY_SLOPE,
-                        dx.data_ptr(), dh.data_ptr(), dW.data_ptr(), part.data_ptr(), st), "kgat_layer_bwd")
-                if plan.distributed:
-                    plan.exchange(dh)                   # dh_nb rows of every rank feed the transposed gather below
+                    args = (dg.ref, plan.r0, plan.r1, _lib.ptr(d_concat), _lib.ptr(dc_slot), cstride, offs[l + 1],
+                            _lib.ptr(up_dx), _lib.ptr(up_dh), plan.w_csc.data_ptr(),
+                            h_in.data_ptr(), h_nb.data_ptr(), _lib.ptr(act), h_out.data_ptr(), _lib.ptr(ctx.masks[l]),
+                            ctx.weights[l].data_ptr(), d_in, d_out, LEAKY_SLOPE,
+                            dx.data_ptr(), dh.data_ptr(), dW.data_ptr(), part.data_ptr())
+                    if peer is not None:
+                        _lib.check(lib.kgat_layer_bwd_push(*args, peer.ref, st), "kgat_layer_bwd_push")
+                    else:
+                        _lib.check(lib.kgat_layer_bwd(*args, st), "kgat_layer_bwd")
+                # dh_nb rows of every rank feed the transposed gather of the next kernel
+                if peer is not None:
+                    peer.barrier()
+                elif plan.distributed:
+                    plan.exchange(dh)
                 d_weights[l] = dW
                 nxt_dx, nxt_dh = dx, dh
             d_entity = None
+            if peer is not None:
+                # last phase: the dW2 of all layers (one slot per rank) and the entity gradient share a barrier
+                slots = peer.buf(("dW2",), (peer.world, w_off[-1]))
+                with _lib.record("peer_push_slot"):
+                    _lib.check(lib.kgat_peer_push_slot(dw_flat.data_ptr(), w_off[-1], slots.data_ptr(), peer.ref, st),
+                               "kgat_peer_push_slot")
             if ctx.needs_input_grad[4]:
-                d_entity = alloc(N, dims[0], dtype=th.float32, device=dev)
+                d_entity = peer.buf(("d_entity",), (N, dims[0])) if peer is not None else \
+                    alloc(N, dims[0], dtype=th.float32, device=dev)
                 with _lib.record("input_bwd_%d" % dims[0]):
-                    _lib.check(lib.kgat_input_bwd(dg.ref, plan.r0, plan.r1, _lib.ptr(d_concat), _lib.ptr(dc_slot), cstride, 0,
-                                                  nxt_dx.data_ptr(), nxt_dh.data_ptr(), plan.w_csc.data_ptr(),
-                                                  dims[0], d_entity.data_ptr(), st), "kgat_input_bwd")
-                if plan.distributed:
+                    args = (dg.ref, plan.r0, plan.r1, _lib.ptr(d_concat), _lib.ptr(dc_slot), cstride, 0,
+                            nxt_dx.data_ptr(), nxt_dh.data_ptr(), plan.w_csc.data_ptr(), dims[0], d_entity.data_ptr())
+                    if peer is not None:
+                        _lib.check(lib.kgat_input_bwd_push(*args, peer.ref, st), "kgat_input_bwd_push")
+                    else:
+                        _lib.check(lib.kgat_input_bwd(*args, st), "kgat_input_bwd")
+                if peer is None and plan.distributed:
                     plan.exchange(d_entity)             # replicated parameters: every rank needs the full gradient
-            if plan.distributed:
+            if peer is not None:
+                peer.barrier()
+                dw_sum = th.empty(w_off[-1], dtype=th.float32, device=dev)
+                with _lib.record("peer_sum_slots"):
+                    _lib.check(lib.kgat_peer_sum_slots(slots.data_ptr(), w_off[-1], peer.world, dw_sum.data_ptr(), st),
+                               "kgat_peer_sum_slots")
+                d_weights = [dw_sum[w_off[l]: w_off[l + 1]].view(dims[l + 1], dims[l]) for l in range(L)]
+                if d_entity is not None:
+                    d_entity = d_entity.clone()         # the arena buffer is overwritten by the next backward
+            elif plan.distributed:
                 plan.reduce(d_weights)                  # one all-reduce for every layer's dW2
         return (None, None, None, None, d_entity, *d_weights)
 
@@ -293,16 +353,26 @@ class DistBprLoss(th.autograd.Function):
     backward needs no communication - each rank keeps the gradient rows of the nodes it owns."""
 
     @staticmethod
-    def forward(ctx, embedding, src, pos, neg, reg_lambda, channel, own, group):
+    def forward(ctx, embedding, src, pos, neg, reg_lambda, channel, own, group, peer=None):
         import torch.distributed as tdist
         dev = embedding.device
         emb = _f32c(embedding, dev)
         node_ids = [i.to(device=dev, dtype=th.int64).contiguous().view(-1) for i in (src, pos, neg)]
         B = node_ids[0].numel()
         cat = th.cat(node_ids)
-        mine = ((cat >= own[0]) & (cat < own[1])).unsqueeze(1)
-        table = emb.index_select(0, cat) * mine
-        tdist.all_reduce(table, group=group)
+        if peer is not None:
+            # every owner stores its rows into the table of every rank (NVLink stores), then one barrier
+            table = peer.buf(("loss_rows", B, emb.shape[1]), (3 * B, emb.shape[1]))
+            with th.cuda.device(dev):
+                with _lib.record("peer_gather_rows_push"):
+                    _lib.check(_lib.load().kgat_peer_gather_rows_push(
+                        emb.data_ptr(), emb.stride(0), emb.shape[1], cat.data_ptr(), 3 * B, own[0], own[1],
+                        table.data_ptr(), peer.ref, _lib.stream_ptr()), "kgat_peer_gather_rows_push")
+            peer.barrier()
+        else:
+            mine = ((cat >= own[0]) & (cat < own[1])).unsqueeze(1)
+            table = emb.index_select(0, cat) * mine
+            tdist.all_reduce(table, group=group)
         ar = th.arange(B, device=dev)
         ids = [ar, ar + B, ar + 2 * B]
         loss, sig, ws = _bpr_forward(table, ids, reg_lambda)
@@ -315,7 +385,7 @@ class DistBprLoss(th.autograd.Function):
         compact = _bpr_backward(ctx.table, ctx.ids, ctx.node_ids, ctx.own, ctx.shape[0], ctx.lam, ctx.sig,
                                 grad_loss, ctx.ws)
         grad = _deliver_compact(ctx.channel, compact, ctx.shape, ctx.table.device)
-        return grad, None, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None, None
 
 
 def bpr_loss(embedding, src, pos, neg, reg_lambda):

@@ -236,6 +236,84 @@ KGAT_API int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
                     const int32_t* mask_ptr, const int32_t* mask_items,
                     int K, int32_t* topk_idx, float* topk_score, kgat_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (8) Multi-GPU: peer-memory exchange for the destination-partitioned step (one process per GPU of one
+ *     NVLink / NVSwitch box).  New capability -- the reference is single-GPU (kgat.py:14,69-71).
+ *
+ *     Every rank owns an ARENA, exported with cudaIpc and mapped by every other rank.  A buffer that all
+ *     ranks need in full (a layer output, dh_nb, the entity gradient, the attention weights, the batch
+ *     rows of the loss) lives at the same offset of every arena; the *_push entry points below are the
+ *     kernels of the single-GPU path with ONE addition: every owned row they produce is stored into the
+ *     own arena AND into every peer's arena (NVLink stores issued next to the local ones), so the
+ *     all-gather overlaps the kernel row by row.  kgat_peer_barrier() is what remains of the collective.
+ *     The caller allocates all exchanged buffers identically on every rank (same offsets).
+ *
+ *     The first KGAT_PEER_HEADER_BYTES of an arena hold the barrier state and are not for payload.
+ *     These are the only entry points that own memory (explicit create / destroy). */
+#define KGAT_MAX_RANKS 8
+#define KGAT_PEER_HEADER_BYTES 1024
+#define KGAT_IPC_HANDLE_BYTES 64
+
+typedef struct kgat_peer_group {
+    int32_t  world, rank;
+    uint64_t arena_bytes;                 /* the same on every rank */
+    void*    arena[KGAT_MAX_RANKS];       /* arena[k]: address, in THIS process, of rank k's arena */
+} kgat_peer_group_t;
+
+/* cudaMalloc + zero-fill an arena on the current device and export it: handle_out_host receives the
+ * KGAT_IPC_HANDLE_BYTES of its cudaIpcMemHandle_t (exchange them over torch.distributed / MPI / a file). */
+KGAT_API int kgat_peer_arena_create(size_t bytes, void** arena_out_host, void* handle_out_host);
+/* Map a peer's arena from its handle (peer access is enabled on demand). */
+KGAT_API int kgat_peer_arena_open(const void* handle_host, void** arena_out_host);
+KGAT_API int kgat_peer_arena_close(void* mapped_arena);        /* for arenas obtained from _open    */
+KGAT_API int kgat_peer_arena_destroy(void* own_arena);         /* for the arena obtained from _create */
+
+/* All ranks enqueue the same sequence of barriers.  On the device: publish everything this rank's stream
+ * has written so far (system-scope release), signal every peer, wait until every peer has signalled the
+ * same barrier count (acquire).  One 32-thread CTA, no host involvement, CUDA-graph capturable.
+ * A peer that does not arrive within timeout_ms (<= 0: 20 000) sets the arena's error flag instead of
+ * hanging the GPU; later barriers then return at once.  kgat_peer_error() reads the flag (synchronises). */
+KGAT_API int kgat_peer_barrier(const kgat_peer_group_t* pg, int timeout_ms, kgat_stream_t stream);
+KGAT_API int kgat_peer_error(const kgat_peer_group_t* pg);
+
+/* kgat_segment_softmax whose w_csr lies in the own arena and is stored to every peer as well (the
+ * attention weights of ALL edges in global CSR order = the concatenation of the ranks' slices). */
+KGAT_API int kgat_segment_softmax_push(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                              const float* logits_csr, float* w_csr, float* w_eid,
+                              const kgat_peer_group_t* pg, kgat_stream_t stream);
+/* kgat_layer_fwd whose h_out (full (n_nodes, d_out) buffer in the own arena) is stored to every peer. */
+KGAT_API int kgat_layer_fwd_push(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                        const float* h_in, const float* w_csr, const float* W2,
+                        const float* drop_mask, int d_in, int d_out, float slope,
+                        float* h_nb, float* act, float* h_out,
+                        float* concat, int64_t concat_stride, int64_t out_off, int64_t in_off,
+                        const kgat_peer_group_t* pg, kgat_stream_t stream);
+/* kgat_layer_bwd whose dh_nb (full (n_nodes, d_in) buffer in the own arena) is stored to every peer. */
+KGAT_API int kgat_layer_bwd_push(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                        const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride, int64_t out_off,
+                        const float* nxt_dx_direct, const float* nxt_dh_nb, const float* w_csc,
+                        const float* h_in, const float* h_nb, const float* act, const float* h_out,
+                        const float* drop_mask, const float* W2, int d_in, int d_out, float slope,
+                        float* dx_direct, float* dh_nb, float* dW2, float* dW2_partials,
+                        const kgat_peer_group_t* pg, kgat_stream_t stream);
+/* kgat_input_bwd whose d_entity (full (n_nodes, d) buffer in the own arena) is stored to every peer. */
+KGAT_API int kgat_input_bwd_push(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
+                        const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride, int64_t in_off,
+                        const float* dx_direct, const float* dh_nb, const float* w_csc, int d,
+                        float* d_entity, const kgat_peer_group_t* pg, kgat_stream_t stream);
+/* Batch rows of the loss head: table[s, :] = emb[ids[s], :] for every slot s whose node
+ * ids[s] lies in [own_begin, own_end), written into the (n_slots, dim) table of EVERY rank (own arena
+ * included); after the barrier every rank holds all rows.  Replaces gather + mask + all-reduce. */
+KGAT_API int kgat_peer_gather_rows_push(const float* emb, int64_t emb_stride, int dim, const int64_t* ids,
+                               int64_t n_slots, int64_t own_begin, int64_t own_end, float* table,
+                               const kgat_peer_group_t* pg, kgat_stream_t stream);
+/* Small replicated sums (the dW2 of all layers): slots is a (world, n) buffer in the arena.
+ * _push_slot copies src[0..n) into slot `rank` of every rank's buffer; after the barrier _sum_slots
+ * adds the world slots in rank order (identical bits on every rank) into out[0..n). */
+KGAT_API int kgat_peer_push_slot(const float* src, int64_t n, float* slots, const kgat_peer_group_t* pg,
+                        kgat_stream_t stream);
+KGAT_API int kgat_peer_sum_slots(const float* slots, int64_t n, int world, float* out, kgat_stream_t stream);
+
 /* Hardware self-test of the tcgen05 path (diagnostics; not on the hot path):
  * C[128,N] = A[128,K] * B[N,K]^T on one CTA, mode 0 = one TF32 pass, mode 1 = 3xTF32.
  * *err_flag (device int) is set to 1 if the tensor-core completion barrier never fires. */

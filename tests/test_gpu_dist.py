@@ -1,6 +1,7 @@
-"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the destination-partitioned step over NCCL
-must reproduce the single-GPU step -- attention weights bit-identical (same kernels, same per-row
-order), embedding rows / loss / gradients within fp32 re-association noise."""
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the destination-partitioned step - with the
+peer-memory exchange (push kernels + device-side barriers over NVLink) and with the NCCL exchange - must
+reproduce the single-GPU step: attention weights bit-identical (same kernels, same per-row order),
+embedding rows / loss / gradients within fp32 re-association noise."""
 import os
 import socket
 
@@ -47,8 +48,27 @@ def _worker(rank, world, port, ret):
         loss1.backward()
         ref = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
         m.zero_grad(set_to_none=True)
+        for exchange in ("peer", "nccl"):
+            _check_exchange(exchange, m, ck, ids, dev, w1, emb1, loss1, ref)
+        ret[rank] = "ok"
+    except Exception as e:
+        ret[rank] = "FAIL: %r" % (e,)
+        raise
+    finally:
+        tdist.destroy_process_group()
+
+
+def _check_exchange(exchange, m, ck, ids, dev, w1, emb1, loss1, ref):
+    from dgl_kgat_b200 import metric
+    from dgl_kgat_b200.dist import DistKGAT
+    from dgl_kgat_b200.synth import pairs_to_user_dict
+    N, R, trip = ck.cfg.n_nodes, ck.cfg.n_relations, ck.triplets
+    U = ck.cfg.n_users
+    if True:
         # distributed
-        dk = DistKGAT(m, N, trip, R, dev)
+        m.zero_grad(set_to_none=True)
+        dk = DistKGAT(m, N, trip, R, dev, exchange=exchange)
+        assert (dk.peer is not None) == (exchange == "peer")
         dk.compute_attention()
         assert th.equal(w1, dk.attention_weights()), "attention weights differ"
         emb2 = dk.gnn()
@@ -70,12 +90,23 @@ def _worker(rank, world, port, ret):
         rec1, ndcg1 = metric.calc_recall_ndcg(emb1.detach(), tr, te, items, 20)
         rec2, ndcg2 = dk.calc_recall_ndcg(emb1.detach(), tr, te, ck.item_id_range, 20)
         assert abs(rec1 - rec2) < 1e-12 and abs(ndcg1 - ndcg2) < 1e-12
-        ret[rank] = "ok"
-    except Exception as e:
-        ret[rank] = "FAIL: %r" % (e,)
-        raise
-    finally:
-        tdist.destroy_process_group()
+        if dk.peer is not None:
+            # the whole partitioned step as one CUDA graph per rank (no NCCL inside)
+            from dgl_kgat_b200.graphed import GraphedDistCFStep
+            eager = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+            loss2_val = loss2.item()
+            del emb2, loss2                  # the eager autograd graph is bound to the default stream
+            m.zero_grad(set_to_none=True)
+            step = GraphedDistCFStep(dk, ids[0].numel())
+            loss3 = step(*ids)
+            th.cuda.synchronize()
+            assert abs(loss3.item() - loss2_val) <= 1e-6 * abs(loss2_val)
+            for k, p in m.named_parameters():
+                if k in eager:
+                    assert th.equal(p.grad, eager[k]), "graphed step differs from the eager step: " + k
+            assert dk.peer.error() == 0, "a peer barrier timed out"
+            step = None
+        dk.close()
 
 
 @pytest.mark.skipif(th.cuda.device_count() < 2, reason="needs at least 2 GPUs")
