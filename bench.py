@@ -265,6 +265,8 @@ def run_ours(args):
     dev = th.device("cuda", local)
     distributed = world > 1
     if distributed:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         tdist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().kgat_device_check(), "kgat_device_check")
 

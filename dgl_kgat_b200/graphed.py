@@ -10,6 +10,11 @@ reference refreshes it once per epoch), ``g.edata['w'] = A_w``, ``gnn``, ``get_l
 per-kernel launch latency between the ~20 kernels of a step.  Inputs travel through three static
 device buffers (one async copy each per call).  Dropout draws fresh masks on every replay (torch's
 graph-safe Philox state).
+
+Capture runs on a side stream, so no autograd graph of an earlier EAGER step may still be alive when a
+step is captured (drop / detach old ``loss`` and ``embedding`` tensors first): the parameters'
+AccumulateGrad nodes stay bound to the stream they were created on for as long as such a graph
+references them, and torch then refuses the capture ("legacy stream depend on a capturing stream").
 """
 from __future__ import annotations
 
@@ -75,11 +80,13 @@ class GraphedCFStep:
 
 
 class GraphedDistCFStep(GraphedCFStep):
-    """The same for the destination-partitioned step of :class:`dist.DistKGAT`: the kernels AND the
-    NCCL collectives of one iteration (weight all-gather, row exchanges, loss-row and dW2 all-reduces)
-    are captured in one CUDA graph per rank.  EXPERIMENTAL: on 2 B200s it bought only ~3 % over the
-    eager step and tearing the process group down after capturing NCCL work was unreliable; bench.py
-    uses it only when KGAT_BENCH_GRAPH_DIST=1."""
+    """The same for the destination-partitioned step of :class:`dist.DistKGAT`, one CUDA graph per rank.
+    With the peer exchange (default) the step consists of this library's kernels only - the row pushes
+    ride on the compute kernels and the device-side barriers are ordinary kernel nodes - so the graph
+    holds no NCCL work and replays without the host: 1.15 ms per step on 2 B200s (eager 1.30 ms;
+    NCCL exchange, eager: 2.06 ms).  With ``exchange="nccl"`` the collectives are captured too;
+    that variant is EXPERIMENTAL (gain ~3 %, process-group teardown after capturing NCCL work was
+    unreliable) and bench.py uses it only when KGAT_BENCH_GRAPH_DIST=1."""
 
     def __init__(self, dk, batch_size, warmup=3):
         self.dk, self.model = dk, dk.model

@@ -48,6 +48,7 @@ def _worker(rank, world, port, ret):
         loss1.backward()
         ref = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
         m.zero_grad(set_to_none=True)
+        emb1, loss1 = emb1.detach(), loss1.detach()      # drop the eager autograd graph (see graphed.py)
         for exchange in ("peer", "nccl"):
             _check_exchange(exchange, m, ck, ids, dev, w1, emb1, loss1, ref)
         ret[rank] = "ok"
