@@ -15,7 +15,8 @@
  *     caller (fp32 values, int32 ids), unless its name ends in _host;
  *   - the library allocates nothing and keeps no state between calls; scratch
  *     comes in through an explicit workspace argument sized by a *_workspace_bytes
- *     query;
+ *     query (only exception: the multi-GPU arenas of section 8, which have explicit
+ *     create / destroy calls);
  *   - work is enqueued on the given stream and the call returns without
  *     synchronising (CUDA-graph capturable), except kgat_graph_build which
  *     performs no host read-back either;
