@@ -52,10 +52,20 @@ __device__ __forceinline__ float4 gather_row(const int32_t* __restrict__ idx, co
         fma4(acc, w2, v2);
         fma4(acc, w3, v3);
     }
-    for (; e < end; e += EPW) {
-        const int s0 = __ldg(idx + e);
-        const float w0 = __ldg(wgt + e);
-        fma4(acc, w0, ldg4(base + static_cast<size_t>(s0) * W));
+    // tail: at most three edges per lane group are left.  Their loads are issued together (a short row -
+    // the ~8 interactions of a user, 44 % of the rows of a CKG - would otherwise be a chain of dependent
+    // index -> feature-row round trips); the additions keep the order of the edges.
+    if (e < end) {
+        const bool p1 = e + EPW < end, p2 = e + 2 * EPW < end;
+        const int s0 = __ldg(idx + e), s1 = p1 ? __ldg(idx + e + EPW) : 0, s2 = p2 ? __ldg(idx + e + 2 * EPW) : 0;
+        const float w0 = __ldg(wgt + e), w1 = p1 ? __ldg(wgt + e + EPW) : 0.f, w2 = p2 ? __ldg(wgt + e + 2 * EPW) : 0.f;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v0 = ldg4(base + static_cast<size_t>(s0) * W);
+        const float4 v1 = p1 ? ldg4(base + static_cast<size_t>(s1) * W) : zero;
+        const float4 v2 = p2 ? ldg4(base + static_cast<size_t>(s2) * W) : zero;
+        fma4(acc, w0, v0);
+        if (p1) fma4(acc, w1, v1);
+        if (p2) fma4(acc, w2, v2);
     }
     return across_groups_sum<LPE>(acc);
 }
@@ -225,7 +235,7 @@ struct BwdCfg {
 };
 
 template <int DIN, int DOUT, bool PUSH>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (DIN * DOUT <= 4096 ? 4 : 1))   // persistent grid: 4 CTAs per SM (bwd_max_ctas)
 layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
                  const float* __restrict__ w_csc, int row_begin, int row_end, int n_tiles,
                  const float* __restrict__ d_concat, const int32_t* __restrict__ dc_slot, int64_t cstride,
