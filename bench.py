@@ -246,7 +246,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "reference models.py op sequence on pure-torch CPU message passing (DGL itself cannot be installed)",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -265,8 +265,6 @@ def run_ours(args):
     dev = th.device("cuda", local)
     distributed = world > 1
     if distributed:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         tdist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().kgat_device_check(), "kgat_device_check")
 
@@ -471,7 +469,7 @@ def run_ours(args):
             "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cpu, "kernels": table, "eval": eval_info,
         }
-        print(json.dumps(line))
+        emit(line)
     if distributed:
         graphed = None
         dk.close()
@@ -479,8 +477,19 @@ def run_ours(args):
         tdist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
+
 if __name__ == "__main__":
     a = parse()
+    # stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so that
+    # anything a native library prints (NCCL's version banner goes to fd 1) cannot end up next to the result
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

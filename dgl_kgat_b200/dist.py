@@ -148,14 +148,70 @@ def partition_rows(indegree: np.ndarray, n_parts: int) -> np.ndarray:
     return np.maximum.accumulate(b)
 
 
-class Partition:
-    """The slice of the CKG owned by ``rank``: edge subsets and the two local graphs."""
+def partition_rows_minmax(edge_cost: np.ndarray, n_parts: int, row_ns: float, edge_ns: float) -> np.ndarray:
+    """Boundaries b[0..n_parts] of contiguous ranges minimising
+    ``row_ns * max_k rows(k) + edge_ns * max_k edges(k)``.
 
-    def __init__(self, n_nodes, triplets, n_rel, rank, world):
+    The phases of a partitioned step are separated by barriers, and a phase is bound either by the ROWS a
+    rank owns (the kernels that push every owned row to all peers over NVLink) or by its EDGES (the
+    gathers), so the step costs the sum of the per-phase maxima, not the maximum of the per-rank sums:
+    balancing a blended per-row cost leaves one rank row-heavy and the others edge-heavy and every phase
+    waits for somebody.  For a row budget R and an edge budget E the greedy left-to-right packing decides
+    feasibility exactly (both constraints are monotone in the range), so the optimum is found by scanning
+    R and bisecting E.  Deterministic: every rank computes the same boundaries."""
+    n = len(edge_cost)
+    if n_parts <= 1 or n == 0:
+        return np.array([0] + [n] * max(n_parts, 1), dtype=np.int64)
+    ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(edge_cost, out=ptr[1:])
+    total, heaviest = int(ptr[-1]), int(edge_cost.max())
+
+    def pack(r_max, e_max):
+        b = [0]
+        for _ in range(n_parts):
+            a = b[-1]
+            by_edges = int(np.searchsorted(ptr, ptr[a] + e_max, side="right")) - 1
+            b.append(max(a, min(n, a + r_max, by_edges)))
+        return b if b[-1] == n else None
+
+    best = None
+    r_lo = -(-n // n_parts)
+    for r_max in sorted({int(r) for r in np.linspace(r_lo, n, 48)}):
+        lo, hi = max(heaviest, -(-total // n_parts)), total
+        if pack(r_max, hi) is None:
+            continue
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if pack(r_max, mid) is None:
+                lo = mid + 1
+            else:
+                hi = mid
+        cost = row_ns * r_max + edge_ns * lo
+        if best is None or cost < best[0]:
+            best = (cost, pack(r_max, lo))
+    return np.asarray(best[1], dtype=np.int64)
+
+
+class Partition:
+    """The slice of the CKG owned by ``rank``: edge subsets and the two local graphs.
+
+    ``row_ns`` = 0 (default): contiguous ranges with equal in-edge counts (``partition_rows``).
+    ``row_ns`` > 0: ranges that minimise ``row_ns * max rows + edge_ns * max edges`` over the ranks
+    (``partition_rows_minmax``; an edge = half an in-edge + half an out-edge, forward and backward gathers).
+    Balancing edges alone gives the rank that holds the users (~8 edges each, 44 % of the rows of an
+    Amazon-book CKG) half of all rows at 4 ranks - measured: its push kernels were NVLink-egress bound
+    (1.7 ns per 256-byte row and 3 peers) while the other ranks idled at the barriers."""
+
+    def __init__(self, n_nodes, triplets, n_rel, rank, world, row_ns=0.0, edge_ns=0.36):
         trip = np.ascontiguousarray(triplets, dtype=np.int32)
         self.n_nodes, self.n_rel, self.n_edges = int(n_nodes), int(n_rel), trip.shape[0]
         self.rank, self.world = rank, world
-        self.bounds = partition_rows(np.bincount(trip[:, 0], minlength=n_nodes), world)
+        indeg = np.bincount(trip[:, 0], minlength=n_nodes).astype(np.int64)
+        if row_ns > 0 and world > 1:
+            both = indeg + np.bincount(trip[:, 2], minlength=n_nodes)
+            self.bounds = partition_rows_minmax(both, world, row_ns, edge_ns / 2)
+        else:
+            self.bounds = partition_rows(indeg, world)
         self.r0, self.r1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
         self.eid_in = np.flatnonzero((trip[:, 0] >= self.r0) & (trip[:, 0] < self.r1))     # head owned: forward
         self.eid_out = np.flatnonzero((trip[:, 2] >= self.r0) & (trip[:, 2] < self.r1))    # tail owned: backward
@@ -228,7 +284,12 @@ class DistKGAT:
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl', got %r" % (exchange,))
         self.exchange = exchange
-        self.part = Partition(n_nodes, triplets, n_rel, self.rank, self.world)
+        # cost model of the partition (measured on B200, Amazon-book shape, ns per step): an edge costs ~0.36
+        # (all gathers of a step), a row ~1 for its dense work plus, with the peer exchange, ~2.9 per peer for
+        # the NVLink copies of its exchanged rows (6 buffers, 1.3 KB per row and peer at ~450 GB/s)
+        row_ns = os.environ.get("KGAT_DIST_ROW_NS")
+        row_ns = float(row_ns) if row_ns is not None else 1.0 + (2.9 * (self.world - 1) if exchange == "peer" else 0.0)
+        self.part = Partition(n_nodes, triplets, n_rel, self.rank, self.world, row_ns=row_ns)
         self.peer = None
         if exchange == "peer":
             dims = [model.entity_embed.weight.shape[1]] + [l.res_fc_2.weight.shape[0] for l in model.layers]

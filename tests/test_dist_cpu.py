@@ -51,6 +51,36 @@ def test_partition_rows_matches_oracle_and_balances():
     assert np.array_equal(np.sort(np.concatenate(owned_out)), np.arange(trip.shape[0]))
 
 
+def test_partition_rows_minmax_is_a_valid_and_better_partition():
+    """The cost-model partition (dist.partition_rows_minmax): boundaries cover every row once, are
+    monotone, never do worse on their own objective than the edge-balanced split, and a row-dominated
+    model degenerates to equal row counts."""
+    trip, N, R = small_graph()
+    deg = np.bincount(trip[:, 0], minlength=N) + np.bincount(trip[:, 2], minlength=N)
+    ptr = np.concatenate([[0], np.cumsum(deg)])
+
+    def objective(b, row_ns, edge_ns):
+        return row_ns * np.diff(b).max() + edge_ns * np.diff(ptr[b]).max()
+
+    for parts in (1, 2, 3, 4, 8):
+        for row_ns, edge_ns in ((1.0, 0.18), (9.7, 0.18), (0.01, 1.0)):
+            b = kdist.partition_rows_minmax(deg, parts, row_ns, edge_ns)
+            assert len(b) == parts + 1 and b[0] == 0 and b[-1] == N and np.all(np.diff(b) >= 0)
+            base = kdist.partition_rows(deg, parts)
+            assert objective(b, row_ns, edge_ns) <= objective(base, row_ns, edge_ns) * (1 + 1e-9)
+        b = kdist.partition_rows_minmax(deg, parts, 1e6, 1e-6)
+        assert np.diff(b).max() == -(-N // parts)
+    # deterministic (every rank must compute the same boundaries)
+    assert np.array_equal(kdist.partition_rows_minmax(deg, 4, 9.7, 0.18), kdist.partition_rows_minmax(deg, 4, 9.7, 0.18))
+    # the Partition object uses it when a row cost is given and still owns every edge exactly once
+    owned = []
+    for r in range(4):
+        p = kdist.Partition(N, trip, R, r, 4, row_ns=9.7)
+        owned.append(p.eid_in)
+        assert np.array_equal(p.bounds, kdist.partition_rows_minmax(deg, 4, 9.7, 0.18))
+    assert np.array_equal(np.sort(np.concatenate(owned)), np.arange(trip.shape[0]))
+
+
 def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
