@@ -390,7 +390,12 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peak, peak_src = measured_peaks()
-    alg = algorithmic_bytes(N, E, R, dims)
+    if distributed:
+        # rank 0's share: its owned rows, the in-edges (forward / attention) it gathers over
+        n_loc, e_loc = dk.part.r1 - dk.part.r0, dk.dg_in.n_edges
+        alg = algorithmic_bytes(n_loc, e_loc, R, dims)
+    else:
+        alg = algorithmic_bytes(N, E, R, dims)
     table = {}
     for name, ms in kernel_ms.items():
         b = alg.get(name)
@@ -398,15 +403,19 @@ def run_ours(args):
                        "GBps": None if b is None else round(b / (ms * 1e-3) / 1e9, 1)}
     roofline = None
     modelled = {k: v for k, v in kernel_ms.items() if alg.get(k) is not None}
-    if modelled and not distributed:
+    if modelled:
         top = max(modelled, key=modelled.get)
         ach = alg[top] / (kernel_ms[top] * 1e-3) / 1e9
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": measured_traffic(top), "peak_source": peak_src, "launch_ms": kernel_ms[top],
-                    "traffic_source": "profiles/traffic_r1.json (ncu --set full, same workload)",
+                    "traffic": None if distributed else measured_traffic(top), "peak_source": peak_src,
+                    "launch_ms": kernel_ms[top],
+                    "traffic_source": None if distributed else "profiles/traffic_r1.json (ncu --set full, same workload)",
                     "algorithmic_bytes": alg[top],
-                    "step_frac": (step_bytes(N, E, R) / (ms_step * 1e-3) / 1e9) / peak,
+                    # whole job: the step's algorithmic bytes over the step time, against world x the peak
+                    "step_frac": (step_bytes(N, E, R) / (ms_step * 1e-3) / 1e9) / (peak * world),
                     "step_alg_GB": step_bytes(N, E, R) / 1e9}
+        if distributed:
+            roofline["scope"] = "rank 0 (%d of %d rows, %d of %d in-edges); step_frac is whole-job" % (n_loc, N, e_loc, E)
 
     # ---- eval users/s -------------------------------------------------------------------------
     eval_info = None
