@@ -33,6 +33,7 @@ import torch.distributed as tdist
 
 import ctypes
 import os
+import socket
 
 from . import _lib, metric, ops
 from .graph import CKGraph
@@ -74,10 +75,14 @@ class PeerArena:
             _lib.check(lib.kgat_peer_arena_create(self.nbytes, ctypes.byref(own), handle), "kgat_peer_arena_create")
             self._own = own.value
             infos = [None] * self.world
-            tdist.all_gather_object(infos, (bytes(handle.raw), self.nbytes), group=group)
-            if any(n != self.nbytes for _, n in infos):
-                raise _lib.KgatError("peer arenas differ in size across ranks: %s" % [n for _, n in infos])
-            for k, (h, _) in enumerate(infos):
+            tdist.all_gather_object(infos, (bytes(handle.raw), self.nbytes, socket.gethostname()), group=group)
+            if len({host for _, _, host in infos}) != 1:
+                raise _lib.KgatError("the peer exchange maps the other ranks' memory with cudaIpc and needs all ranks "
+                                     "on one NVLink box; ranks span %s - use exchange='nccl'"
+                                     % sorted({host for _, _, host in infos}))
+            if any(n != self.nbytes for _, n, _ in infos):
+                raise _lib.KgatError("peer arenas differ in size across ranks: %s" % [n for _, n, _ in infos])
+            for k, (h, _, _) in enumerate(infos):
                 if k == self.rank:
                     self._pg.arena[k] = self._own
                     continue
