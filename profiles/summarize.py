@@ -84,10 +84,10 @@ if os.path.exists(rep):
     import json
 
     def bench_key(name):
-        m = re.search(r"layer_(fwd|bwd)_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", name)
+        m = re.search(r"layer_(fwd|bwd)_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)[,>]", name)
         if m:
             return "layer_%s_%sx%s" % m.groups()
-        m = re.search(r"input_bwd_kernel<\(?(?:int\))?(\d+)>", name)
+        m = re.search(r"input_bwd_kernel<\(?(?:int\))?(\d+)[,>]", name)
         if m:
             return "input_bwd_%s" % m.group(1)
         if "att_logits" in name:
