@@ -291,15 +291,25 @@ layer_fwd_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict_
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-template <int DIN, int DOUT>
+// EPI selects the two tile GEMMs of phase 2 (dW2 += dpre^T z and dz = dpre W2): 0 = fp32 FFMA from shared
+// memory, 1 = tensor cores (mma.sync m16n8k8 3xTF32, see FwdSmem).  With the MMA the three shared arrays
+// get a row stride of width + 8 floats: the fragment loads that walk ROWS with the lane's t index (A of the
+// dW product = dpre^T, both B operands) then hit 32 different banks, the one that walks rows with g (A of
+// the dz product) is 2-way conflicted.
+template <int DIN, int DOUT, int EPI = 0>
 struct BwdCfg {
     static constexpr int BJ = (DOUT * DIN >= 4096) ? 4 : ((DOUT * DIN >= 2048) ? 2 : 1);
     static constexpr int NBLOCKS = DOUT * DIN / (4 * BJ);
     static constexpr int NB = (NBLOCKS + THREADS - 1) / THREADS;
-    static constexpr size_t bytes = sizeof(float) * (DOUT * DIN + TM * DOUT + TM * DIN + COOP_FLOATS) + 16;
+    static constexpr int LDP = EPI ? DOUT + 8 : DOUT;       // sDP row stride
+    static constexpr int LDZ = EPI ? DIN + 8 : DIN;         // sZ
+    static constexpr int LDW = EPI ? DIN + 8 : DIN;         // sW (W2 as given, [DOUT][DIN])
+    static constexpr int WT = (DOUT / 16) * (DIN / 8);      // 16 x 8 tiles of dW2
+    static constexpr int TPW = WT > 0 ? (WT + WARPS - 1) / WARPS : 1;    // ... per warp
+    static constexpr size_t bytes = sizeof(float) * (DOUT * LDW + TM * LDP + TM * LDZ + COOP_FLOATS) + 16;
 };
 
-template <int DIN, int DOUT, bool PUSH>
+template <int DIN, int DOUT, bool PUSH, int EPI>
 __global__ void __launch_bounds__(THREADS, (DIN * DOUT <= 4096 ? 4 : 1))   // persistent grid: 4 CTAs per SM (bwd_max_ctas)
 layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
                  const float* __restrict__ w_csc, int row_begin, int row_end, int n_tiles,
@@ -311,27 +321,35 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                  const float* __restrict__ drop_mask, const float* __restrict__ W2, float slope,
                  float* __restrict__ dx_direct, float* __restrict__ dh_nb, float* __restrict__ partials,
                  PeerOut po) {
-    using C = BwdCfg<DIN, DOUT>;
+    using C = BwdCfg<DIN, DOUT, EPI>;
     constexpr int BJ = C::BJ, NBLOCKS = C::NBLOCKS, NB = C::NB;
+    constexpr int LDP = C::LDP, LDZ = C::LDZ, LDW = C::LDW, WT = C::WT, TPW = C::TPW;
     constexpr int LPI = DIN / 4, LPO = DOUT / 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sDP = reinterpret_cast<float*>(smem_raw);     // [TM][DOUT]
-    float* sZ = sDP + TM * DOUT;                         // [TM][DIN]
-    float* sW = sZ + TM * DIN;                           // [DOUT][DIN] as given
-    float4* sPart = reinterpret_cast<float4*>(sW + DOUT * DIN);
+    float* sDP = reinterpret_cast<float*>(smem_raw);     // [TM][LDP]
+    float* sZ = sDP + TM * LDP;                          // [TM][LDZ]
+    float* sW = sZ + TM * LDZ;                           // [DOUT][LDW], W2 as given
+    float4* sPart = reinterpret_cast<float4*>(sW + DOUT * LDW);
     int* sLong = reinterpret_cast<int*>(sPart + WARPS * 32);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int idx = tid; idx < DOUT * DIN / 4; idx += THREADS)
-        reinterpret_cast<float4*>(sW)[idx] = __ldg(reinterpret_cast<const float4*>(W2) + idx);
+        *reinterpret_cast<float4*>(sW + (idx / LPI) * LDW + (idx % LPI) * 4) =
+            __ldg(reinterpret_cast<const float4*>(W2) + idx);
 
-    float acc[NB][BJ][4];
+    float acc[NB][BJ][4];          // EPI 0: dW2 blocks of this thread
 #pragma unroll
     for (int n = 0; n < NB; ++n)
 #pragma unroll
         for (int a = 0; a < BJ; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[n][a][b] = 0.f;
+    float cw[TPW][4];              // EPI 1: dW2 accumulator fragments of this warp's 16 x 8 tiles
+#pragma unroll
+    for (int q = 0; q < TPW; ++q)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) cw[q][b] = 0.f;
+    const int fg = lane >> 2, ft = lane & 3;      // fragment coordinates of this lane
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int row0 = row_begin + tile * TM;
@@ -389,8 +407,8 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                 const float4 x = ldg4(h_in + oi), hn = ldg4(h_nb + oi);
                 z = make_float4(x.x * hn.x, x.y * hn.y, x.z * hn.z, x.w * hn.w);
             }
-            if (lane < LPO) *reinterpret_cast<float4*>(sDP + rl * DOUT + lane * 4) = dp;
-            if (lane < LPI) *reinterpret_cast<float4*>(sZ + rl * DIN + lane * 4) = z;
+            if (lane < LPO) *reinterpret_cast<float4*>(sDP + rl * LDP + lane * 4) = dp;
+            if (lane < LPI) *reinterpret_cast<float4*>(sZ + rl * LDZ + lane * 4) = z;
         };
         bool warp_long = false;
         for (int rl = warp; rl < TM; rl += WARPS) {
@@ -418,6 +436,68 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
             __syncthreads();
         }
 
+        if constexpr (EPI == 1) {
+            static_assert(TM == 32 && DIN % 8 == 0 && DOUT % 16 == 0, "m16n8k8 tiling");
+            constexpr int NTN = DIN / 8;
+            // phase 2a: dW2 (DOUT x DIN) += dpre^T (DOUT x 32) z (32 x DIN): A[m][k] = sDP[k][m], B[k][n] = sZ[k][n]
+#pragma unroll
+            for (int ks = 0; ks < TM / 8; ++ks) {
+#pragma unroll
+                for (int q = 0; q < TPW; ++q) {
+                    const int p = warp + q * WARPS;
+                    if (p < WT) {                                     // warp-uniform
+                        const int mt = p / NTN, nt = p % NTN;
+                        const float* ap = sDP + (8 * ks + ft) * LDP + 16 * mt + fg;
+                        const float* bp = sZ + (8 * ks + ft) * LDZ + 8 * nt + fg;
+                        uint32_t ah[4], al[4], bh[2], bl[2];
+                        split_tf32(ap[0], ah[0], al[0]);
+                        split_tf32(ap[8], ah[1], al[1]);
+                        split_tf32(ap[4 * LDP], ah[2], al[2]);
+                        split_tf32(ap[4 * LDP + 8], ah[3], al[3]);
+                        split_tf32(bp[0], bh[0], bl[0]);
+                        split_tf32(bp[4 * LDZ], bh[1], bl[1]);
+                        mma_tf32_16x8x8(cw[q], al, bh);
+                        mma_tf32_16x8x8(cw[q], ah, bl);
+                        mma_tf32_16x8x8(cw[q], ah, bh);
+                    }
+                }
+            }
+            // phase 2b: dz (32 x DIN) = dpre (32 x DOUT) W2 (DOUT x DIN): A[m][k] = sDP[m][k], B[k][n] = sW[k][n]
+            for (int p = warp; p < 2 * NTN; p += WARPS) {
+                const int mt = p / NTN, nt = p % NTN;
+                const float* a0p = sDP + (16 * mt + fg) * LDP + ft;
+                const float* a1p = a0p + 8 * LDP;
+                const float* bp = sW + ft * LDW + 8 * nt + fg;
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < DOUT / 8; ++ks) {
+                    uint32_t ah[4], al[4], bh[2], bl[2];
+                    split_tf32(a0p[8 * ks], ah[0], al[0]);
+                    split_tf32(a1p[8 * ks], ah[1], al[1]);
+                    split_tf32(a0p[8 * ks + 4], ah[2], al[2]);
+                    split_tf32(a1p[8 * ks + 4], ah[3], al[3]);
+                    split_tf32(bp[(8 * ks) * LDW], bh[0], bl[0]);
+                    split_tf32(bp[(8 * ks + 4) * LDW], bh[1], bl[1]);
+                    mma_tf32_16x8x8(c, al, bh);
+                    mma_tf32_16x8x8(c, ah, bl);
+                    mma_tf32_16x8x8(c, ah, bh);
+                }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int row = row0 + 16 * mt + fg + 8 * half;
+                    if (row < row_end) {
+                        const size_t o = static_cast<size_t>(row) * DIN + 8 * nt + 2 * ft;
+                        const float2 hn = __ldg(reinterpret_cast<const float2*>(h_nb + o));
+                        const float2 hi = __ldg(reinterpret_cast<const float2*>(h_in + o));
+                        const float d0 = c[2 * half], d1 = c[2 * half + 1];
+                        *reinterpret_cast<float2*>(dx_direct + o) = make_float2(d0 * hn.x, d1 * hn.y);
+                        const float2 dh = make_float2(d0 * hi.x, d1 * hi.y);
+                        *reinterpret_cast<float2*>(dh_nb + o) = dh;
+                        if (PUSH) peer_store(po, o, dh);
+                    }
+                }
+            }
+        } else {
         // phase 2a: dW2 += dpre^T z
 #pragma unroll
         for (int n = 0; n < NB; ++n) {
@@ -426,10 +506,10 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                 const int i0 = (b % LPI) * 4, j0 = (b / LPI) * BJ;
 #pragma unroll 4
                 for (int r = 0; r < TM; ++r) {
-                    const float4 zv = *reinterpret_cast<const float4*>(sZ + r * DIN + i0);
+                    const float4 zv = *reinterpret_cast<const float4*>(sZ + r * LDZ + i0);
 #pragma unroll
                     for (int a = 0; a < BJ; ++a) {
-                        const float d = sDP[r * DOUT + j0 + a];
+                        const float d = sDP[r * LDP + j0 + a];
                         acc[n][a][0] = fmaf(d, zv.x, acc[n][a][0]);
                         acc[n][a][1] = fmaf(d, zv.y, acc[n][a][1]);
                         acc[n][a][2] = fmaf(d, zv.z, acc[n][a][2]);
@@ -450,11 +530,11 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
             for (int k = 0; k < RPT; ++k) dz[k] = 0.f;
 #pragma unroll 4
             for (int j = 0; j < DOUT; j += 4) {
-                const float w0 = sW[(j + 0) * DIN + i], w1 = sW[(j + 1) * DIN + i], w2 = sW[(j + 2) * DIN + i],
-                            w3 = sW[(j + 3) * DIN + i];
+                const float w0 = sW[(j + 0) * LDW + i], w1 = sW[(j + 1) * LDW + i], w2 = sW[(j + 2) * LDW + i],
+                            w3 = sW[(j + 3) * LDW + i];
 #pragma unroll
                 for (int k = 0; k < RPT; ++k) {
-                    const float4 d = *reinterpret_cast<const float4*>(sDP + (rg + k * RG) * DOUT + j);
+                    const float4 d = *reinterpret_cast<const float4*>(sDP + (rg + k * RG) * LDP + j);
                     dz[k] = fmaf(d.x, w0, dz[k]);
                     dz[k] = fmaf(d.y, w1, dz[k]);
                     dz[k] = fmaf(d.z, w2, dz[k]);
@@ -473,19 +553,33 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                 }
             }
         }
+        }   // EPI == 0
     }
 
     // one dW2 partial per CTA
     float* my = partials + static_cast<size_t>(blockIdx.x) * DOUT * DIN;
+    if constexpr (EPI == 1) {
 #pragma unroll
-    for (int n = 0; n < NB; ++n) {
-        const int b = tid + n * THREADS;
-        if (b < NBLOCKS) {
-            const int i0 = (b % LPI) * 4, j0 = (b / LPI) * BJ;
+        for (int q = 0; q < TPW; ++q) {
+            const int p = warp + q * WARPS;
+            if (p < WT) {
+                const int mt = p / (DIN / 8), nt = p % (DIN / 8);
+                float* o = my + (16 * mt + fg) * DIN + 8 * nt + 2 * ft;
+                *reinterpret_cast<float2*>(o) = make_float2(cw[q][0], cw[q][1]);
+                *reinterpret_cast<float2*>(o + 8 * DIN) = make_float2(cw[q][2], cw[q][3]);
+            }
+        }
+    } else {
 #pragma unroll
-            for (int a = 0; a < BJ; ++a)
-                *reinterpret_cast<float4*>(my + (j0 + a) * DIN + i0) =
-                    make_float4(acc[n][a][0], acc[n][a][1], acc[n][a][2], acc[n][a][3]);
+        for (int n = 0; n < NB; ++n) {
+            const int b = tid + n * THREADS;
+            if (b < NBLOCKS) {
+                const int i0 = (b % LPI) * 4, j0 = (b / LPI) * BJ;
+#pragma unroll
+                for (int a = 0; a < BJ; ++a)
+                    *reinterpret_cast<float4*>(my + (j0 + a) * DIN + i0) =
+                        make_float4(acc[n][a][0], acc[n][a][1], acc[n][a][2], acc[n][a][3]);
+            }
         }
     }
 }
@@ -621,19 +715,32 @@ struct BwdArgs {
 
 inline int bwd_max_ctas() { return 4 * num_sms(); }
 
-template <int DIN, int DOUT, bool PUSH>
+// Tile GEMMs of layer_bwd: tensor cores (widths DIN >= 32, DOUT >= 16) on the single-GPU path - parity-tested
+// and measured on B200 (step 1.403 -> 1.359 ms); the multi-GPU PUSH instantiations keep the fp32 FFMA GEMMs
+// until the MMA variant has been run under the peer exchange as well.  KGAT_BWD_EPILOGUE=mma / ffma forces one.
+inline int bwd_epilogue(int d_in, int d_out, bool push) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = std::getenv("KGAT_BWD_EPILOGUE");
+        forced = !e ? -1 : (std::strcmp(e, "mma") == 0 ? 1 : (std::strcmp(e, "ffma") == 0 ? 0 : -1));
+    }
+    const int want = forced >= 0 ? forced : (push ? 0 : 1);
+    return (want == 1 && d_in >= 32 && d_out >= 16) ? 1 : 0;
+}
+
+template <int DIN, int DOUT, bool PUSH, int EPI>
 int launch_bwd_t(const BwdArgs& a) {
-    constexpr size_t smem = BwdCfg<DIN, DOUT>::bytes;
+    constexpr size_t smem = BwdCfg<DIN, DOUT, EPI>::bytes;
     static bool configured = false;
     if (!configured) {
-        KGAT_CUDA(cudaFuncSetAttribute(layer_bwd_kernel<DIN, DOUT, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        KGAT_CUDA(cudaFuncSetAttribute(layer_bwd_kernel<DIN, DOUT, PUSH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         configured = true;
     }
     const int rows = a.row_end - a.row_begin;
     const int n_tiles = (rows + TM - 1) / TM;
     const int grid = n_tiles < bwd_max_ctas() ? n_tiles : bwd_max_ctas();
-    layer_bwd_kernel<DIN, DOUT, PUSH><<<grid, THREADS, smem, a.st>>>(
+    layer_bwd_kernel<DIN, DOUT, PUSH, EPI><<<grid, THREADS, smem, a.st>>>(
         a.g->csc_ptr, a.g->csc_dst, a.w_csc, a.row_begin, a.row_end, n_tiles, a.d_concat, a.dc_slot, a.cstride,
         a.out_off,
         a.nxt_dx_direct, a.nxt_dh_nb, a.h_in, a.h_nb, a.act, a.h_out, a.drop_mask, a.W2, a.slope, a.dx_direct,
@@ -647,7 +754,11 @@ int launch_bwd_t(const BwdArgs& a) {
 
 template <int DIN, int DOUT>
 int launch_bwd(const BwdArgs& a) {
-    return a.push ? launch_bwd_t<DIN, DOUT, true>(a) : launch_bwd_t<DIN, DOUT, false>(a);
+    if constexpr (DIN >= 32 && DOUT >= 16) {
+        if (bwd_epilogue(DIN, DOUT, a.push) == 1)
+            return a.push ? launch_bwd_t<DIN, DOUT, true, 1>(a) : launch_bwd_t<DIN, DOUT, false, 1>(a);
+    }
+    return a.push ? launch_bwd_t<DIN, DOUT, true, 0>(a) : launch_bwd_t<DIN, DOUT, false, 0>(a);
 }
 
 #define KGAT_DIM_PAIRS(X) \
