@@ -32,6 +32,41 @@ def test_library_exports_every_declared_symbol():
     assert loaded.kgat_error_string(-2).decode().startswith("unsupported")
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every binding in _lib.SIGNATURES has as many arguments as the C prototype, pointers bound as
+    pointers and integers / floats with the width the header declares (a mismatch would corrupt the call
+    silently)."""
+    text = open(os.path.join(ROOT, "include", "kgat_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = dict(re.findall(r"KGAT_API\s+[\w\s\*]+?\b(kgat_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S))
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    scalar = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
+              "float": ctypes.c_float, "double": ctypes.c_double, "uint64_t": ctypes.c_uint64}
+    for name, params in protos.items():
+        args = [a.strip() for a in params.split(",")] if params.strip() not in ("", "void") else []
+        bound = _lib.SIGNATURES[name][1]
+        assert len(args) == len(bound), "%s: header has %d parameters, binding %d" % (name, len(args), len(bound))
+        for a, b in zip(args, bound):
+            is_ptr = "*" in a or a.startswith("kgat_stream_t")
+            if is_ptr:
+                assert b is ctypes.c_void_p or issubclass(b, ctypes._Pointer), (name, a, b)
+            else:
+                ctype = a.replace("const", "").split()[0]
+                assert ctypes.sizeof(b) == ctypes.sizeof(scalar[ctype]), (name, a, b)
+                assert (b in (ctypes.c_float, ctypes.c_double)) == (ctype in ("float", "double")), (name, a, b)
+
+
+def test_peer_group_struct_layout_matches_header():
+    text = open(os.path.join(ROOT, "include", "kgat_b200.h")).read()
+    assert "#define KGAT_MAX_RANKS %d" % _lib.MAX_RANKS in text
+    assert "#define KGAT_PEER_HEADER_BYTES %d" % _lib.PEER_HEADER_BYTES in text
+    assert "#define KGAT_IPC_HANDLE_BYTES %d" % _lib.IPC_HANDLE_BYTES in text
+    body = text[text.index("typedef struct kgat_peer_group {"): text.index("} kgat_peer_group_t;")]
+    assert [f for f in re.findall(r"(\w+)(?:\[\w+\])?;", body)] == ["rank", "arena_bytes", "arena"]
+    assert [n for n, _ in _lib.KgatPeerGroup._fields_] == ["world", "rank", "arena_bytes", "arena"]
+    assert ctypes.sizeof(_lib.KgatPeerGroup) == 4 + 4 + 8 + 8 * _lib.MAX_RANKS
+
+
 def test_graph_struct_layout_matches_header():
     text = open(os.path.join(ROOT, "include", "kgat_b200.h")).read()
     body = text[text.index("typedef struct kgat_graph {"): text.index("} kgat_graph_t;")]
