@@ -414,6 +414,11 @@ def run_ours(args):
                     # whole job: the step's algorithmic bytes over the step time, against world x the peak
                     "step_frac": (step_bytes(N, E, R) / (ms_step * 1e-3) / 1e9) / (peak * world),
                     "step_alg_GB": step_bytes(N, E, R) / 1e9}
+        # fractions against the nominal 8 TB/s north_star quotes as well, and the
+        # compulsory-traffic C-model (perfect reuse) next to the E-model
+        roofline["frac_of_nominal_8TBps"] = ach / 8000.0
+        roofline["step_frac_of_nominal_8TBps"] = roofline["step_frac"] * peak / 8000.0
+        roofline["step_c_model_GB"] = (E * (12 + 6 * 8) + N * (256 + 2 * 2 * 640)) / 1e9
         if distributed:
             roofline["scope"] = "rank 0 (%d of %d rows, %d of %d in-edges); step_frac is whole-job" % (n_loc, N, e_loc, E)
 
