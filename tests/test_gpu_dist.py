@@ -23,6 +23,10 @@ def _free_port():
 def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    # The partitioned (PUSH) backward kernels still use the fp32 FFMA tile GEMMs while the single-GPU path
+    # defaults to the tensor-core ones; this test is about the exchange, so both sides are pinned to the same
+    # arithmetic (the tensor-core GEMMs are held against the fp64 oracle in test_gpu_parity.py).
+    os.environ["KGAT_BWD_EPILOGUE"] = "ffma"
     th.cuda.set_device(rank)
     dev = th.device("cuda", rank)
     tdist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)

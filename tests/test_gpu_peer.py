@@ -45,6 +45,10 @@ def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["KGAT_PEER_TIMEOUT_MS"] = "15000"
+    # The partitioned (PUSH) backward kernels still use the fp32 FFMA tile GEMMs while the single-GPU path
+    # defaults to the tensor-core ones; this test is about the exchange, so both sides are pinned to the same
+    # arithmetic (the tensor-core GEMMs are held against the fp64 oracle in test_gpu_parity.py).
+    os.environ["KGAT_BWD_EPILOGUE"] = "ffma"
     th.cuda.set_device(0)                       # every rank on the same GPU
     dev = th.device("cuda", 0)
     tdist.init_process_group("gloo", rank=rank, world_size=world)
