@@ -264,3 +264,58 @@ def test_synth_shapes():
     assert (c.n_nodes, c.n_edges, c.n_relations) == (136880, 3492324, 44)
     c = synth.CONFIGS["amazon-book-10x"]
     assert (c.n_nodes, c.n_edges, c.n_relations) == (1706790, 36633020, 41)
+
+
+@pytest.mark.parametrize("d_in,d_out", [(64, 64), (64, 32), (32, 16), (128, 64), (32, 32)])
+def test_tensor_core_tile_decomposition_of_the_layer_gemms(d_in, d_out):
+    """Index arithmetic of the mma.sync m16n8k8 tile GEMMs in csrc/propagate.cu, restated with the PTX
+    fragment layout (lane = 4 g + t: A holds (g, t), (g+8, t), (g, t+4), (g+8, t+4); B holds (k=t, n=g),
+    (k=t+4, n=g); C holds (g, 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)): every warp / tile / k-step
+    assignment of the forward product z W2^T and of the two backward products dpre^T z and dpre W2 must
+    cover each output element exactly once and sum over the right operands."""
+    rng = np.random.default_rng(0)
+    z, dp = rng.standard_normal((32, d_in)), rng.standard_normal((32, d_out))
+    w2 = rng.standard_normal((d_out, d_in))
+    lanes = [(l >> 2, l & 3) for l in range(32)]
+
+    def mma_tile(a_elem, b_elem, ksteps):
+        acc = np.zeros((16, 8))
+        for ks in range(ksteps):
+            a, b = np.zeros((16, 8)), np.zeros((8, 8))
+            for g, t in lanes:
+                a[g, t], a[g + 8, t], a[g, t + 4], a[g + 8, t + 4] = (a_elem(g, 8 * ks + t), a_elem(g + 8, 8 * ks + t),
+                                                                      a_elem(g, 8 * ks + t + 4), a_elem(g + 8, 8 * ks + t + 4))
+                b[t, g], b[t + 4, g] = b_elem(8 * ks + t, g), b_elem(8 * ks + t + 4, g)
+            acc += a @ b
+        return acc
+
+    def scatter(out, acc, r0, c0):
+        for g, t in lanes:
+            for dr, dc, v in ((0, 0, acc[g, 2 * t]), (0, 1, acc[g, 2 * t + 1]), (8, 0, acc[g + 8, 2 * t]),
+                              (8, 1, acc[g + 8, 2 * t + 1])):
+                assert np.isnan(out[r0 + g + dr, c0 + 2 * t + dc]), "element written twice"
+                out[r0 + g + dr, c0 + 2 * t + dc] = v
+
+    # forward: pre (32 x d_out) = z W2^T; pairs p = warp + 8 q -> (mt, nt) = (p / NT, p % NT)
+    nt_fwd = d_out // 8
+    pre = np.full((32, d_out), np.nan)
+    for p in range(2 * nt_fwd):
+        mt, nt = divmod(p, nt_fwd)
+        acc = mma_tile(lambda m, k: z[16 * mt + m, k], lambda k, n: w2[8 * nt + n, k], d_in // 8)
+        scatter(pre, acc, 16 * mt, 8 * nt)
+    assert np.allclose(pre, z @ w2.T)
+    # backward: dW2 (d_out x d_in) += dpre^T z over the 32 rows; dz (32 x d_in) = dpre W2
+    ntn = d_in // 8
+    dw = np.full((d_out, d_in), np.nan)
+    for p in range((d_out // 16) * ntn):
+        mt, nt = divmod(p, ntn)
+        acc = mma_tile(lambda m, k: dp[k, 16 * mt + m], lambda k, n: z[k, 8 * nt + n], 4)
+        scatter(dw, acc, 16 * mt, 8 * nt)
+    assert np.allclose(dw, dp.T @ z)
+    dz = np.full((32, d_in), np.nan)
+    for p in range(2 * ntn):
+        mt, nt = divmod(p, ntn)
+        acc = mma_tile(lambda m, k: dp[16 * mt + m, k], lambda k, n: w2[k, 8 * nt + n], d_out // 8)
+        scatter(dz, acc, 16 * mt, 8 * nt)
+    assert np.allclose(dz, dp @ w2)
+
