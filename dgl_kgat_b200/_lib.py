@@ -48,6 +48,7 @@ SIGNATURES = {
     "kgat_graph_build_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
     "kgat_graph_build": (C.c_int, [_GP, c_i32p, c_i32p, c_i32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kgat_attention_logits": (C.c_int, [_GP, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, C.c_void_p]),
+    "kgat_attention_fallbacks": (C.c_int, []),
     "kgat_segment_softmax": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "kgat_edge_weights_from_eid": (C.c_int, [_GP, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "kgat_layer_fwd": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int,

@@ -256,9 +256,11 @@ using namespace kgat;
 #include <cstring>
 
 int kgat_launch_att_logits_umma(const kgat_graph_t* g, const float* entity, const float* rel_emb, const float* W_R,
-                                float* logits_csr, cudaStream_t st);
+                                float* logits_csr, int* only_if, cudaStream_t st);
 int kgat_launch_att_logits_umma16(const kgat_graph_t* g, const float* entity, const float* rel_emb,
-                                  const float* W_R, float* logits_csr, cudaStream_t st);
+                                  const float* W_R, float* logits_csr, int* fallback, cudaStream_t st);
+int kgat_launch_att_range(const float* W_R, int64_t n, int* word, cudaStream_t st);
+int* kgat_att_fallback_word();
 
 // KGAT_ATT_IMPL selects the kernel for d = rd = 64 (A/B runs): "f16" (default) tcgen05 split-fp16,
 // "tf32" tcgen05 3xTF32, "ffma" fp32 FFMA tiles.
@@ -280,16 +282,26 @@ extern "C" int kgat_attention_logits(const kgat_graph_t* g, const float* entity,
     const int64_t E = g->n_edges;
     const int impl = att_impl();
     if (d == 64 && rd == 64 && g->n_rel <= 1024 && impl == 2) {
-        return kgat_launch_att_logits_umma16(g, entity, rel_emb, W_R, logits_csr, st);
+        // The split-fp16 kernel is exact to ~3e-7 only for |W_r| < 32 and |entity| < 65504; the reference
+        // computes in fp32 (models.py:140-143).  Three launches, no host round trip (capture-safe): the range
+        // kernel decides from W_R, the fp16 kernel runs unless told not to and reports non-finite logits, the
+        // 3xTF32 kernel (fp32 range) recomputes everything iff the word is set - an empty launch otherwise.
+        int* word = kgat_att_fallback_word();
+        if (!word) return KGAT_ERR_CUDA;
+        int rc = kgat_launch_att_range(W_R, g->n_rel * static_cast<int64_t>(d) * rd, word, st);
+        if (rc != KGAT_OK) return rc;
+        rc = kgat_launch_att_logits_umma16(g, entity, rel_emb, W_R, logits_csr, word, st);
+        if (rc != KGAT_OK) return rc;
+        return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, word, st);
     } else if (d == 64 && rd == 64 && g->n_rel <= 1024 && impl == 1) {
-        return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, st);
+        return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, nullptr, st);
     } else if (d == 64 && rd == 64) {
         using S = AttSmem<64, 64>;
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce configured;
+        if (configured.need()) {
             KGAT_CUDA(cudaFuncSetAttribute(att_logits_tile_kernel<64, 64>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
-            configured = true;
+            configured.set();
         }
         // tiles = sum_r ceil(E_r / TILE) <= E / TILE + R; surplus blocks exit immediately
         const int64_t grid = E / ATT_TILE + g->n_rel;

@@ -78,10 +78,18 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
                        const int32_t* __restrict__ bk_tail, const int32_t* __restrict__ bk_pos,
                        const float* __restrict__ ent, const float* __restrict__ rel_emb,
                        const float* __restrict__ W_R, float* __restrict__ logits_csr,
-                       int* __restrict__ err) {
+                       int* __restrict__ err, int* __restrict__ only_if) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // Launched behind the split-fp16 kernel as its fp32-range fallback: only_if[0] != 0 means that kernel
+    // declined (|W_r| >= 32) or produced a non-finite logit (an operand left the fp16 range); otherwise
+    // there is nothing to do.  The word is final here (stream order), so the exit is grid-uniform.
+    if (only_if) {
+        if (*reinterpret_cast<volatile int*>(only_if) == 0) return;
+        if (blockIdx.x == 0 && tid == 0) atomicAdd(only_if + 1, 1);     // fallbacks taken (kgat_attention_fallbacks)
+    }
 
     // ---- one-time setup: tile prefix per relation, TMEM, barriers -------------------------------
     if (warp == 0) {
@@ -312,6 +320,24 @@ att_logits_umma_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const int
 }  // namespace
 
 __device__ int g_umma_error = 0;      // set when a tensor-core completion barrier timed out
+// [0] = "the split-fp16 attention kernel cannot serve this call" (rewritten by every call), [1] = number of
+// calls that therefore ran the fp32-range 3xTF32 kernel since the last kgat_attention_fallbacks()
+__device__ int g_att_fallback[2] = {0, 0};
+
+namespace {
+// one CTA: word[0] = any |W_r| >= 32 (2^11 w_hi would overflow fp16, attention_umma16.cu)
+__global__ void __launch_bounds__(1024) att_range_kernel(const float* __restrict__ W, int64_t n, int* __restrict__ word) {
+    int bad = 0;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(W) + i);
+        bad |= !(fabsf(v.x) < 32.0f) | !(fabsf(v.y) < 32.0f) | !(fabsf(v.z) < 32.0f) | !(fabsf(v.w) < 32.0f);
+    }
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) bad |= !(fabsf(__ldg(W + i)) < 32.0f);
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) word[0] = bad ? 1 : 0;
+}
+}  // namespace
 
 }  // namespace kgat
 
@@ -321,9 +347,31 @@ int kgat_eval_umma_error_take();
 
 // device address of the shared tensor-core error word (attention_umma16.cu reports through it too)
 int* kgat_umma_error_word() {
-    int* p = nullptr;
-    if (cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_umma_error) != cudaSuccess) return nullptr;
+    static PerDevice<int*> cache;
+    int*& p = cache.get();
+    if (!p && cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_umma_error) != cudaSuccess) return nullptr;
     return p;
+}
+
+int* kgat_att_fallback_word() {
+    static PerDevice<int*> cache;
+    int*& p = cache.get();
+    if (!p && cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_att_fallback) != cudaSuccess) return nullptr;
+    return p;
+}
+
+int kgat_launch_att_range(const float* W_R, int64_t n, int* word, cudaStream_t st) {
+    att_range_kernel<<<1, 1024, 0, st>>>(W_R, n, word);
+    KGAT_LAUNCH_CHECK();
+    return KGAT_OK;
+}
+
+extern "C" int kgat_attention_fallbacks(void) {
+    int v[2] = {0, 0}, zero = 0;
+    if (cudaMemcpyFromSymbol(v, g_att_fallback, sizeof(v)) != cudaSuccess) return KGAT_ERR_CUDA;
+    if (v[1] != 0 && cudaMemcpyToSymbol(g_att_fallback, &zero, sizeof(int), sizeof(int)) != cudaSuccess)
+        return KGAT_ERR_CUDA;
+    return v[1];
 }
 
 extern "C" int kgat_umma_error_flag(void) {
@@ -337,25 +385,26 @@ extern "C" int kgat_umma_error_flag(void) {
 
 // Launcher used by kgat_attention_logits for d = rd = 64 (declared in attention.cu).
 int kgat_launch_att_logits_umma(const kgat_graph_t* g, const float* entity, const float* rel_emb, const float* W_R,
-                                float* logits_csr, cudaStream_t st) {
-    static int* err_flag = nullptr;
-    static bool configured = false;
+                                float* logits_csr, int* only_if, cudaStream_t st) {
+    static PerDevice<int*> err_flags;
+    static PerDeviceOnce configured;
     static int epi_w = 32;
-    if (!configured) {
-        KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&err_flag), g_umma_error));
+    if (configured.need()) {
+        KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&err_flags.get()), g_umma_error));
         KGAT_CUDA(cudaFuncSetAttribute(att_logits_umma_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
         KGAT_CUDA(cudaFuncSetAttribute(att_logits_umma_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
         const char* e = std::getenv("KGAT_ATT_EPI");
         if (e && std::atoi(e) == 16) epi_w = 16;
-        configured = true;
+        configured.set();
     }
     const int64_t max_tiles = g->n_edges / TILE + g->n_rel;
     const int grid = static_cast<int>(max_tiles < num_sms() ? max_tiles : num_sms());
+    int* err_flag = err_flags.get();
     auto kern = epi_w == 16 ? att_logits_umma_kernel<16, 1> : att_logits_umma_kernel<32, 0>;
     kern<<<grid, THREADS, sizeof(Smem), st>>>(g->rel_ptr, static_cast<int>(g->n_rel), g->bk_head, g->bk_tail,
-                                              g->bk_pos, entity, rel_emb, W_R, logits_csr, err_flag);
+                                              g->bk_pos, entity, rel_emb, W_R, logits_csr, err_flag, only_if);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }

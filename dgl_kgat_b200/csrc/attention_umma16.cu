@@ -10,9 +10,11 @@
 // The 2^11 scale keeps lo' a NORMAL fp16 number whenever hi is (fp16 has 5 exponent bits), so the
 // pair carries ~2^-23 relative error for 6e-5 <= |x| < 65504 and <= 1.5e-11 absolute below that; all
 // three products carry the same 2^11 factor, so they accumulate into ONE fp32 TMEM accumulator and
-// the epilogue multiplies by 2^-11.  Range limits of this kernel (outside them the result is inf/NaN
-// and the tensor-core error word is set for W): |entity| < 65504, |W_r| < 32 (2^11 w_hi must stay
-// finite in fp16); KGAT_ATT_IMPL=tf32 / ffma have fp32 range.
+// the epilogue multiplies by 2^-11.  Range limits of this kernel: |entity| < 65504, |W_r| < 32 (2^11 w_hi
+// must stay finite in fp16).  They are enforced on the device without a host round trip (attention.cu):
+// att_range_kernel raises fallback[0] when some |W_r| >= 32 and this kernel then does nothing; an entity
+// value outside the range yields a non-finite logit, which the epilogue reports through the same word; the
+// 3xTF32 kernel (fp32 range) launched right behind recomputes every logit when the word is set.
 // Why fp16 and not TF32: a kind::f16 MMA moves half the operand bytes per multiply-add (the TF32
 // kernel stores 128 KB and the tensor core fetches 224 KB of shared memory per tile, at 128 B/clk),
 // a stage is 32 KB so six stages (three tiles) are in flight, and a single accumulator halves the
@@ -144,10 +146,17 @@ att_logits_umma16_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const i
                          const int32_t* __restrict__ bk_tail, const int32_t* __restrict__ bk_pos,
                          const float* __restrict__ ent, const float* __restrict__ rel_emb,
                          const float* __restrict__ W_R, float* __restrict__ logits_csr,
-                         int* __restrict__ err) {
+                         int* __restrict__ err, int* __restrict__ fallback) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // Range protocol (attention.cu): fallback[0] was set by att_range_kernel when some |W_r| >= 32; a CTA
+    // that sees it does nothing - the fp32-range kernel launched behind this one recomputes every logit.
+    // One thread reads the word so the decision is CTA-uniform even if another CTA raises it meanwhile.
+    if (tid == 0) s.epi_abort = *reinterpret_cast<volatile int*>(fallback);
+    __syncthreads();
+    if (s.epi_abort) return;
 
     // ---- one-time setup: tile prefix per relation, rel_ptr copy, TMEM, barriers -----------------
     if (warp == 0) {
@@ -251,7 +260,6 @@ att_logits_umma16_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const i
                     for (int idx = tid; idx < D * D; idx += N_GRP) {
                         const int k = idx >> 6, n = idx & 63;
                         const float w = __ldg(Wg + idx);
-                        if (!(fabsf(w) < 32.0f)) atomicExch(err, 2);  // 2^11 w would leave the fp16 range
                         const __half hi = __float2half_rn(w);
                         const float hf = __half2float(hi);
                         const int p = kpos(k);
@@ -416,10 +424,18 @@ att_logits_umma16_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const i
                     asm volatile("bar.arrive 2, %0;" ::"n"(N_EPI) : "memory");
                 } else {
                     asm volatile("bar.sync 2, %0;" ::"n"(N_EPI) : "memory");
-                    if (pos >= 0) logits_csr[pos] = p + s.part[eb][row];
+                    if (pos >= 0) {
+                        const float v = p + s.part[eb][row];
+                        logits_csr[pos] = v;
+                        if (!(fabsf(v) < INFINITY)) *reinterpret_cast<volatile int*>(fallback) = 1;
+                    }
                 }
             } else {
-                if (pos >= 0) logits_csr[pos] = p;
+                if (pos >= 0) {
+                    logits_csr[pos] = p;
+                    // an entity value outside the fp16 range turns into inf/NaN here: ask for the fp32-range kernel
+                    if (!(fabsf(p) < INFINITY)) *reinterpret_cast<volatile int*>(fallback) = 1;
+                }
             }
         }
 #ifdef KGAT_ATT_PROFILE
@@ -452,21 +468,20 @@ int* kgat_umma_error_word();      // attention_umma.cu
 
 // Launcher used by kgat_attention_logits for d = rd = 64 (declared in attention.cu).
 int kgat_launch_att_logits_umma16(const kgat_graph_t* g, const float* entity, const float* rel_emb,
-                                  const float* W_R, float* logits_csr, cudaStream_t st) {
-    static bool configured = false;
-    static int* err_flag = nullptr;
-    if (!configured) {
-        err_flag = kgat_umma_error_word();
-        if (!err_flag) return KGAT_ERR_CUDA;
+                                  const float* W_R, float* logits_csr, int* fallback, cudaStream_t st) {
+    static PerDeviceOnce configured;
+    int* err_flag = kgat_umma_error_word();
+    if (!err_flag) return KGAT_ERR_CUDA;
+    if (configured.need()) {
         KGAT_CUDA(cudaFuncSetAttribute(att_logits_umma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
-        configured = true;
+        configured.set();
     }
     const int64_t max_tiles = g->n_edges / TILE + g->n_rel;
     const int grid = static_cast<int>(max_tiles < num_sms() ? max_tiles : num_sms());
     att_logits_umma16_kernel<<<grid, THREADS, sizeof(Smem), st>>>(
         g->rel_ptr, static_cast<int>(g->n_rel), g->bk_head, g->bk_tail, g->bk_pos, entity, rel_emb, W_R, logits_csr,
-        err_flag);
+        err_flag, fallback);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }

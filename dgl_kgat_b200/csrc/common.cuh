@@ -35,16 +35,38 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 inline cudaStream_t as_stream(kgat_stream_t s) { return static_cast<cudaStream_t>(s); }
 
-inline int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
-    return n;
+constexpr int MAX_DEVICES = 64;
+
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev % MAX_DEVICES;
 }
+
+inline int num_sms() {
+    static int n[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0)
+            n[dev] = 148;
+    }
+    return n[dev];
+}
+
+// Function attributes (the opt-in to more than 48 KB of dynamic shared memory) and device-symbol
+// addresses are PER DEVICE: a launcher remembers which devices of the process it has prepared.
+//     static PerDeviceOnce once;  if (once.need()) { cudaFuncSetAttribute(...); once.set(); }
+struct PerDeviceOnce {
+    bool done[MAX_DEVICES] = {};
+    int cur = 0;
+    bool need() { cur = current_device(); return !done[cur]; }
+    void set() { done[cur] = true; }
+};
+template <typename T>
+struct PerDevice {
+    T v[MAX_DEVICES] = {};
+    T& get() { return v[current_device()]; }
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

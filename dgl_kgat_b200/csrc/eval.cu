@@ -165,10 +165,10 @@ extern "C" int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
                                            static_cast<int>(n_items), mask_ptr, mask_items, K, topk_idx, topk_score,
                                            as_stream(stream));
     const size_t smem = sizeof(float) * (2 * BK * LDT + BM * (BN + 1)) + (sizeof(float) + sizeof(int)) * BM * K + 16;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static PerDevice<size_t> configured;
+    if (smem > configured.get()) {
         KGAT_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured.get() = smem;
     }
     const unsigned grid = static_cast<unsigned>((n_users + BM - 1) / BM);
     score_topk_kernel<<<grid, EV_THREADS, smem, as_stream(stream)>>>(

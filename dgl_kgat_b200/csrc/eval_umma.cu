@@ -312,12 +312,12 @@ int kgat_launch_score_topk_umma(const float* emb, int64_t emb_stride, int dim, c
                                 const int32_t* mask_items, int K, int32_t* topk_idx, float* topk_score,
                                 cudaStream_t st) {
     static int* err_flag = nullptr;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&err_flag), g_eval_umma_error));
         KGAT_CUDA(cudaFuncSetAttribute(score_topk_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
-        configured = true;
+        configured.set();
     }
     const unsigned grid = static_cast<unsigned>((n_users + TM - 1) / TM);
     score_topk_umma_kernel<<<grid, THREADS, sizeof(Smem), st>>>(emb, emb_stride, dim, user_ids, n_users, item_ids,

@@ -684,11 +684,11 @@ inline int fwd_epilogue(int d_in) {
 template <int DIN, int DOUT, bool PUSH, int EPI>
 int launch_fwd_t(const FwdArgs& a) {
     constexpr size_t smem = FwdSmem<DIN, DOUT, EPI>::bytes;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         KGAT_CUDA(cudaFuncSetAttribute(layer_fwd_kernel<DIN, DOUT, PUSH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-        configured = true;
+        configured.set();
     }
     const int rows = a.row_end - a.row_begin;
     const unsigned grid = (rows + TM - 1) / TM;
@@ -731,11 +731,11 @@ inline int bwd_epilogue(int d_in, int d_out, bool push) {
 template <int DIN, int DOUT, bool PUSH, int EPI>
 int launch_bwd_t(const BwdArgs& a) {
     constexpr size_t smem = BwdCfg<DIN, DOUT, EPI>::bytes;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         KGAT_CUDA(cudaFuncSetAttribute(layer_bwd_kernel<DIN, DOUT, PUSH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-        configured = true;
+        configured.set();
     }
     const int rows = a.row_end - a.row_begin;
     const int n_tiles = (rows + TM - 1) / TM;

@@ -526,8 +526,8 @@ extern "C" int kgat_transr_fwd(const float* entity, int64_t n_nodes, const float
     const size_t cnt_bytes = sizeof(int) * PLAN_WARPS * static_cast<size_t>(R);
     const size_t plan_smem = key_bytes > cnt_bytes ? key_bytes : cnt_bytes;
 
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         const int plan_max = MAX_ROWS * (int)sizeof(unsigned long long);
         KGAT_CUDA(cudaFuncSetAttribute(transr_plan_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        plan_max));
@@ -535,7 +535,7 @@ extern "C" int kgat_transr_fwd(const float* entity, int64_t n_nodes, const float
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, plan_max));
         KGAT_CUDA(cudaFuncSetAttribute(transr_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(MainSmem)));
-        configured = true;
+        configured.set();
     }
     if (narrow)
         transr_plan_kernel<uint32_t><<<1, PLAN_THREADS, plan_smem, st>>>(

@@ -99,11 +99,18 @@ KGAT_API int    kgat_graph_build(const kgat_graph_t* g, const int32_t* head, con
  *     edge, relation-grouped -- replaces the loop of apply_edges(_att_score)
  *     (models.py:135-152).  entity [n_nodes,d], rel_emb [n_rel,rd], W_R [n_rel,d,rd].
  *     logits_csr[c] is the logit of the edge at CSR position c.
- *     d = rd = 64 runs on the tensor cores (tcgen05, 3xTF32, fp32 accumulate in TMEM); other widths use
- *     fp32 FFMA kernels.  Environment: KGAT_ATT_IMPL=ffma forces the FFMA kernel (A/B measurements). */
+ *     d = rd = 64 runs on the tensor cores (tcgen05 split-fp16, fp32 accumulate in TMEM); other widths use
+ *     fp32 FFMA kernels.  The reference computes in fp32 (models.py:140-143); the split-fp16 kernel is only
+ *     valid for |W_R| < 32 and |entity| < 65504, so the call checks the range ON THE DEVICE (no host round
+ *     trip, CUDA-graph capturable) and re-runs the logits with the fp32-range 3xTF32 kernel when an operand
+ *     is outside it; kgat_attention_fallbacks() reports how often that happened.
+ *     Environment: KGAT_ATT_IMPL=tf32 / ffma force those kernels (A/B measurements). */
 KGAT_API int kgat_attention_logits(const kgat_graph_t* g, const float* entity, const float* rel_emb,
                           const float* W_R, int d, int rd, float* logits_csr,
                           kgat_stream_t stream);
+/* number of kgat_attention_logits calls on the current device that took the fp32-range fallback since the
+ * last call of this function (then cleared).  Synchronises the device. */
+KGAT_API int kgat_attention_fallbacks(void);
 
 /* (3a) softmax over the in-edges of every destination row -- replaces
  *      edge_softmax (models.py:153).  Rows [row_begin,row_end).  Writes the weights

@@ -123,6 +123,40 @@ def test_attention_logits_precision_by_magnitude(dev, scale):
     assert max(out.values()) < 1e-5, out
 
 
+@pytest.mark.parametrize("case", ["W_R_40", "entity_7e4", "in_range"])
+def test_attention_operand_range_guard(dev, case):
+    """The reference computes the logits in fp32 (models.py:140-143); the default split-fp16 kernel is only
+    valid for |W_R| < 32 and |entity| < 65504.  Outside that range the PRODUCT path (Model.compute_attention,
+    no environment override) must not return inf/NaN weights: the library detects it on the device and
+    re-runs the logits with the fp32-range tensor-core kernel, and says so through
+    kgat_attention_fallbacks()."""
+    lib = _lib.load()
+    ck = synth_ckg("tiny")
+    N, R, trip = ck.cfg.n_nodes, ck.cfg.n_relations, ck.triplets
+    th.manual_seed(11)
+    m = models.Model(True, 64, "kgat", 3, 64, 0.0, n_entities=N, n_relations=R, relation_dim=64).to(dev)
+    with th.no_grad():
+        if case == "W_R_40":
+            m.W_R[3].mul_(40.0 / float(m.W_R[3].abs().max()))          # one relation with max |w| = 40
+            m.entity_embed.weight.mul_(0.005)                            # keep the logits moderate
+        elif case == "entity_7e4":
+            m.entity_embed.weight[17, 5] = 7.0e4                         # one value above the fp16 range (65504)
+            m.W_R.mul_(1e-4)
+    assert lib.kgat_attention_fallbacks() >= 0                           # clears the counter
+    g = CKGraph(N, trip, n_rel=R)
+    w = m.compute_attention(g)
+    th.cuda.synchronize()
+    taken = lib.kgat_attention_fallbacks()
+    assert bool(th.isfinite(w).all()), "out-of-range operands produced non-finite attention weights"
+    w64 = kgat_ref.compute_attention({k: v.detach().cpu().double() for k, v in m.state_dict().items()}, trip, N).numpy()
+    got = w.cpu().numpy().astype(np.float64)
+    # weights below 1e-30 are denormal noise in fp32 either way: compare where the oracle weight is representable
+    sel = w64 > 1e-30
+    assert float((np.abs(got - w64)[sel] / w64[sel]).max()) < 1e-5
+    assert taken == (0 if case == "in_range" else 1), (case, taken)
+    assert lib.kgat_umma_error_flag() == 0
+
+
 @pytest.mark.parametrize("impl", ["tf32", "f16"])
 def test_attention_umma_ragged_tiles(dev, impl, monkeypatch):
     """Relation buckets that are empty, smaller than a tile, or one edge over a tile boundary."""
