@@ -131,6 +131,68 @@ class DeviceEdgeBatchSampler:
                 yield (s[b:e], d[b:e], None if r is None else r[b:e], ns[b:e], nd[b:e], false_neg[b:e])
 
 
+class UniqueGroupSampler:
+    """The reference's pure-Python fallback samplers (dataset.py:246-266 ``pos_mode="unique",
+    neg_mode="tail"`` and :294-310 ``pos_mode="unique", neg_mode="exclude_pos"``) as array code on one
+    torch device (CPU or CUDA): a batch holds ``batch_size`` DISTINCT group keys (heads / users; drawn with
+    replacement only when there are fewer groups than the batch, like ``rd.sample`` vs ``rd.choice`` there),
+    one uniformly chosen member ``(rel, value)`` of each group as the positive, and a negative value drawn
+    uniformly from ``[0, n_neg)`` and RE-DRAWN until ``(group, rel, negative)`` is not a member of the group
+    (the ``while True`` loops at dataset.py:260-262 and :303-305) - so, unlike the edge samplers, a batch
+    never contains a false negative and ``false_neg`` is None."""
+
+    def __init__(self, group, rel, value, n_neg, batch_size, n_batch, device=None, generator=None):
+        import torch as th
+        self.th = th
+        self.device = th.device("cpu") if device is None else th.device(device)
+        group = np.asarray(group, np.int64)
+        value = np.asarray(value, np.int64)
+        rel = np.zeros_like(group) if rel is None else np.asarray(rel, np.int64)
+        order = np.argsort(group, kind="stable")               # members keep their input order inside a group
+        g_sorted = group[order]
+        keys, start = np.unique(g_sorted, return_index=True)
+        to = lambda a: th.as_tensor(np.ascontiguousarray(a), dtype=th.long, device=self.device)
+        self.keys, self.ptr = to(keys), to(np.append(start, len(g_sorted)))
+        self.m_rel, self.m_val = to(rel[order]), to(value[order])
+        self.n_neg, self.batch_size, self.n_batch = int(n_neg), int(batch_size), int(n_batch)
+        self._n_rel = int(rel.max()) + 1 if len(rel) else 1
+        self._members = th.unique(self._key(to(g_sorted), self.m_rel, self.m_val))      # sorted
+        self.gen = generator
+
+    def _key(self, g, r, v):
+        return (g * self._n_rel + r) * self.n_neg + v
+
+    def _is_member(self, g, r, v):
+        th = self.th
+        inside = (v >= 0) & (v < self.n_neg)           # values outside the negative range cannot collide with a draw
+        q = self._key(g, r, v.clamp(0, self.n_neg - 1))
+        pos = th.searchsorted(self._members, q).clamp_(max=self._members.shape[0] - 1)
+        return inside & (self._members[pos] == q)
+
+    def __iter__(self):
+        th = self.th
+        G, B = self.keys.shape[0], self.batch_size
+        for _ in range(self.n_batch):
+            if B <= G:
+                gi = th.randperm(G, device=self.device, generator=self.gen)[:B]
+            else:
+                gi = th.randint(0, G, (B,), device=self.device, generator=self.gen)
+            lo, n = self.ptr[gi], self.ptr[gi + 1] - self.ptr[gi]
+            pick = lo + (th.rand(B, device=self.device, generator=self.gen) * n).long().minimum(n - 1)
+            g, r, v = self.keys[gi], self.m_rel[pick], self.m_val[pick]
+            neg = th.randint(0, self.n_neg, (B,), device=self.device, generator=self.gen)
+            bad = self._is_member(g, r, neg)
+            for _ in range(1000):                       # rejection: only the collided draws are repeated
+                idx = bad.nonzero().squeeze(1)
+                if idx.numel() == 0:
+                    break
+                neg[idx] = th.randint(0, self.n_neg, (idx.numel(),), device=self.device, generator=self.gen)
+                bad = self._is_member(g, r, neg)
+            else:
+                raise RuntimeError("negative sampling did not terminate: a group contains every candidate")
+            yield g, r, v, neg
+
+
 class DataLoader(object):
     def __init__(self, data_name, symmetric=True, as_continuous_ids=True, add_uv2KG=True, seed=1234,
                  data_dir=None, _frames=None):
@@ -245,6 +307,23 @@ class DataLoader(object):
                 cache[key] = DeviceEdgeBatchSampler(src, dst, etype, n_nodes, batch_size, mode, dev)
         return cache[key]
 
+    def _unique_sampler(self, name, group, rel, value, n_neg, batch_size, n):
+        """dataset.py:236-243 / :285-292: one batch of everything for batch_size < 0 or > n, else n // bs + 1."""
+        if batch_size < 0 or batch_size > n:
+            batch_size, n_batch = n, 1
+        else:
+            n_batch = n // batch_size + 1
+        cache = self.__dict__.setdefault("_samplers", {})
+        dev = self.__dict__.get("_sampler_device")
+        key = (name + "-unique", batch_size, str(dev))
+        if key not in cache:
+            import torch as th
+            gen = None
+            if dev is None:
+                gen = th.Generator().manual_seed(int(self._rng.integers(0, 2 ** 31 - 1)))
+            cache[key] = UniqueGroupSampler(group, rel, value, n_neg, batch_size, n_batch, dev, gen)
+        return cache[key]
+
     @staticmethod
     def _n_batch(batch_size, n):
         if batch_size < 0 or batch_size > n:
@@ -255,9 +334,17 @@ class DataLoader(object):
         """Yields ``(h, r, pos_t, neg_t, false_neg)`` batches (dataset.py:234-282).  As in the
         reference the names refer to the t->h graph: "h" is the edge SOURCE (= KG tail), "pos_t"
         the edge destination (= KG head), and the corrupted node is the destination."""
-        if not (pos_mode == "uniform" and neg_mode == "tail"):
-            raise NotImplementedError("only pos_mode='uniform', neg_mode='tail' (the mode kgat.py uses)")
         t = self.train_KG_triplet
+        if pos_mode == "unique" and neg_mode == "tail":
+            # dataset.py:246-266: distinct heads, one of the head's (r, t) pairs, a tail that is not one of
+            # the head's tails under that relation; n_batch as at dataset.py:236-243
+            sampler = self._unique_sampler("kg", t[:, 0], t[:, 1], t[:, 2], self.n_KG_entity, batch_size,
+                                           self.n_train_KG_triplet)
+            for h, r, pos_t, neg_t in sampler:
+                yield h, r, pos_t, neg_t, None
+            return
+        if not (pos_mode == "uniform" and neg_mode == "tail"):
+            raise NotImplementedError("KG_sampler modes: ('uniform', 'tail') and ('unique', 'tail'), as in the reference")
         sampler = self._sampler("kg", t[:, 2], t[:, 0], t[:, 1], self.n_KG_entity,
                                 self._n_batch(batch_size, self.n_train_KG_triplet), "tail")
         for s, d, r, _, nd, false_neg in sampler:
@@ -268,8 +355,19 @@ class DataLoader(object):
         """Yields ``(users, pos_items, neg_items, false_neg)`` batches over the symmetric
         user-item graph (dataset.py:283-325): users = edge destinations, pos_items = edge sources,
         neg_items = uniformly corrupted sources."""
+        if pos_mode == "unique" and neg_mode == "exclude_pos":
+            # dataset.py:294-310: distinct users, one of the user's train items, an item the user has not
+            # interacted with.  As in the reference the items are RAW ids in [0, n_items) - train_user_dict is
+            # built before the id offset (dataset.py:45-50) - so a caller adds n_users to index the embedding.
+            u = np.concatenate([np.full(len(v), k, np.int64) for k, v in self.train_user_dict.items()])
+            v = np.concatenate([np.asarray(v, np.int64) for v in self.train_user_dict.values()])
+            sampler = self._unique_sampler("cf", u, None, v, self.n_items, batch_size, self.n_train)
+            for users, _, pos_items, neg_items in sampler:
+                yield users, pos_items, neg_items, None
+            return
         if not (pos_mode == "uniform" and neg_mode == "random"):
-            raise NotImplementedError("only pos_mode='uniform', neg_mode='random' (the mode kgat.py uses)")
+            raise NotImplementedError("CF_pair_sampler modes: ('uniform', 'random') and ('unique', 'exclude_pos'), "
+                                      "as in the reference")
         t = self._train_uv_triplet
         sampler = self._sampler("cf", t[:, 2], t[:, 0], None, self.n_users + self.n_items,
                                 self._n_batch(batch_size, t.shape[0]), "head")

@@ -26,8 +26,16 @@ from . import _lib
 class GraphedCFStep:
     def __init__(self, model, g, batch_size, refresh_attention=True, warmup=3):
         self.model, self.g, self.refresh_attention = model, g, refresh_attention
-        if not refresh_attention and "w" not in g.edata:
-            raise KeyError("edata['w'] is not set and refresh_attention is False")
+        self._cap_w = self._seen_w = None
+        if not refresh_attention:
+            if "w" not in g.edata:
+                raise KeyError("edata['w'] is not set and refresh_attention is False")
+            # The capture bakes in the ADDRESSES of the CSR / CSC weight layouts that are current now.  The
+            # reference refreshes the attention once per epoch (kgat.py:139-145) and every refresh (and every
+            # eval) produces new weight tensors, so the graph owns these two buffers and __call__ copies the
+            # graph's current weights into them whenever they have changed since the last replay.
+            dev = model.entity_embed.weight.device
+            self._cap_w = self._seen_w = g.edge_weight_layouts(dev)
         self._capture(model, batch_size, warmup)
 
     def _capture(self, model, batch_size, warmup):
@@ -70,7 +78,21 @@ class GraphedCFStep:
         loss.backward()
         return loss
 
+    def _sync_weights(self):
+        """Bring the captured weight buffers up to date with ``g.edata['w']`` (two device copies, only after
+        a refresh): without this a graph captured in epoch 1 would train every later epoch on epoch-1
+        attention."""
+        if self._cap_w is None:
+            return
+        cur = self.g.edge_weight_layouts(self.device)
+        if cur[0] is not self._seen_w[0] or cur[1] is not self._seen_w[1]:
+            if cur[0] is not self._cap_w[0]:
+                self._cap_w[0].copy_(cur[0])
+                self._cap_w[1].copy_(cur[1])
+            self._seen_w = cur
+
     def __call__(self, src_ids, pos_ids, neg_ids):
+        self._sync_weights()
         for dst, src in zip(self.ids, (src_ids, pos_ids, neg_ids)):
             dst.copy_(th.as_tensor(src), non_blocking=True)
         self.graph.replay()
@@ -90,6 +112,7 @@ class GraphedDistCFStep(GraphedCFStep):
 
     def __init__(self, dk, batch_size, warmup=3):
         self.dk, self.model = dk, dk.model
+        self._cap_w = self._seen_w = None           # the partitioned step refreshes the attention inside the graph
         self._capture(dk.model, batch_size, warmup)
 
     def _body(self):

@@ -120,7 +120,14 @@ def train_eval(args):
     test_log = MetricLogger(['epoch', 'recall', 'ndcg'], ['%d', '%.5f', '%.5f'],
                             os.path.join(args.save_dir, 'test{:d}.csv'.format(args.save_id)))
     best_epoch, best_recall = -1, 0.0
-    test_recall = test_ndcg = float("nan")
+    test_recall = test_ndcg = float("nan")       # test metrics AT THE BEST validation epoch (kgat.py:179-198)
+    if args.resume:
+        best_epoch, best_recall = int(ckpt.get("best_epoch", -1)), float(ckpt.get("best_recall", 0.0))
+        test_recall, test_ndcg = float(ckpt.get("test_recall", test_recall)), float(ckpt.get("test_ndcg", test_ndcg))
+        if "torch_rng" in ckpt:
+            th.set_rng_state(ckpt["torch_rng"].cpu())
+        if "cuda_rng" in ckpt:
+            th.cuda.set_rng_state(ckpt["cuda_rng"].cpu(), dev)
 
     train_g, test_g = dataset.train_g, dataset.test_g
     for g in (train_g, test_g):                              # kgat.py:95-109
@@ -146,6 +153,10 @@ def train_eval(args):
             else:
                 loss = model.transR(as_ids(h), as_ids(r), as_ids(pos_t), as_ids(neg_t))
                 loss.backward()
+                # drop the eager autograd graph at once: while it lives, the parameters' AccumulateGrad nodes stay
+                # bound to this stream and torch refuses to capture a graphed step (the last, partial batch of an
+                # epoch is always eager, and the CF step is captured right after it in epoch 1)
+                loss = loss.detach()
             optimizer.step()
             optimizer.zero_grad()
             total.add_(loss.detach())               # summed on the device: no host sync per iteration
@@ -177,6 +188,7 @@ def train_eval(args):
                 embedding = model.gnn(train_g, train_g.ndata['id'])
                 loss = model.get_loss(embedding, as_ids(user_ids), as_ids(item_pos_ids), as_ids(item_neg_ids))
                 loss.backward()
+                loss, embedding = loss.detach(), None           # see the KG phase: no eager graph may outlive its step
             optimizer.step()
             optimizer.zero_grad()
             total.add_(loss.detach())               # summed on the device: no host sync per iteration
@@ -192,19 +204,26 @@ def train_eval(args):
             is_best = val_recall > best_recall
             valid_log.log(epoch=epoch, recall=val_recall, ndcg=val_ndcg, is_best=int(is_best))
             t0 = time()
-            test_recall, test_ndcg = eval(model, test_g, dataset.train_valid_user_dict, dataset.test_user_dict,
-                                          item_id_range, True, args.use_attention)
+            # the reference evaluates the test users in both branches (kgat.py:185,193) but keeps the numbers it
+            # reports at the end only when the validation recall improved (kgat.py:181-187)
+            cur_recall, cur_ndcg = eval(model, test_g, dataset.train_valid_user_dict, dataset.test_user_dict,
+                                        item_id_range, True, args.use_attention)
             if is_best:
                 best_recall, best_epoch = val_recall, epoch
+                test_recall, test_ndcg = cur_recall, cur_ndcg
                 test_log.log(epoch=epoch, recall=test_recall, ndcg=test_ndcg)
-            info += "\t[{:.1f}s] test recall:{:.5f}, test ndcg:{:.5f}".format(time() - t0, test_recall, test_ndcg)
+            info += "\t[{:.1f}s] test recall:{:.5f}, test ndcg:{:.5f}".format(time() - t0, cur_recall, cur_ndcg)
             logging.info(info)
         if args.save_every > 0 and epoch % args.save_every == 0:
             path = os.path.join(args.save_dir, 'ckpt{:d}.pt'.format(args.save_id))
-            th.save({'state_dict': model.state_dict(), 'optimizer': optimizer.state_dict(), 'epoch': epoch}, path)
+            th.save({'state_dict': model.state_dict(), 'optimizer': optimizer.state_dict(), 'epoch': epoch,
+                     'best_epoch': best_epoch, 'best_recall': best_recall, 'test_recall': test_recall,
+                     'test_ndcg': test_ndcg, 'torch_rng': th.get_rng_state(), 'cuda_rng': th.cuda.get_rng_state(dev)},
+                    path)
             logging.info("checkpoint written to %s", path)
 
     logging.info("Final test recall:{:.5f}, test ndcg:{:.5f}, best epoch:{}".format(test_recall, test_ndcg, best_epoch))
+    train_eval.last_model = model            # for callers (and tests) that want the trained parameters
     return test_recall, test_ndcg, best_epoch
 
 

@@ -208,6 +208,46 @@ def test_samplers_semantics():
     assert tot == 2 * dl.n_train
 
 
+@pytest.mark.parametrize("batch", [256, 5000])
+def test_unique_mode_samplers_exclusion_rule(batch):
+    """pos_mode="unique" branches of both samplers (reference dataset.py:246-266, :294-310): distinct group
+    keys per batch while there are enough groups, the positive is a member of its group, the negative never
+    is (the reference re-draws until it is not), no false_neg vector, n // batch + 1 batches."""
+    dl = dataset.DataLoader.from_synthetic("tiny")
+    trip = dl.train_KG_triplet
+    by_head = {}
+    for h, r, t in trip:
+        by_head.setdefault(int(h), set()).add((int(r), int(t)))
+    n = 0
+    for h, r, pos_t, neg_t, false_neg in dl.KG_sampler(batch, pos_mode="unique", neg_mode="tail"):
+        n += 1
+        h, r, pos_t, neg_t = (np.asarray(x) for x in (h, r, pos_t, neg_t))
+        assert false_neg is None and h.shape == (batch,)
+        if batch <= len(by_head):
+            assert len(set(h.tolist())) == batch                    # rd.sample: without replacement
+        if n <= 3:
+            for a, b, c, d in zip(h.tolist(), r.tolist(), pos_t.tolist(), neg_t.tolist()):
+                assert (b, c) in by_head[a] and (b, d) not in by_head[a] and 0 <= d < dl.n_KG_entity
+    assert n == dl.n_train_KG_triplet // batch + 1
+    n = 0
+    for users, pos, neg, false_neg in dl.CF_pair_sampler(batch, pos_mode="unique", neg_mode="exclude_pos"):
+        n += 1
+        users, pos, neg = (np.asarray(x) for x in (users, pos, neg))
+        assert false_neg is None
+        if batch <= dl.n_users:
+            assert len(set(users.tolist())) == batch
+        else:
+            assert set(users.tolist()) <= set(int(k) for k in dl.train_user_dict)
+        for u, p_, q in zip(users.tolist()[:300], pos.tolist()[:300], neg.tolist()[:300]):
+            items = set(int(x) for x in dl.train_user_dict[u])
+            assert p_ in items and q not in items and 0 <= q < dl.n_items      # RAW item ids, as in the reference
+    assert n == dl.n_train // batch + 1
+    with pytest.raises(NotImplementedError):
+        next(iter(dl.KG_sampler(batch, pos_mode="unique", neg_mode="head")))
+    with pytest.raises(NotImplementedError):
+        next(iter(dl.CF_pair_sampler(batch, pos_mode="uniform", neg_mode="exclude_pos")))
+
+
 def test_device_sampler_same_contract_as_host_sampler():
     """dataset.DeviceEdgeBatchSampler (run on the CPU device here) keeps the batch contract."""
     dl = dataset.DataLoader.from_synthetic("tiny")
