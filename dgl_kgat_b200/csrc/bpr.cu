@@ -4,11 +4,14 @@
 //
 // Forward: one warp per batch element gathers its three rows with 128-bit loads; a fixed-order
 // two-stage fp64 reduction produces the scalar.  Backward: the gradient touches at most 3B of the N
-// embedding rows, so instead of a dense (N, dim) tensor it is produced COMPACT: the 3B (node, slot)
-// pairs are radix-sorted by node, one warp per distinct node sums that node's contributions in slot
-// order (deterministic, no atomics) into rows[position of the segment head], and row_slot[node] points
+// embedding rows, so instead of a dense (N, dim) tensor it is produced COMPACT: the slots that name the
+// same node are chained through an N-sized head array (one integer atomicExch per slot), the smallest
+// slot of a chain is the node's leader and its warp sums the chain's contributions in ascending slot
+// order (deterministic, no floating-point atomics, no sort) into rows[leader], and row_slot[node] points
 // there (-1 elsewhere).  kgat_layer_bwd / kgat_input_bwd read the gradient through row_slot.
-#include <cub/device/device_radix_sort.cuh>
+// Three graph nodes (memset, link, accumulate) where the first version spent seven (a CUB radix sort of the
+// 3B keys among them) - 0.08 ms of a 1.36 ms step.
+#include <limits.h>
 
 #include "common.cuh"
 
@@ -70,41 +73,83 @@ bpr_finish_kernel(const double* __restrict__ partial, int n_blocks, int B, float
     if (threadIdx.x == 0) loss[0] = static_cast<float>(s_a[0] / B + static_cast<double>(lambda) * s_r[0] / B);
 }
 
-// key = node id of slot i, or n_nodes (sorts last, skipped) when the node is not owned by this rank
-__global__ void bpr_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ pos,
+// Backward, step 1: thread per slot i (slot = role * B + b, role 0/1/2 = src/pos/neg).  The slots that
+// name the same node are chained through head[node] (= row_slot, -1 everywhere on entry):
+// next[i] = previous head.  The chain ORDER depends on the arrival order of the atomics and is not used
+// for anything but membership.  Slots of nodes this rank does not own are marked -2.
+__global__ void bpr_link_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ pos,
                                 const int64_t* __restrict__ neg, int B, int64_t own_begin, int64_t own_end,
-                                int64_t n_nodes, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+                                int32_t* __restrict__ head, int32_t* __restrict__ next) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * B) return;
     const int role = i / B, b = i - role * B;
     const int64_t id = role == 0 ? src[b] : (role == 1 ? pos[b] : neg[b]);
-    keys[i] = static_cast<uint32_t>((id >= own_begin && id < own_end) ? id : n_nodes);
-    vals[i] = i;
+    next[i] = (id >= own_begin && id < own_end) ? atomicExch(head + id, i) : -2;
 }
 
-// one warp per sorted position that starts a segment of equal node ids
+// Backward, step 2: one warp per slot.  The warp walks the chain of its node; the slot that is the
+// SMALLEST member is the node's leader (exactly one per node, the same one in every run) and sums the
+// contributions of all members in ascending slot order - a fixed order, so the gradient is bit-identical
+// from run to run without a sort and without floating-point atomics - into rows[leader slot];
+// row_slot[node] then points there (the chain head it held is no longer needed: only this warp read it).
 __global__ void __launch_bounds__(BPR_THREADS)
 bpr_bwd_kernel(const float* __restrict__ emb, int64_t stride, int dim, const int64_t* __restrict__ src,
-               const int64_t* __restrict__ pos, const int64_t* __restrict__ neg, int B, float lambda,
+               const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
+               const int64_t* __restrict__ node_src, const int64_t* __restrict__ node_pos,
+               const int64_t* __restrict__ node_neg, int B, float lambda,
                const float* __restrict__ sig, const float* __restrict__ grad_loss,
-               const uint32_t* __restrict__ keys, const int32_t* __restrict__ slots, uint32_t n_nodes,
-               float* __restrict__ rows, int64_t rows_stride, int32_t* __restrict__ row_slot,
-               int32_t* __restrict__ rows_node) {
+               const int32_t* __restrict__ next, float* __restrict__ rows, int64_t rows_stride,
+               int32_t* __restrict__ row_slot, int32_t* __restrict__ rows_node) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * BPR_WARPS + warp;
     if (i >= 3 * B) return;
-    const uint32_t node = keys[i];
-    const bool head = (i == 0 || keys[i - 1] != node) && node < n_nodes;     // node == n_nodes: not owned
-    if (!head) {
+    const int nx = next[i];
+    if (nx == -2) {                                  // node owned by another rank
         if (lane == 0) rows_node[i] = -1;
         return;
     }
+    const int my_role = i / B, my_b = i - my_role * B;
+    const int64_t node = my_role == 0 ? node_src[my_b] : (my_role == 1 ? node_pos[my_b] : node_neg[my_b]);
+    // One walk over the chain: member t goes to lane t % 32, register t / 32 (chains of up to 256 slots
+    // live in registers; a longer one - a node drawn hundreds of times in one batch - falls back to
+    // re-walking the chain for every member, still correct).
+    constexpr int PER = 8;
+    const int first = *reinterpret_cast<const volatile int32_t*>(row_slot + node);   // chain head, read ONCE
+    int m[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) m[r] = INT_MAX;
+    int smallest = INT_MAX, len = 0;
+    for (int j = first; j >= 0; j = next[j]) {
+        smallest = min(smallest, j);
+#pragma unroll
+        for (int r = 0; r < PER; ++r)
+            if ((len >> 5) == r && (len & 31) == lane) m[r] = j;
+        ++len;
+    }
+    if (smallest != i) {
+        if (lane == 0) rows_node[i] = -1;
+        return;
+    }
+    const bool in_regs = len <= 32 * PER;
     const float scale = grad_loss[0] / static_cast<float>(B);
     // dim <= 256: each lane owns up to two float4 column groups
     float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
     const int c0 = lane * 4, c1 = c0 + 128;
-    for (int j = i; j < 3 * B && keys[j] == node; ++j) {
-        const int slot = slots[j];
+    int done = -1;                                   // largest slot already accumulated
+    for (int t = 0; t < len; ++t) {
+        // next member in ascending order: the smallest slot above `done`
+        int slot = INT_MAX;
+        if (in_regs) {
+#pragma unroll
+            for (int r = 0; r < PER; ++r)
+                if (m[r] > done && m[r] < slot) slot = m[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) slot = min(slot, __shfl_xor_sync(FULL_MASK, slot, o));
+        } else {
+            for (int j = first; j >= 0; j = next[j])
+                if (j > done && j < slot) slot = j;
+        }
+        done = slot;
         const int role = slot / B, b = slot - role * B;
         const float sg = __ldg(sig + b);
         const float* s = emb + src[b] * stride;
@@ -138,6 +183,7 @@ bpr_bwd_kernel(const float* __restrict__ emb, int64_t stride, int dim, const int
     float* out = rows + static_cast<int64_t>(i) * rows_stride;
     if (c0 < dim) *reinterpret_cast<float4*>(out + c0) = acc0;
     if (c1 < dim) *reinterpret_cast<float4*>(out + c1) = acc1;
+    __syncwarp();                                    // every lane has finished reading the chain head
     if (lane == 0) {
         row_slot[node] = i;
         rows_node[i] = static_cast<int32_t>(node);
@@ -145,26 +191,6 @@ bpr_bwd_kernel(const float* __restrict__ emb, int64_t stride, int dim, const int
 }
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-
-struct BwdWs { size_t keys_a, keys_b, vals_a, vals_b, cub, cub_bytes, total; };
-
-BwdWs plan_bwd(int B) {
-    BwdWs w{};
-    const size_t n = static_cast<size_t>(3) * (B > 0 ? B : 1);
-    size_t off = 0;
-    w.keys_a = off; off += align_up(n * 4);
-    w.keys_b = off; off += align_up(n * 4);
-    w.vals_a = off; off += align_up(n * 4);
-    w.vals_b = off; off += align_up(n * 4);
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
-                                    static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr),
-                                    static_cast<int>(n), 0, 32);
-    w.cub_bytes = bytes;
-    w.cub = off; off += align_up(bytes);
-    w.total = off;
-    return w;
-}
 
 }  // namespace
 }  // namespace kgat
@@ -174,7 +200,7 @@ using namespace kgat;
 extern "C" size_t kgat_bpr_workspace_bytes(int64_t batch) {
     if (batch <= 0) return 256;
     const size_t fwd = align_up(static_cast<size_t>(2) * sizeof(double) * ((batch + BPR_WARPS - 1) / BPR_WARPS));
-    const size_t bwd = plan_bwd(static_cast<int>(batch)).total;
+    const size_t bwd = align_up(static_cast<size_t>(3) * sizeof(int32_t) * batch);       // the slot chains
     return fwd > bwd ? fwd : bwd;
 }
 
@@ -213,24 +239,16 @@ extern "C" int kgat_bpr_loss_bwd(const float* emb, int64_t emb_stride, int dim, 
     if (workspace_bytes < kgat_bpr_workspace_bytes(batch)) return KGAT_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
     const int B = static_cast<int>(batch);
-    const BwdWs w = plan_bwd(B);
-    char* ws = static_cast<char*>(workspace);
-    uint32_t* ka = reinterpret_cast<uint32_t*>(ws + w.keys_a);
-    uint32_t* kb = reinterpret_cast<uint32_t*>(ws + w.keys_b);
-    int32_t* va = reinterpret_cast<int32_t*>(ws + w.vals_a);
-    int32_t* vb = reinterpret_cast<int32_t*>(ws + w.vals_b);
-    KGAT_CUDA(cudaMemsetAsync(row_slot, 0xff, sizeof(int32_t) * n_nodes, st));          // -1 everywhere
-    bpr_keys_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(node_src ? node_src : src, node_pos ? node_pos : pos,
-                                                         node_neg ? node_neg : neg, B, own_begin, own_end, n_nodes,
-                                                         ka, va);
+    int32_t* next = static_cast<int32_t*>(workspace);
+    const int64_t* ns = node_src ? node_src : src;
+    const int64_t* np_ = node_pos ? node_pos : pos;
+    const int64_t* nn = node_neg ? node_neg : neg;
+    KGAT_CUDA(cudaMemsetAsync(row_slot, 0xff, sizeof(int32_t) * n_nodes, st));          // -1 everywhere: empty chains
+    bpr_link_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(ns, np_, nn, B, own_begin, own_end, row_slot, next);
     KGAT_LAUNCH_CHECK();
-    int bits = 1;
-    while (bits < 32 && (static_cast<uint64_t>(n_nodes) >> bits) != 0) ++bits;      // keys go up to n_nodes
-    size_t bytes = w.cub_bytes;
-    KGAT_CUDA(cub::DeviceRadixSort::SortPairs(ws + w.cub, bytes, ka, kb, va, vb, 3 * B, 0, bits, st));
     bpr_bwd_kernel<<<(3 * B + BPR_WARPS - 1) / BPR_WARPS, BPR_THREADS, 0, st>>>(
-        emb, emb_stride, dim, src, pos, neg, B, reg_lambda, sig, grad_loss, kb, vb, static_cast<uint32_t>(n_nodes), rows,
-        dim, row_slot, rows_node);
+        emb, emb_stride, dim, src, pos, neg, ns, np_, nn, B, reg_lambda, sig, grad_loss, next, rows, dim, row_slot,
+        rows_node);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }

@@ -125,6 +125,15 @@ class PeerArena:
         with th.cuda.device(self.device):
             return int(_lib.load().kgat_peer_error(self.ref))
 
+    def check(self):
+        """Raise if a barrier of this rank ever timed out.  After a timeout the barriers stop waiting (so the
+        GPU does not hang), which means every later phase reads half-pushed rows: the training / eval drivers
+        call this at their synchronisation points so a lost peer is an error, not silently corrupted numbers."""
+        e = self.error()
+        if e:
+            raise _lib.KgatError("peer barrier timed out on rank %d waiting for rank %d: the exchanged buffers "
+                                 "are incomplete, results since then are invalid" % (self.rank, e - 1))
+
     def close(self):
         """Collective: unmap the peers' arenas, then free the own one."""
         if self._closed:
@@ -320,6 +329,16 @@ class DistKGAT:
         self.w_full = None
         self._plan = None
         self._dw_views = None
+        self._calls = 0
+        self.poll_every = int(os.environ.get("KGAT_PEER_POLL_EVERY", "128"))
+
+    def poll_peers(self, force=False):
+        """Every ``poll_every``-th call (or when forced): synchronise and raise if a peer barrier timed out."""
+        if self.peer is None or th.cuda.is_current_stream_capturing():
+            return
+        self._calls += 1
+        if force or (self.poll_every > 0 and self._calls % self.poll_every == 0):
+            self.peer.check()
 
     # attention-update mode ---------------------------------------------------------------
     def compute_attention(self):
@@ -376,6 +395,7 @@ class DistKGAT:
         and undefined with the peer exchange; ``full_embedding`` fills them); differentiable."""
         if self._plan is None:
             raise RuntimeError("call compute_attention() first")
+        self.poll_peers()
         m = self.model
         weights = [l.res_fc_2.weight for l in m.layers]
         masks = list(drop_masks) if drop_masks is not None else [None] * len(weights)
@@ -401,6 +421,7 @@ class DistKGAT:
     # evaluation ----------------------------------------------------------------------------
     def calc_recall_ndcg(self, embedding_full, train_user_dict, test_user_dict, item_id_range, K):
         """metric.calc_recall_ndcg with the eval users sharded over ranks (metric.py:36-69)."""
+        self.poll_peers(force=True)
         users = list(test_user_dict.keys())
         mine = users[self.rank::self.world]
         sub = {u: test_user_dict[u] for u in mine}

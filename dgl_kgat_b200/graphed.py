@@ -115,6 +115,10 @@ class GraphedDistCFStep(GraphedCFStep):
         self._cap_w = self._seen_w = None           # the partitioned step refreshes the attention inside the graph
         self._capture(dk.model, batch_size, warmup)
 
+    def __call__(self, src_ids, pos_ids, neg_ids):
+        self.dk.poll_peers()                # a lost peer must surface as an error, not as corrupted gradients
+        return super().__call__(src_ids, pos_ids, neg_ids)
+
     def _body(self):
         dk = self.dk
         for p in self.model.parameters():
