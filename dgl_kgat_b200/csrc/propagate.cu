@@ -715,16 +715,17 @@ struct BwdArgs {
 
 inline int bwd_max_ctas() { return 4 * num_sms(); }
 
-// Tile GEMMs of layer_bwd: tensor cores (widths DIN >= 32, DOUT >= 16) on the single-GPU path - parity-tested
-// and measured on B200 (step 1.403 -> 1.359 ms); the multi-GPU PUSH instantiations keep the fp32 FFMA GEMMs
-// until the MMA variant has been run under the peer exchange as well.  KGAT_BWD_EPILOGUE=mma / ffma forces one.
+// Tile GEMMs of layer_bwd: tensor cores (widths DIN >= 32, DOUT >= 16), single-GPU and partitioned (PUSH)
+// instantiations alike, so one GPU and N GPUs run the same arithmetic (tests/test_gpu_dist.py compares them
+// directly).  KGAT_BWD_EPILOGUE=mma / ffma forces one.
 inline int bwd_epilogue(int d_in, int d_out, bool push) {
     static int forced = -2;
     if (forced == -2) {
         const char* e = std::getenv("KGAT_BWD_EPILOGUE");
         forced = !e ? -1 : (std::strcmp(e, "mma") == 0 ? 1 : (std::strcmp(e, "ffma") == 0 ? 0 : -1));
     }
-    const int want = forced >= 0 ? forced : (push ? 0 : 1);
+    (void)push;
+    const int want = forced >= 0 ? forced : 1;
     return (want == 1 && d_in >= 32 && d_out >= 16) ? 1 : 0;
 }
 

@@ -303,7 +303,7 @@ def _bpr_backward(table, ids, node_ids, own, n_nodes, reg_lambda, sig, grad_loss
     row_slot = th.empty(n_nodes, dtype=th.int32, device=dev)
     nptr = [None] * 3 if node_ids is None else [t.data_ptr() for t in node_ids]
     with th.cuda.device(dev):
-        with _lib.record("bpr_loss_bwd", 6):
+        with _lib.record("bpr_loss_bwd", 3):
             _lib.check(lib.kgat_bpr_loss_bwd(table.data_ptr(), table.stride(0), dim, ids[0].data_ptr(), ids[1].data_ptr(),
                                              ids[2].data_ptr(), B, float(reg_lambda), sig.data_ptr(), g.data_ptr(),
                                              nptr[0], nptr[1], nptr[2], own[0], own[1], n_nodes,

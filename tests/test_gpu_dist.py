@@ -23,10 +23,8 @@ def _free_port():
 def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    # The partitioned (PUSH) backward kernels still use the fp32 FFMA tile GEMMs while the single-GPU path
-    # defaults to the tensor-core ones; this test is about the exchange, so both sides are pinned to the same
-    # arithmetic (the tensor-core GEMMs are held against the fp64 oracle in test_gpu_parity.py).
-    os.environ["KGAT_BWD_EPILOGUE"] = "ffma"
+    # default arithmetic on both sides: the partitioned (PUSH) kernels run the same tensor-core tile GEMMs as
+    # the single-GPU path
     th.cuda.set_device(rank)
     dev = th.device("cuda", rank)
     tdist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -114,10 +112,13 @@ def _check_exchange(exchange, m, ck, ids, dev, w1, emb1, loss1, ref):
         dk.close()
 
 
-@pytest.mark.skipif(th.cuda.device_count() < 2, reason="needs at least 2 GPUs")
-def test_two_gpu_step_matches_single_gpu():
-    world = 2
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_step_matches_single_gpu(world):
+    """world in {2, 4, 8}, skipped by device count (reference semantics held: models.py:146-168,
+    kgat.py:159-161 - the partitioned step must give the single-GPU numbers)."""
+    if th.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs, the box has %d" % (world, th.cuda.device_count()))
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
-    assert dict(ret) == {0: "ok", 1: "ok"}
+    assert dict(ret) == {k: "ok" for k in range(world)}
