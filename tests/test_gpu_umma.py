@@ -138,7 +138,7 @@ def test_attention_operand_range_guard(dev, case):
     with th.no_grad():
         if case == "W_R_40":
             m.W_R[3].mul_(40.0 / float(m.W_R[3].abs().max()))          # one relation with max |w| = 40
-            m.entity_embed.weight.mul_(0.005)                            # keep the logits moderate
+            m.entity_embed.weight.mul_(0.001)                            # keep the logits O(1): the bar is relative
         elif case == "entity_7e4":
             m.entity_embed.weight[17, 5] = 7.0e4                         # one value above the fp16 range (65504)
             m.W_R.mul_(1e-4)
