@@ -141,13 +141,31 @@ using namespace kgat;
 int kgat_launch_score_topk_umma(const float* emb, int64_t emb_stride, int dim, const int32_t* user_ids, int n_users,
                                 const int32_t* item_ids, int n_items, const int32_t* mask_ptr,
                                 const int32_t* mask_items, int K, int32_t* topk_idx, float* topk_score,
-                                cudaStream_t st);
+                                int* only_if, cudaStream_t st);
+int kgat_launch_score_topk_f16(const float* emb, int64_t emb_stride, int dim, const int32_t* user_ids, int n_users,
+                               const int32_t* item_ids, int n_items, const int32_t* mask_ptr,
+                               const int32_t* mask_items, int K, int32_t* topk_idx, float* topk_score,
+                               void* workspace, size_t workspace_bytes, cudaStream_t st);
+bool kgat_score_topk_f16_supported(int dim, int K);
+size_t kgat_score_topk_f16_workspace(int64_t n_users, int64_t n_items, int dim, int K);
+int kgat_eval_fallbacks_take();
 
-// KGAT_EVAL_IMPL=ffma selects the fp32 FFMA tile kernel instead of the tcgen05 3xTF32 kernel (A/B runs).
-static bool eval_use_umma() {
+// KGAT_EVAL_IMPL (A/B runs): "f16" (default, needs a workspace) tcgen05 split-fp16 with pre-split operands,
+// "tf32" tcgen05 3xTF32, "ffma" fp32 FFMA tiles.
+static int eval_impl() {
     const char* e = std::getenv("KGAT_EVAL_IMPL");
-    return !(e && std::strcmp(e, "ffma") == 0);
+    if (e && std::strcmp(e, "ffma") == 0) return 0;
+    if (e && std::strcmp(e, "tf32") == 0) return 1;
+    return 2;
 }
+static bool eval_use_umma() { return eval_impl() != 0; }
+
+extern "C" size_t kgat_score_topk_workspace_bytes(int64_t n_users, int64_t n_items, int dim, int K) {
+    if (n_users <= 0 || n_items <= 0 || !kgat_score_topk_f16_supported(dim, K)) return 0;
+    return kgat_score_topk_f16_workspace(n_users, n_items, dim, K);
+}
+
+extern "C" int kgat_eval_fallbacks(void) { return kgat_eval_fallbacks_take(); }
 
 extern "C" int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
                                const int32_t* user_ids, int64_t n_users,
@@ -163,7 +181,7 @@ extern "C" int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
     if (dim <= 256 && K <= 32 && eval_use_umma())
         return kgat_launch_score_topk_umma(emb, emb_stride, dim, user_ids, static_cast<int>(n_users), item_ids,
                                            static_cast<int>(n_items), mask_ptr, mask_items, K, topk_idx, topk_score,
-                                           as_stream(stream));
+                                           nullptr, as_stream(stream));
     const size_t smem = sizeof(float) * (2 * BK * LDT + BM * (BN + 1)) + (sizeof(float) + sizeof(int)) * BM * K + 16;
     static PerDevice<size_t> configured;
     if (smem > configured.get()) {
@@ -176,4 +194,26 @@ extern "C" int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
         mask_ptr, mask_items, K, topk_idx, topk_score);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
+}
+
+extern "C" int kgat_score_topk_ws(const float* emb, int64_t emb_stride, int dim,
+                                  const int32_t* user_ids, int64_t n_users,
+                                  const int32_t* item_ids, int64_t n_items,
+                                  const int32_t* mask_ptr, const int32_t* mask_items,
+                                  int K, int32_t* topk_idx, float* topk_score,
+                                  void* workspace, size_t workspace_bytes, kgat_stream_t stream) {
+    KGAT_REQUIRE(emb && user_ids && item_ids && topk_idx);
+    KGAT_REQUIRE(n_users >= 0 && n_items >= 0 && n_users < INT_MAX && n_items < INT_MAX);
+    KGAT_REQUIRE((mask_ptr == nullptr) == (mask_items == nullptr) || (mask_ptr && !mask_items));
+    KGAT_REQUIRE(aligned16(emb) && emb_stride % 4 == 0);
+    if (dim <= 0 || dim % 4 != 0 || K <= 0 || K > MAX_K) return KGAT_ERR_UNSUPPORTED_DIM;
+    if (n_users == 0) return KGAT_OK;
+    if (eval_impl() == 2 && n_items > 0 && kgat_score_topk_f16_supported(dim, K)) {
+        KGAT_REQUIRE(workspace && aligned16(workspace));
+        return kgat_launch_score_topk_f16(emb, emb_stride, dim, user_ids, static_cast<int>(n_users), item_ids,
+                                          static_cast<int>(n_items), mask_ptr, mask_items, K, topk_idx, topk_score,
+                                          workspace, workspace_bytes, as_stream(stream));
+    }
+    return kgat_score_topk(emb, emb_stride, dim, user_ids, n_users, item_ids, n_items, mask_ptr, mask_items, K,
+                           topk_idx, topk_score, stream);
 }

@@ -52,10 +52,17 @@ score_topk_umma_kernel(const float* __restrict__ emb, int64_t stride, int dim,
                        const int32_t* __restrict__ user_ids, int n_users,
                        const int32_t* __restrict__ item_ids, int n_items,
                        const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items, int K,
-                       int32_t* __restrict__ topk_idx, float* __restrict__ topk_score, int* __restrict__ err) {
+                       int32_t* __restrict__ topk_idx, float* __restrict__ topk_score, int* __restrict__ err,
+                       int* __restrict__ only_if) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // launched behind the split-fp16 kernel (eval_f16.cu) as its fp32-range fallback: runs only when that
+    // kernel stood down (only_if[0] != 0, final here by stream order); counts the fallbacks in only_if[1]
+    if (only_if) {
+        if (*reinterpret_cast<volatile int*>(only_if) == 0) return;
+        if (blockIdx.x == 0 && tid == 0) atomicAdd(only_if + 1, 1);
+    }
     const int u0 = blockIdx.x * TM;
     const int n_it = (n_items + TN - 1) / TN;           // item tiles
     const int n_kb = (dim + KB - 1) / KB;                // K-blocks per tile
@@ -299,20 +306,25 @@ __device__ int g_eval_umma_error = 0;     // set when a tensor-core completion b
 using namespace kgat;
 
 // read-and-clear, used by kgat_umma_error_flag()
+int kgat_eval_f16_error_take();    // eval_f16.cu
+
 int kgat_eval_umma_error_take() {
     int v = 0, zero = 0;
     if (cudaMemcpyFromSymbol(&v, g_eval_umma_error, sizeof(int)) != cudaSuccess) return KGAT_ERR_CUDA;
     if (v != 0) cudaMemcpyToSymbol(g_eval_umma_error, &zero, sizeof(int));
-    return v;
+    const int w = kgat_eval_f16_error_take();
+    if (w < 0) return w;
+    return (v != 0 || w != 0) ? 1 : 0;
 }
 
 // Launcher used by kgat_score_topk (eval.cu) when dim <= 256 and K <= 32.
 int kgat_launch_score_topk_umma(const float* emb, int64_t emb_stride, int dim, const int32_t* user_ids, int n_users,
                                 const int32_t* item_ids, int n_items, const int32_t* mask_ptr,
                                 const int32_t* mask_items, int K, int32_t* topk_idx, float* topk_score,
-                                cudaStream_t st) {
-    static int* err_flag = nullptr;
+                                int* only_if, cudaStream_t st) {
+    static PerDevice<int*> err_flags;
     static PerDeviceOnce configured;
+    int*& err_flag = err_flags.get();
     if (configured.need()) {
         KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&err_flag), g_eval_umma_error));
         KGAT_CUDA(cudaFuncSetAttribute(score_topk_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -322,7 +334,7 @@ int kgat_launch_score_topk_umma(const float* emb, int64_t emb_stride, int dim, c
     const unsigned grid = static_cast<unsigned>((n_users + TM - 1) / TM);
     score_topk_umma_kernel<<<grid, THREADS, sizeof(Smem), st>>>(emb, emb_stride, dim, user_ids, n_users, item_ids,
                                                                 n_items, mask_ptr, mask_items, K, topk_idx, topk_score,
-                                                                err_flag);
+                                                                err_flag, only_if);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }

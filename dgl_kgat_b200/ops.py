@@ -404,12 +404,16 @@ def score_topk(emb: th.Tensor, user_ids: th.Tensor, item_ids: th.Tensor, mask_pt
         raise _lib.KgatError("top-%d of %d items" % (K, n_items))
     topk = th.empty(n_users, K, dtype=th.int32, device=dev)
     scores = th.empty(n_users, K, dtype=th.float32, device=dev) if want_scores else None
+    # the pre-split operand tiles and the per-range top-K lists of the fast path live in a workspace
+    ws_bytes = lib.kgat_score_topk_workspace_bytes(n_users, n_items, emb.shape[1], K)
+    ws = th.empty(max(ws_bytes, 16), dtype=th.uint8, device=dev)
     with th.cuda.device(dev):
-        with _lib.record("score_topk"):
-            _lib.check(lib.kgat_score_topk(emb.data_ptr(), emb.stride(0), emb.shape[1], user_ids.data_ptr(), n_users,
-                                           item_ids.data_ptr(), n_items, _lib.ptr(mask_ptr),
-                                           _lib.ptr(mask_items) if mask_items is not None and mask_items.numel() else None,
-                                           K, topk.data_ptr(), _lib.ptr(scores), _lib.stream_ptr()), "kgat_score_topk")
+        with _lib.record("score_topk", 4):
+            _lib.check(lib.kgat_score_topk_ws(emb.data_ptr(), emb.stride(0), emb.shape[1], user_ids.data_ptr(), n_users,
+                                              item_ids.data_ptr(), n_items, _lib.ptr(mask_ptr),
+                                              _lib.ptr(mask_items) if mask_items is not None and mask_items.numel() else None,
+                                              K, topk.data_ptr(), _lib.ptr(scores), ws.data_ptr(), ws_bytes,
+                                              _lib.stream_ptr()), "kgat_score_topk_ws")
     return (topk, scores) if want_scores else topk
 
 

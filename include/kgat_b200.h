@@ -244,6 +244,28 @@ KGAT_API int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
                     const int32_t* mask_ptr, const int32_t* mask_items,
                     int K, int32_t* topk_idx, float* topk_score, kgat_stream_t stream);
 
+/* (5') the same contract with a caller-provided workspace: the fast path of the evaluation.  The user rows and
+ *      the item rows are split ONCE into fp16 (hi, 2^11-scaled residual) operand tiles laid out for the tensor
+ *      cores inside the workspace, every CTA keeps its 128-user tile resident and streams item tiles with bulk
+ *      asynchronous copies (tcgen05 kind::f16, fp32 accumulate in TMEM), the work is cut into
+ *      (user tile x item range) units so that any user count fills the GPU, and the per-range top-K lists are
+ *      merged (ties -> lower position).  Same results as kgat_score_topk to fp32 rounding of the scores.
+ *      Covers dim <= 192 and K <= 22 (K <= 54 for dim <= 128); other shapes, KGAT_EVAL_IMPL=tf32|ffma, and
+ *      operands outside the fp16 range (|x| >= 65504, detected on the device, counted by
+ *      kgat_eval_fallbacks()) run the kgat_score_topk kernels.  workspace: device memory of at least
+ *      kgat_score_topk_workspace_bytes(...) bytes (0: the shape is not covered and no workspace is needed),
+ *      16-byte aligned, only used during the call (stream order). */
+KGAT_API size_t kgat_score_topk_workspace_bytes(int64_t n_users, int64_t n_items, int dim, int K);
+KGAT_API int kgat_score_topk_ws(const float* emb, int64_t emb_stride, int dim,
+                       const int32_t* user_ids, int64_t n_users,
+                       const int32_t* item_ids, int64_t n_items,
+                       const int32_t* mask_ptr, const int32_t* mask_items,
+                       int K, int32_t* topk_idx, float* topk_score,
+                       void* workspace, size_t workspace_bytes, kgat_stream_t stream);
+/* number of kgat_score_topk_ws calls on the current device that fell back to the fp32-range kernel since the
+ * last call of this function (then cleared).  Synchronises the device. */
+KGAT_API int kgat_eval_fallbacks(void);
+
 /* ------------------------------------------------------------------------------------------------
  * (8) Multi-GPU: peer-memory exchange for the destination-partitioned step (one process per GPU of one
  *     NVLink / NVSwitch box).  New capability -- the reference is single-GPU (kgat.py:14,69-71).

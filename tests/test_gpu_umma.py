@@ -191,7 +191,7 @@ def test_eval_umma_vs_ffma_vs_oracle(dev):
         s64[j, tr[u]] = 0.0
     want = np.argsort(-s64.numpy(), axis=1, kind="stable")[:, :20]
     out = {}
-    for impl in ("ffma", "umma"):
+    for impl in ("ffma", "tf32", "f16"):
         os.environ["KGAT_EVAL_IMPL"] = impl
         try:
             topk, _ = metric.topk_items(emb.to(dev), tr, te, th.as_tensor(items, device=dev), 20,
@@ -216,4 +216,74 @@ def test_eval_umma_vs_ffma_vs_oracle(dev):
                 assert r.index(3) < r.index(7), (impl, j)
     assert _lib.load().kgat_umma_error_flag() == 0
     print("exact top-20 rows:", out)
-    assert out["umma"] > 0.95 and out["ffma"] > 0.95
+    assert out["f16"] > 0.95 and out["tf32"] > 0.95 and out["ffma"] > 0.95
+
+
+def _dense_topk(emb, users, items, tr, K):
+    s64 = emb[users].double() @ emb[items].double().t()
+    for j, u in enumerate(users):
+        s64[j, tr[u]] = 0.0
+    return np.argsort(-s64.numpy(), axis=1, kind="stable")[:, :K], s64.numpy()
+
+
+def _assert_topk(got, want, s64, K):
+    for j in range(got.shape[0]):
+        if np.array_equal(got[j], want[j]):
+            continue
+        s = s64[j]
+        tol = 2e-6 * max(1.0, np.abs(s).max())
+        assert np.allclose(np.sort(s[got[j]])[::-1], s[want[j]], rtol=0, atol=tol), j
+        assert all(abs(s[a] - s[b]) <= tol for a, b in zip(got[j], want[j]) if a != b), j
+
+
+@pytest.mark.parametrize("n_users,n_items,dim,K", [(1, 20, 176, 20), (129, 127, 176, 20), (700, 5000, 176, 20),
+                                                   (300, 1111, 64, 7), (257, 2049, 128, 22), (64, 300, 192, 1)])
+def test_eval_f16_shapes_splits_and_merge(dev, n_users, n_items, dim, K):
+    """The pre-split / bulk-copy scoring kernel over ragged user and item counts, partial K-blocks (dim 176 =
+    2.75 blocks of 64), one to many item ranges per user tile and the merge of their lists, against a dense fp64
+    ranking; exact ties (duplicated item rows in different ranges) must come out in index order."""
+    rng = np.random.default_rng(n_users + n_items)
+    th.manual_seed(n_users)
+    N = n_users + n_items
+    emb = th.randn(N, dim)
+    if n_items > 10:
+        emb[n_users + n_items - 2] = emb[n_users + 1]           # exact tie far apart on the item axis
+    users = list(range(n_users))
+    items = np.arange(n_users, N)
+    tr = {u: np.unique(rng.integers(0, n_items, rng.integers(0, min(30, n_items)))) for u in users}
+    te = {u: rng.integers(0, n_items, 2) for u in users}
+    topk, _ = metric.topk_items(emb.to(dev), tr, te, th.as_tensor(items, device=dev), K,
+                                plan=metric.EvalPlan(tr, te, n_items))
+    got = topk.cpu().numpy()
+    want, s64 = _dense_topk(emb, users, items, tr, K)
+    _assert_topk(got, want, s64, K)
+    for j in range(n_users):
+        r = got[j].tolist()
+        assert len(set(r)) == K and min(r) >= 0 and max(r) < n_items
+        if n_items > 10 and 1 in r and n_items - 2 in r:
+            assert r.index(1) < r.index(n_items - 2), j
+    lib = _lib.load()
+    assert lib.kgat_umma_error_flag() == 0 and lib.kgat_eval_fallbacks() == 0
+
+
+def test_eval_f16_range_guard(dev):
+    """A value outside the fp16 range must not silently corrupt the ranking: the split kernel detects it, the
+    fp16 kernel stands down and the fp32-range kernel produces the result (counted by kgat_eval_fallbacks)."""
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    th.manual_seed(5)
+    n_users, n_items, dim, K = 200, 900, 176, 20
+    emb = th.randn(n_users + n_items, dim)
+    emb[n_users + 17, 3] = 1.0e5
+    users = list(range(n_users))
+    items = np.arange(n_users, n_users + n_items)
+    tr = {u: np.unique(rng.integers(0, n_items, 5)) for u in users}
+    te = {u: rng.integers(0, n_items, 2) for u in users}
+    assert lib.kgat_eval_fallbacks() >= 0
+    topk, _ = metric.topk_items(emb.to(dev), tr, te, th.as_tensor(items, device=dev), K,
+                                plan=metric.EvalPlan(tr, te, n_items))
+    th.cuda.synchronize()
+    assert lib.kgat_eval_fallbacks() == 1
+    want, s64 = _dense_topk(emb, users, items, tr, K)
+    _assert_topk(topk.cpu().numpy(), want, s64, K)
+    assert lib.kgat_umma_error_flag() == 0
