@@ -4,10 +4,11 @@
 // Replaces the per-user loop of the reference (metric.py:44-59): item-matrix re-gather, GEMV, mask, full
 // sort, device->host sync per user.  score[u, i] = <emb[user u], emb[item i]> is a (U x dim) x (dim x I)
 // GEMM (469 GFLOP for the 53 469 eval users of the Amazon-book shape); the ranking needs fp32 accuracy
-// (one half-precision pass would reorder near-ties), so every fp32 value is split
-//     x = hi + 2^-11 lo',   hi = RN_fp16(x),   lo' = RN_fp16((x - hi) * 2^11)            (22 significant bits)
-//     u . i  ~=  hi_u . hi_i  +  2^-11 (hi_u . lo'_i + lo'_u . hi_i)
-// and the two brackets accumulate in two fp32 TMEM accumulators, combined when they are read out.
+// (one half-precision pass would reorder near-ties), so every fp32 value is pre-scaled by one power of two
+// s (chosen so that max |x| s lies in [2^13, 2^14): the residual below stays a normal fp16 number) and split
+//     x s = hi + lo,   hi = RN_fp16(x s),   lo = RN_fp16(x s - hi)                       (22 significant bits)
+//     s^2 u . i  ~=  hi_u . hi_i + hi_u . lo_i + lo_u . hi_i
+// all three products into ONE fp32 TMEM accumulator; the ranking does not see the scale.
 //
 // What changed against eval_umma.cu (3xTF32, 5.4 ms): there, eight producer warps re-gathered, re-split and
 // re-stored the USER tile for every item tile, and the grid was one CTA per 128 users (52 CTAs on 148 SMs
@@ -15,20 +16,25 @@
 //   * eval_split_kernel splits the user rows and the item rows ONCE into fp16 hi / lo' tiles that already
 //     have the K-major SWIZZLE_128B shared-memory layout (128 rows x 64 features = 16 KB per array), so a
 //     tile is a contiguous blob in HBM / L2;
-//   * the main kernel keeps its user tile (hi and lo', all K-blocks, 96 KB at dim 176) RESIDENT in shared
-//     memory and streams item K-blocks [I_hi ; I_lo'] (32 KB) through a 3-stage ring with
+//   * the main kernel keeps its user tile (hi and lo, all K-blocks, 96 KB at dim 176) RESIDENT in shared
+//     memory and streams the item arrays (I_hi, I_lo: 16 KB each) through a 4-slot ring with
 //     cp.async.bulk + mbarrier complete_tx: no LSU gather, no conversion, no st.shared on the operand path -
 //     one thread issues the copies;
-//   * per K-step of 16 features: U_hi x [I_hi ; I_lo']^T (N = 256: columns 0..127 hi.hi, 128..255 hi.lo')
-//     and U_lo' x I_hi^T (N = 128, into columns 128..255): kind::f16 moves half the operand bytes of TF32 and
-//     runs at twice its rate;
+//   * per K-step of 16 features three M = 128, N = 128 kind::f16 MMAs (half the operand bytes of TF32 at
+//     twice its rate) into one of FOUR accumulator buffers;
+//   * two read-out groups of four warps alternate over the item tiles (one warp per SM sub-partition could
+//     not keep up with the tensor pipe: measured 13 000 clocks per tile against 2 300), each with its own
+//     candidate buffers and sorted lists;
 //   * work unit = (user tile, item range): the item axis is cut into S ranges so that the grid fills the
 //     SMs at any user count (an 8-way user shard of Amazon-book has 53 user tiles); every unit keeps its own
-//     top-K and topk_merge_kernel merges the S sorted lists of a user (ties -> lower item index, as a
+//     top-K and topk_merge_kernel merges the sorted lists of a user (ties -> lower item index, as a
 //     direct insertion would).
-// Range: |x| < 65504 (fp16).  eval_split_kernel checks it and raises a device word; the main kernel then does
-// nothing and the 3xTF32 kernel (fp32 range) launched behind it computes the result instead - no host round trip.
+// Range: any finite fp32 magnitude (the scale is computed per call).  inf / NaN or a dynamic range above 2^16
+// inside the operands raise a device word; the main kernel then does nothing and the 3xTF32 kernel launched
+// behind it computes the result instead - no host round trip.
 #include <limits.h>
+
+#include <cstdlib>
 
 #include <cuda_fp16.h>
 
@@ -42,18 +48,22 @@ constexpr int TM = 128, TN = 128;                 // users per CTA, items per ac
 constexpr int KB = 64;                            // features per K-block: one 128-byte swizzled fp16 row
 constexpr int NKB_MAX = 3;                        // dim <= 192: the user tile must stay resident
 constexpr uint32_t ARR_BYTES = TM * KB * 2;       // 16 KB: 128 rows x 64 fp16
-constexpr uint32_t BLK_BYTES = 2 * ARR_BYTES;     // hi, lo' of one K-block
-constexpr int NST = 3;                            // item K-block ring
-constexpr int THREADS = 256;                      // warp 0 copies, warp 1 MMA, warps 4..7 top-K
-constexpr int N_EPI = 128;
+constexpr uint32_t BLK_BYTES = 2 * ARR_BYTES;     // hi, lo of one K-block
+constexpr int NSLOT = 4;                          // ring of item ARRAYS (I_hi and I_lo are consumed separately)
+constexpr int N_GRP = 2;                          // read-out groups: group g takes the tiles n with n % 2 == g
+constexpr int N_EPI = 128;                        // threads per read-out group (one TMEM lane each)
+constexpr int THREADS = 128 + N_GRP * N_EPI;      // warp 0 copies, warp 1 MMA, warps 4..7 / 8..11 top-K
+constexpr int N_ACC = 4;                          // accumulator buffers (128 TMEM columns each)
 constexpr size_t SMEM_LIMIT = 232448;             // 227 KB opt-in shared memory per CTA
-constexpr int CAP = 12, CH = 8;                   // candidate-buffer depth per row, columns per TMEM load
-constexpr int S_MAX = 16;                         // item ranges per user tile
-constexpr uint32_t TMEM_COLS = 512;               // 2 buffers x (128 + 128) columns
-constexpr float LO_SCALE = 2048.0f, LO_INV = 1.0f / 2048.0f;
+constexpr int CAP = 12, CH = 8;                   // candidate-buffer depth per row, columns per chunk
+constexpr int S_MAX = 8;                          // item ranges per user tile
+constexpr int L_MAX = N_GRP * S_MAX;              // sorted lists per user that the merge sees
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int TARGET_EXP = 13;                    // operands are pre-scaled so that max |x| lies in [2^13, 2^14)
 
 __host__ __device__ inline size_t smem_bytes(int nkb, int K) {
-    return static_cast<size_t>(nkb + NST) * BLK_BYTES + static_cast<size_t>(K + CAP) * TM * 8 + 128;
+    return static_cast<size_t>(nkb) * BLK_BYTES + static_cast<size_t>(NSLOT) * ARR_BYTES +
+           static_cast<size_t>(N_GRP) * (K + CAP) * TM * 8 + 256;
 }
 
 // instruction descriptor for kind::f16 with fp16 operands (a_format = b_format = 0), fp32 accumulate
@@ -86,22 +96,107 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                  : "memory");
 }
 
+// 64-bit ranking key: larger key = ranks earlier.  High word: the score's bits made order-preserving as an
+// unsigned integer; low word: ~index, so that among equal scores the LOWER index has the larger key.
+__device__ __forceinline__ unsigned long long make_key(float score, int idx) {
+    const uint32_t b = __float_as_uint(score);
+    const uint32_t o = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return (static_cast<unsigned long long>(o) << 32) | static_cast<uint32_t>(~idx);
+}
+__device__ __forceinline__ float key_score(unsigned long long k) {
+    const uint32_t o = static_cast<uint32_t>(k >> 32);
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ int key_index(unsigned long long k) { return static_cast<int>(~static_cast<uint32_t>(k)); }
+
 __device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
-// (a, b) -> packed hi pair and packed scaled-residual pair; ok &= both inside the fp16 range
-__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo, bool& ok) {
-    ok = ok && (fabsf(a) < 65504.0f) && (fabsf(b) < 65504.0f);
+// (a, b) already scaled -> packed hi pair and packed residual pair
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(a, b);
     const float2 f = __half22float2(h);
     hi = pack_h2(h);
-    lo = pack_h2(__floats2half2_rn((a - f.x) * LO_SCALE, (b - f.y) * LO_SCALE));
+    lo = pack_h2(__floats2half2_rn(a - f.x, b - f.y));
 }
 
 // ------------------------------------------------------------------------------------------------
 // operand preparation: one thread = one 16-byte chunk (8 features) of one row of one K-block
 // ------------------------------------------------------------------------------------------------
-// blob layout: tile t (128 rows), K-block kb: [hi 16 KB][lo' 16 KB] at ((t * nkb + kb) * 32 KB); inside an
-// array element (r, p), p = feature index inside the K-block, sits at the SWIZZLE_128B position
+struct PrepIdx { int c, r, kb, tile; bool is_user, valid; };
+
+__device__ __forceinline__ PrepIdx prep_index(int u_tiles, int i_tiles, int nkb) {
+    const int64_t gid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    PrepIdx p;
+    p.c = static_cast<int>(gid & 7);
+    p.r = static_cast<int>((gid >> 3) & 127);
+    const int64_t blk = gid >> 10;
+    p.kb = static_cast<int>(blk % nkb);
+    p.tile = static_cast<int>(blk / nkb);
+    p.valid = p.tile < u_tiles + i_tiles;
+    p.is_user = p.tile < u_tiles;
+    if (!p.is_user) p.tile -= u_tiles;
+    return p;
+}
+
+__device__ __forceinline__ void prep_load(const PrepIdx& p, const float* __restrict__ emb, int64_t stride, int dim,
+                                          const int32_t* __restrict__ user_ids, int n_users,
+                                          const int32_t* __restrict__ item_ids, int n_items, float4& v0, float4& v1) {
+    v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    v1 = v0;
+    const int row = p.tile * TM + p.r;
+    const int n_rows = p.is_user ? n_users : n_items;
+    const int32_t* ids = p.is_user ? user_ids : item_ids;
+    const int k0 = p.kb * KB + p.c * 8;
+    if (p.valid && row < n_rows) {
+        const float* src = emb + static_cast<size_t>(__ldg(ids + row)) * stride + k0;
+        if (k0 < dim) v0 = ldg4(src);
+        if (k0 + 4 < dim) v1 = ldg4(src + 4);
+    }
+}
+
+// pass 1: word[0] = bits of max |x| over the user and item rows (non-negative floats order like their bit
+// patterns), word[1] |= 1 if a value is inf / NaN (then the fp32 kernel takes over), word[3] = bits of the
+// smallest non-zero chunk maximum (8 consecutive features of a row): the dynamic range of the operands
+__global__ void __launch_bounds__(256)
+eval_absmax_kernel(const float* __restrict__ emb, int64_t stride, int dim,
+                   const int32_t* __restrict__ user_ids, int n_users, int u_tiles,
+                   const int32_t* __restrict__ item_ids, int n_items, int i_tiles, int nkb,
+                   unsigned int* __restrict__ word) {
+    const PrepIdx p = prep_index(u_tiles, i_tiles, nkb);
+    float4 v0, v1;
+    prep_load(p, emb, stride, dim, user_ids, n_users, item_ids, n_items, v0, v1);
+    float m = fmaxf(fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))),
+                    fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
+    const float sum = v0.x + v0.y + v0.z + v0.w + v1.x + v1.y + v1.z + v1.w;       // NaN / inf propagate
+    bool bad = !(fabsf(sum) < INFINITY) || !(m < INFINITY);
+    m = warp_max(m);
+    bad = __any_sync(FULL_MASK, bad);
+    float lo = m > 0.f ? m : INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lo = fminf(lo, __shfl_xor_sync(FULL_MASK, lo, o));
+    if ((threadIdx.x & 31) == 0) {
+        if (m > 0.f) atomicMax(word, __float_as_uint(m));
+        if (lo < INFINITY) atomicMin(word + 3, __float_as_uint(lo));
+        if (bad) atomicOr(word + 1, 1u);
+    }
+}
+
+// The fp16 pair resolves a value x to max(2^-22 |x|, 2^-39 max|x|): fine while the embeddings span less than
+// ~2^16 in magnitude.  A table with a wilder dynamic range (an outlier 10^5 times the typical entry) goes to
+// the fp32-range kernel instead.
+constexpr float MAX_DYNAMIC_RANGE = 65536.0f;
+
+// scale = 2^e with max |x| * scale in [2^13, 2^14): the fp16 pair (hi, lo) = (RN(x s), RN(x s - hi)) then
+// carries 22 significant bits for every value within 2^-16 of the maximum and <= 2^-38 max ABSOLUTE error
+// below that, whatever the magnitude of the embeddings - no range limit, no separate scale for the residual
+__device__ __forceinline__ float operand_scale(unsigned int max_bits) {
+    const float m = __uint_as_float(max_bits);
+    if (!(m > 0.f) || !(m < INFINITY)) return 1.0f;
+    return ldexpf(1.0f, TARGET_EXP - ilogbf(m));
+}
+
+// pass 2.  blob layout: tile t (128 rows), K-block kb: [hi 16 KB][lo 16 KB] at ((t * nkb + kb) * 32 KB);
+// inside an array element (r, p), p = feature index inside the K-block, sits at the SWIZZLE_128B position
 // (r / 8) * 1024 + (r % 8) * 128 + (((p / 8) ^ (r % 8)) * 16) + (p % 8) * 2.  Rows past the end and features
 // past dim are zero.
 __global__ void __launch_bounds__(256)
@@ -109,34 +204,24 @@ eval_split_kernel(const float* __restrict__ emb, int64_t stride, int dim,
                   const int32_t* __restrict__ user_ids, int n_users, int u_tiles,
                   const int32_t* __restrict__ item_ids, int n_items, int i_tiles, int nkb,
                   unsigned char* __restrict__ u_blob, unsigned char* __restrict__ i_blob,
-                  int* __restrict__ fallback) {
-    const int64_t gid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int c = static_cast<int>(gid & 7), r = static_cast<int>((gid >> 3) & 127);
-    const int64_t blk = gid >> 10;
-    const int kb = static_cast<int>(blk % nkb);
-    int tile = static_cast<int>(blk / nkb);
-    if (tile >= u_tiles + i_tiles) return;
-    const bool is_user = tile < u_tiles;
-    if (!is_user) tile -= u_tiles;
-    const int row = tile * TM + r;
-    const int n_rows = is_user ? n_users : n_items;
-    const int32_t* ids = is_user ? user_ids : item_ids;
-    const int k0 = kb * KB + c * 8;
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-    if (row < n_rows) {
-        const float* src = emb + static_cast<size_t>(__ldg(ids + row)) * stride + k0;
-        if (k0 < dim) v0 = ldg4(src);
-        if (k0 + 4 < dim) v1 = ldg4(src + 4);
+                  const unsigned int* word) {
+    const PrepIdx p = prep_index(u_tiles, i_tiles, nkb);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // the decision every later kernel of this call reads (stream order): word[1] != 0 -> fp32 kernel
+        const float hi = __uint_as_float(word[0]), lo = __uint_as_float(word[3]);
+        if (hi > 0.f && lo < INFINITY && hi > lo * MAX_DYNAMIC_RANGE) atomicOr(const_cast<unsigned int*>(word) + 1, 1u);
     }
-    bool ok = true;
+    if (!p.valid) return;
+    float4 v0, v1;
+    prep_load(p, emb, stride, dim, user_ids, n_users, item_ids, n_items, v0, v1);
+    const float sc = operand_scale(word[0]);
     uint4 hi, lo;
-    split_pair(v0.x, v0.y, hi.x, lo.x, ok);
-    split_pair(v0.z, v0.w, hi.y, lo.y, ok);
-    split_pair(v1.x, v1.y, hi.z, lo.z, ok);
-    split_pair(v1.z, v1.w, hi.w, lo.w, ok);
-    if (!ok) *reinterpret_cast<volatile int*>(fallback) = 1;       // a value outside the fp16 range (or NaN)
-    unsigned char* dst = (is_user ? u_blob : i_blob) + (static_cast<size_t>(tile) * nkb + kb) * BLK_BYTES +
-                         (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+    split_pair(v0.x * sc, v0.y * sc, hi.x, lo.x);
+    split_pair(v0.z * sc, v0.w * sc, hi.y, lo.y);
+    split_pair(v1.x * sc, v1.y * sc, hi.z, lo.z);
+    split_pair(v1.z * sc, v1.w * sc, hi.w, lo.w);
+    unsigned char* dst = (p.is_user ? u_blob : i_blob) + (static_cast<size_t>(p.tile) * nkb + p.kb) * BLK_BYTES +
+                         (p.r >> 3) * 1024 + (p.r & 7) * 128 + ((p.c ^ (p.r & 7)) << 4);
     *reinterpret_cast<uint4*>(dst) = hi;
     *reinterpret_cast<uint4*>(dst + ARR_BYTES) = lo;
 }
@@ -149,42 +234,40 @@ score_topk_f16_kernel(const unsigned char* __restrict__ u_blob, const unsigned c
                       int n_users, int n_items, int nkb, int n_ks, int S,
                       const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items, int K,
                       int32_t* __restrict__ out_idx, float* __restrict__ out_score, int* __restrict__ err,
-                      const int* __restrict__ fallback) {
+                      const unsigned int* __restrict__ word) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* sU = smem_raw;                                     // nkb x [hi 16 KB][lo' 16 KB]
-    unsigned char* sB = sU + static_cast<size_t>(nkb) * BLK_BYTES;    // NST x [I_hi 16 KB][I_lo' 16 KB]
-    float* ls = reinterpret_cast<float*>(sB + NST * BLK_BYTES);       // sorted top-K lists, [position][row]
-    int* li = reinterpret_cast<int*>(ls + K * TM);
-    float* cs = reinterpret_cast<float*>(li + K * TM);                // candidate buffers, [slot][row]
-    int* ci = reinterpret_cast<int*>(cs + CAP * TM);
-    uint64_t* full = reinterpret_cast<uint64_t*>(ci + CAP * TM);      // [NST]
-    uint64_t* empty = full + NST;                                     // [NST]
-    uint64_t* acc_full = empty + NST;                                 // [2]
-    uint64_t* acc_empty = acc_full + 2;                               // [2]
-    uint64_t* u_full = acc_empty + 2;                                 // [1]
+    unsigned char* sU = smem_raw;                                     // nkb x [hi 16 KB][lo 16 KB]
+    unsigned char* sB = sU + static_cast<size_t>(nkb) * BLK_BYTES;    // NSLOT x 16 KB
+    unsigned long long* lk_all = reinterpret_cast<unsigned long long*>(sB + NSLOT * ARR_BYTES);   // per group: top-K keys [K][TM]
+    float* cs_all = reinterpret_cast<float*>(lk_all + N_GRP * K * TM);    // per group: candidates [CAP][TM]
+    int* ci_all = reinterpret_cast<int*>(cs_all + N_GRP * CAP * TM);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ci_all + N_GRP * CAP * TM);   // [NSLOT]
+    uint64_t* empty = full + NSLOT;                                   // [NSLOT]
+    uint64_t* acc_full = empty + NSLOT;                               // [N_ACC]
+    uint64_t* acc_empty = acc_full + N_ACC;                           // [N_ACC]
+    uint64_t* u_full = acc_empty + N_ACC;                             // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 1);
-    volatile int* flags = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [0] abort, [1] epilogue abort, [2] skip
+    volatile int* flags = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [0] abort, [1] skip
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // operands outside the fp16 range: this kernel stands down, the fp32-range kernel behind it runs
-    if (tid == 0) flags[2] = *reinterpret_cast<const volatile int*>(fallback);
+    // inf / NaN among the operands: this kernel stands down, the fp32 kernel behind it runs
+    if (tid == 0) flags[1] = static_cast<int>(*reinterpret_cast<const volatile unsigned int*>(word + 1));
     __syncthreads();
-    if (flags[2]) return;
+    if (flags[1]) return;
 
     if (warp == 1) umma::tmem_alloc(tmem_slot, TMEM_COLS);
     if (tid == 0) {
-        for (int i = 0; i < NST; ++i) {
+        for (int i = 0; i < NSLOT; ++i) {
             umma::mbar_init(&full[i], 1);
             umma::mbar_init(&empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < N_ACC; ++i) {
             umma::mbar_init(&acc_full[i], 1);
             umma::mbar_init(&acc_empty[i], N_EPI);
         }
         umma::mbar_init(u_full, 1);
         umma::fence_barrier_init();
         flags[0] = 0;
-        flags[1] = 0;
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -205,51 +288,57 @@ score_topk_f16_kernel(const unsigned char* __restrict__ u_blob, const unsigned c
             for (int kb = 0; kb < nkb; ++kb)
                 bulk_copy_g2s(sU + static_cast<size_t>(kb) * BLK_BYTES, usrc + static_cast<size_t>(kb) * BLK_BYTES,
                               BLK_BYTES, u_full);
+            // the item blob of tiles it0..it1 is one contiguous sequence of arrays: hi, lo, hi, lo, ...
+            const unsigned char* isrc = i_blob + static_cast<size_t>(it0) * nkb * BLK_BYTES;
+            const int n_arr = (it1 - it0) * nkb * 2;
             int slot = 0, use = 0;
-            for (int it = it0; it < it1 && !flags[0]; ++it) {
-                const unsigned char* isrc = i_blob + static_cast<size_t>(it) * nkb * BLK_BYTES;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    if (!umma::mbar_wait(&empty[slot], (use & 1) ^ 1)) flags[0] = 1;
-                    mbar_expect_tx(&full[slot], BLK_BYTES);
-                    bulk_copy_g2s(sB + static_cast<size_t>(slot) * BLK_BYTES, isrc + static_cast<size_t>(kb) * BLK_BYTES,
-                                  BLK_BYTES, &full[slot]);
-                    if (++slot == NST) { slot = 0; ++use; }
-                }
+            for (int a = 0; a < n_arr && !flags[0]; ++a) {
+                if (!umma::mbar_wait(&empty[slot], (use & 1) ^ 1)) flags[0] = 1;
+                mbar_expect_tx(&full[slot], ARR_BYTES);
+                bulk_copy_g2s(sB + static_cast<size_t>(slot) * ARR_BYTES, isrc + static_cast<size_t>(a) * ARR_BYTES,
+                              ARR_BYTES, &full[slot]);
+                if (++slot == NSLOT) { slot = 0; ++use; }
             }
         }
     } else if (warp == 1) {
         // =========================================================== MMA issuer
+        // per K-step of 16 features, all three products into ONE accumulator (same shape, same columns):
+        //   I_hi array:  D += U_hi I_hi^T,  D += U_lo I_hi^T        I_lo array:  D += U_hi I_lo^T
         if (lane == 0) {
-            const uint32_t idesc256 = make_idesc_f16(TM, 256), idesc128 = make_idesc_f16(TM, 128);
+            const uint32_t idesc = make_idesc_f16(TM, TN);
             if (!umma::mbar_wait(u_full, 0)) flags[0] = 1;
             umma::fence_after_sync();
             const uint32_t aU0 = umma::smem_u32(sU), bI0 = umma::smem_u32(sB);
             int slot = 0, use = 0;
             for (int it = it0; it < it1 && !flags[0]; ++it) {
-                const int n = it - it0, buf = n & 1;
-                if (!umma::mbar_wait(&acc_empty[buf], ((n >> 1) & 1) ^ 1)) flags[0] = 1;
+                const int n = it - it0, buf = n % N_ACC;
+                if (!umma::mbar_wait(&acc_empty[buf], ((n / N_ACC) & 1) ^ 1)) flags[0] = 1;
                 umma::fence_after_sync();
-                const uint32_t tD = tmem + buf * 256;
+                const uint32_t tD = tmem + buf * TN;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    if (!umma::mbar_wait(&full[slot], use & 1)) flags[0] = 1;
-                    umma::fence_after_sync();
-                    const uint32_t aU = aU0 + kb * BLK_BYTES, bI = bI0 + slot * BLK_BYTES;
+                    const uint32_t aHi = aU0 + kb * BLK_BYTES, aLo = aHi + ARR_BYTES;
                     const int nks = min(KB / 16, n_ks - kb * (KB / 16));     // the last K-block may be partial
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint32_t off = ks * 32;                          // 16 fp16 inside the 128-byte row
-                        const uint64_t dB = umma::make_smem_desc_sw128(bI + off);   // rows 0..127 I_hi, 128..255 I_lo'
-                        mma_f16(tD, umma::make_smem_desc_sw128(aU + off), dB, idesc256, (kb | ks) != 0);
-                        mma_f16(tD + 128, umma::make_smem_desc_sw128(aU + ARR_BYTES + off), dB, idesc128, 1);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (!umma::mbar_wait(&full[slot], use & 1)) flags[0] = 1;
+                        umma::fence_after_sync();
+                        const uint32_t bI = bI0 + slot * ARR_BYTES;
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint32_t off = ks * 32;                      // 16 fp16 inside the 128-byte row
+                            const uint64_t dB = umma::make_smem_desc_sw128(bI + off);
+                            mma_f16(tD, umma::make_smem_desc_sw128(aHi + off), dB, idesc, (kb | ks | h) != 0);
+                            if (h == 0) mma_f16(tD, umma::make_smem_desc_sw128(aLo + off), dB, idesc, 1);
+                        }
+                        umma::mma_commit(&empty[slot]);
+                        if (++slot == NSLOT) { slot = 0; ++use; }
                     }
-                    umma::mma_commit(&empty[slot]);
-                    if (++slot == NST) { slot = 0; ++use; }
                 }
                 umma::mma_commit(&acc_full[buf]);
             }
         }
     } else if (warp >= 4) {
-        // =========================================================== epilogue (warps 4..7): mask + top-K
-        const int q = warp & 3, row = q * 32 + lane, et = tid - 128;
+        // =========================================================== read-out groups: mask + top-K
+        const int grp = (warp - 4) >> 2, q = warp & 3, row = q * 32 + lane;
         const bool sel = u0 + row < n_users;
         const int item_begin = it0 * TN;
         int cnt = 0, mp = 0, mend = 0, next_mask = INT_MAX;
@@ -260,103 +349,133 @@ score_topk_f16_kernel(const unsigned char* __restrict__ u_blob, const unsigned c
             while (mp < mend && mask_items[mp] < item_begin) ++mp;      // this unit starts inside the item axis
             next_mask = mp < mend ? mask_items[mp] : INT_MAX;
         }
-        float* const lsr = ls + row;                     // element p of this row's list: lsr[p * TM]
-        int* const lir = li + row;
-        float* const csr = cs + row;
-        int* const cir = ci + row;
-        int ncand = 0;
-        // merge the buffered candidates, in arrival (= ascending item) order, into the sorted list; a
-        // candidate displaces only entries it beats strictly, so ties keep the lower index first
+        unsigned long long* const lkr = lk_all + grp * K * TM + row;   // entry p of this row's list: lkr[p * TM]
+        float* const csr = cs_all + grp * CAP * TM + row;
+        int* const cir = ci_all + grp * CAP * TM + row;
+        int ncand = 0, minpos = 0;
+        // The row's K best so far are an UNSORTED set of 64-bit keys (order-preserving score bits, then the
+        // complemented item index: the smallest key is the entry that ranks last - lowest score, and among
+        // equal scores the highest index).  A candidate that beats the threshold replaces that entry and the
+        // minimum is found again by one pass over the K keys: independent loads, no serial shifting (the
+        // sorted insertion it replaces was 30 % of the kernel).  Candidates arrive in ascending item order and
+        // displace only entries they beat strictly, so ties keep the lower index; the list is sorted once, at the end.
+        auto rescan = [&]() {
+            unsigned long long mk = lkr[0];
+            int mp_ = 0;
+#pragma unroll 4
+            for (int p = 1; p < K; ++p) {
+                const unsigned long long k = lkr[p * TM];
+                if (k < mk) { mk = k; mp_ = p; }
+            }
+            minpos = mp_;
+            thr = key_score(mk);
+        };
         auto flush = [&]() {
             for (int t = 0; t < ncand; ++t) {
                 const float sc = csr[t * TM];
-                if (cnt < K || sc > thr) {
-                    int p = cnt < K ? cnt : K - 1;
-                    while (p > 0 && lsr[(p - 1) * TM] < sc) {
-                        lsr[p * TM] = lsr[(p - 1) * TM];
-                        lir[p * TM] = lir[(p - 1) * TM];
-                        --p;
-                    }
-                    lsr[p * TM] = sc;
-                    lir[p * TM] = cir[t * TM];
-                    if (cnt < K) ++cnt;
-                    if (cnt == K) thr = lsr[(K - 1) * TM];
+                if (cnt < K) {
+                    lkr[cnt * TM] = make_key(sc, cir[t * TM]);
+                    if (++cnt == K) rescan();
+                } else if (sc > thr) {
+                    lkr[minpos * TM] = make_key(sc, cir[t * TM]);
+                    rescan();
                 }
             }
             ncand = 0;
         };
-        auto consume = [&](const float* a, const float* b, int item0, bool tile_full) {
-            // when ANY row of the warp is about to overflow its buffer every row merges now (rows of a warp
-            // fill their buffers at similar rates, so the serial insertion chain runs a few times per tile)
-            if (__any_sync(FULL_MASK, sel && ncand > CAP - CH)) flush();
-            if (!sel) return;
-            if (tile_full && cnt == K && next_mask >= item0 + CH) {
-                // fast path (almost every chunk): no bounds, no mask, list already full
+        // One warp reads out 32 rows, so the steady state has to be cheap in ISSUE SLOTS: a 3-level max tree
+        // and one compare decide whether any of the chunk's 8 scores can enter this row's list; only then are
+        // the scores looked at one by one.  (Testing and appending every score individually cost ~20
+        // instructions per score: 13 000 clocks per tile against the 2 300 the tensor pipe needs - measured.)
+        auto consume = [&](const float* sc, int item0, bool tile_full) {
+            if (sel) {
+                if (tile_full && cnt == K && next_mask >= item0 + CH) {
+                    // fast path (almost every chunk): no bounds, no mask, list already full
+                    const float mx = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])),
+                                           fmaxf(fmaxf(sc[4], sc[5]), fmaxf(sc[6], sc[7])));
+                    if (mx > thr) {
 #pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                    const float sc = fmaf(b[i], LO_INV, a[i]);
-                    if (sc > thr) {
-                        csr[ncand * TM] = sc;
-                        cir[ncand * TM] = item0 + i;
-                        ++ncand;
+                        for (int i = 0; i < CH; ++i) {
+                            if (sc[i] > thr) {
+                                csr[ncand * TM] = sc[i];
+                                cir[ncand * TM] = item0 + i;
+                                ++ncand;
+                            }
+                        }
                     }
-                }
-            } else {
+                } else {
 #pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                    const int item = item0 + i;
-                    float sc = fmaf(b[i], LO_INV, a[i]);
-                    if (item == next_mask) {                // train item: score forced to 0.0 (metric.py:50)
-                        sc = 0.0f;
-                        do {
-                            ++mp;
-                            next_mask = mp < mend ? mask_items[mp] : INT_MAX;
-                        } while (next_mask == item);
-                    }
-                    if (item < n_items && (cnt < K || sc > thr)) {
-                        csr[ncand * TM] = sc;
-                        cir[ncand * TM] = item;
-                        ++ncand;
+                    for (int i = 0; i < CH; ++i) {
+                        const int item = item0 + i;
+                        float v = sc[i];
+                        if (item == next_mask) {            // train item: score forced to 0.0 (metric.py:50)
+                            v = 0.0f;
+                            do {
+                                ++mp;
+                                next_mask = mp < mend ? mask_items[mp] : INT_MAX;
+                            } while (next_mask == item);
+                        }
+                        if (item < n_items && (cnt < K || v > thr)) {
+                            csr[ncand * TM] = v;
+                            cir[ncand * TM] = item;
+                            ++ncand;
+                        }
                     }
                 }
             }
+            // when ANY row of the warp could overflow its buffer with the next chunk every row merges now
+            if (__any_sync(FULL_MASK, sel && ncand > CAP - CH)) flush();
         };
-        for (int it = it0; it < it1; ++it) {
-            const int n = it - it0, buf = n & 1;
-            if (!umma::mbar_wait(&acc_full[buf], (n >> 1) & 1)) { flags[0] = 1; flags[1] = 1; }
-            if (et == 0 && flags[0]) flags[1] = 1;
+        for (int it = it0 + grp; it < it1; it += N_GRP) {
+            const int n = it - it0, buf = n % N_ACC;
+            // no barrier between the read-out warps: each follows the accumulator barriers on its own
+            if (!umma::mbar_wait(&acc_full[buf], (n / N_ACC) & 1)) flags[0] = 1;
             umma::fence_after_sync();
-            asm volatile("bar.sync 1, %0;" ::"n"(N_EPI) : "memory");
-            if (flags[1]) break;
-            const uint32_t ta = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
+            if (flags[0]) break;
+            const uint32_t ta = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * TN;
             const bool tile_full = (it + 1) * TN <= n_items;
             const int item_tile = it * TN;
-            float a0[CH], b0[CH], a1[CH], b1[CH];            // chunk c + 1 loads while chunk c is consumed
-            umma::tmem_ld8(ta, a0);
-            umma::tmem_ld8(ta + 128, b0);
+            if (next_mask < item_tile) {                      // train items inside the other group's tiles
+                while (mp < mend && mask_items[mp] < item_tile) ++mp;
+                next_mask = mp < mend ? mask_items[mp] : INT_MAX;
+            }
+            float a0[16], a1[16];                            // columns c + 16.. load while columns c.. are consumed
+            umma::tmem_ld16(ta, a0);
 #pragma unroll 1
-            for (int c0 = 0; c0 < TN; c0 += 2 * CH) {
+            for (int c0 = 0; c0 < TN; c0 += 32) {
                 umma::tmem_ld_wait();
-                umma::tmem_ld8(ta + c0 + CH, a1);
-                umma::tmem_ld8(ta + 128 + c0 + CH, b1);
-                consume(a0, b0, item_tile + c0, tile_full);
+                umma::tmem_ld16(ta + c0 + 16, a1);
+                consume(a0, item_tile + c0, tile_full);
+                consume(a0 + 8, item_tile + c0 + 8, tile_full);
                 umma::tmem_ld_wait();
-                if (c0 + 2 * CH < TN) {
-                    umma::tmem_ld8(ta + c0 + 2 * CH, a0);
-                    umma::tmem_ld8(ta + 128 + c0 + 2 * CH, b0);
-                }
-                consume(a1, b1, item_tile + c0 + CH, tile_full);
+                if (c0 + 32 < TN) umma::tmem_ld16(ta + c0 + 32, a0);
+                consume(a1, item_tile + c0 + 16, tile_full);
+                consume(a1 + 8, item_tile + c0 + 24, tile_full);
             }
             umma::fence_before_sync();
             umma::mbar_arrive(&acc_empty[buf]);
         }
-        if (sel && !flags[1]) {
+        if (sel && !flags[0]) {
             flush();
-            const size_t o = (static_cast<size_t>(u0 + row) * S + sp) * K;
+            // selection sort of the K keys, largest first (once per row and kernel)
+            for (int p = 0; p < cnt; ++p) {
+                unsigned long long best = lkr[p * TM];
+                int bp = p;
+                for (int j = p + 1; j < cnt; ++j) {
+                    const unsigned long long k = lkr[j * TM];
+                    if (k > best) { best = k; bp = j; }
+                }
+                lkr[bp * TM] = lkr[p * TM];
+                lkr[p * TM] = best;
+            }
+            // the lists leave in SCALED units (s^2 u.i): the merge compares those, so that tiny embeddings whose
+            // true scores underflow fp32 still rank correctly; the merge converts the final scores
+            const size_t o = ((static_cast<size_t>(u0 + row) * S + sp) * N_GRP + grp) * K;
             for (int p = 0; p < K; ++p) {
                 const bool ok = p < cnt;
-                out_idx[o + p] = ok ? lir[p * TM] : -1;
-                if (out_score) out_score[o + p] = ok ? lsr[p * TM] : -INFINITY;
+                const unsigned long long k = ok ? lkr[p * TM] : 0ull;
+                out_idx[o + p] = ok ? key_index(k) : -1;
+                out_score[o + p] = ok ? key_score(k) : -INFINITY;
             }
         }
     }
@@ -367,39 +486,41 @@ score_topk_f16_kernel(const unsigned char* __restrict__ u_blob, const unsigned c
     if (warp == 1) umma::tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// S sorted lists per user (one per item range, ascending ranges) -> the user's top-K.  Equal scores keep the
-// entry of the lower range first and inside a range the lists are already index-ordered, so ties rank the
-// lower item index first, exactly as one list over the whole item axis would.
+// L sorted lists per user (one per item range and read-out group) -> the user's top-K: highest score first,
+// equal scores by lower item index - exactly what one list over the whole item axis would hold.
 __global__ void __launch_bounds__(128)
-topk_merge_kernel(const int32_t* __restrict__ part_idx, const float* __restrict__ part_score, int n_users, int S,
+topk_merge_kernel(const int32_t* __restrict__ part_idx, const float* __restrict__ part_score, int n_users, int L,
                   int K, int32_t* __restrict__ out_idx, float* __restrict__ out_score,
-                  const int* __restrict__ fallback) {
-    if (*reinterpret_cast<const volatile int*>(fallback)) return;
+                  const unsigned int* __restrict__ word) {
+    if (*reinterpret_cast<const volatile unsigned int*>(word + 1)) return;
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_users) return;
-    unsigned char ptr[S_MAX];
+    const float inv = 1.0f / operand_scale(word[0]);          // scores back to the caller's units: / s, twice
+    unsigned char ptr[L_MAX];
 #pragma unroll
-    for (int s = 0; s < S_MAX; ++s) ptr[s] = 0;
-    const size_t base = static_cast<size_t>(u) * S * K;
+    for (int s = 0; s < L_MAX; ++s) ptr[s] = 0;
+    const size_t base = static_cast<size_t>(u) * L * K;
     for (int k = 0; k < K; ++k) {
         int best = -1, best_idx = -1;
         float best_sc = -INFINITY;
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < L; ++s) {
             if (ptr[s] >= K) continue;
             const size_t o = base + static_cast<size_t>(s) * K + ptr[s];
             const int idx = part_idx[o];
             if (idx < 0) continue;
             const float sc = part_score[o];
-            if (best < 0 || sc > best_sc) { best = s; best_sc = sc; best_idx = idx; }
+            if (best < 0 || sc > best_sc || (sc == best_sc && idx < best_idx)) { best = s; best_sc = sc; best_idx = idx; }
         }
         out_idx[static_cast<size_t>(u) * K + k] = best_idx;
-        if (out_score) out_score[static_cast<size_t>(u) * K + k] = best >= 0 ? best_sc : -INFINITY;
+        if (out_score) out_score[static_cast<size_t>(u) * K + k] = best >= 0 ? best_sc * inv * inv : -INFINITY;
         if (best >= 0) ++ptr[best];
     }
 }
 
 __device__ int g_eval_f16_error = 0;      // a tensor-core / copy completion barrier timed out
-__device__ int g_eval_fallback[2] = {0, 0};   // [0] operands outside the fp16 range (per call), [1] fallbacks taken
+// [0] bits of max |x|, [1] fp32 kernel wanted (inf / NaN / dynamic range), [2] fallbacks taken, [3] bits of the
+// smallest non-zero chunk maximum; [0], [1], [3] are per call
+__device__ unsigned int g_eval_word[4] = {0, 0, 0, 0x7f800000u};
 
 inline size_t align1k(size_t x) { return (x + 1023) / 1024 * 1024; }
 
@@ -428,8 +549,8 @@ inline Plan make_plan(int64_t n_users, int64_t n_items, int dim, int K, int sms)
     size_t off = 0;
     p.u_blob = off; off += align1k(static_cast<size_t>(p.u_tiles) * p.nkb * BLK_BYTES);
     p.i_blob = off; off += align1k(static_cast<size_t>(p.i_tiles) * p.nkb * BLK_BYTES);
-    p.part_idx = off; off += align1k(static_cast<size_t>(n_users) * S_MAX * K * 4);
-    p.part_score = off; off += align1k(static_cast<size_t>(n_users) * S_MAX * K * 4);
+    p.part_idx = off; off += align1k(static_cast<size_t>(n_users) * L_MAX * K * 4);
+    p.part_score = off; off += align1k(static_cast<size_t>(n_users) * L_MAX * K * 4);
     p.total = off;
     return p;
 }
@@ -457,11 +578,11 @@ int kgat_eval_f16_error_take() {
 }
 
 int kgat_eval_fallbacks_take() {
-    int v[2] = {0, 0}, zero = 0;
-    if (cudaMemcpyFromSymbol(v, g_eval_fallback, sizeof(v)) != cudaSuccess) return KGAT_ERR_CUDA;
-    if (v[1] != 0 && cudaMemcpyToSymbol(g_eval_fallback, &zero, sizeof(int), sizeof(int)) != cudaSuccess)
+    unsigned int v[4] = {0, 0, 0, 0}, zero = 0;
+    if (cudaMemcpyFromSymbol(v, g_eval_word, sizeof(v)) != cudaSuccess) return KGAT_ERR_CUDA;
+    if (v[2] != 0 && cudaMemcpyToSymbol(g_eval_word, &zero, sizeof(int), 2 * sizeof(int)) != cudaSuccess)
         return KGAT_ERR_CUDA;
-    return v[1];
+    return static_cast<int>(v[2]);
 }
 
 int kgat_launch_score_topk_umma(const float* emb, int64_t emb_stride, int dim, const int32_t* user_ids, int n_users,
@@ -469,18 +590,19 @@ int kgat_launch_score_topk_umma(const float* emb, int64_t emb_stride, int dim, c
                                 const int32_t* mask_items, int K, int32_t* topk_idx, float* topk_score,
                                 int* only_if, cudaStream_t st);
 
-// split -> score + top-K per (user tile, item range) -> merge; the 3xTF32 kernel runs behind iff an operand
-// was outside the fp16 range (an empty launch otherwise)
+// max |x| -> split (pre-scaled fp16 pairs) -> score + top-K per (user tile, item range, read-out group) -> merge;
+// the 3xTF32 kernel runs behind iff an operand was inf / NaN (an empty launch otherwise)
 int kgat_launch_score_topk_f16(const float* emb, int64_t emb_stride, int dim, const int32_t* user_ids, int n_users,
                                const int32_t* item_ids, int n_items, const int32_t* mask_ptr,
                                const int32_t* mask_items, int K, int32_t* topk_idx, float* topk_score,
                                void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    static PerDevice<int*> err_words, fb_words;
+    static PerDevice<int*> err_words;
+    static PerDevice<unsigned int*> words;
     static PerDevice<size_t> smem_set;
     int*& err_word = err_words.get();
-    int*& fb_word = fb_words.get();
+    unsigned int*& word = words.get();
     if (!err_word) KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&err_word), g_eval_f16_error));
-    if (!fb_word) KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&fb_word), g_eval_fallback));
+    if (!word) KGAT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&word), g_eval_word));
     const Plan p = make_plan(n_users, n_items, dim, K, num_sms());
     if (workspace_bytes < p.total) return KGAT_ERR_WORKSPACE;
     const size_t smem = smem_bytes(p.nkb, K);
@@ -489,23 +611,25 @@ int kgat_launch_score_topk_f16(const float* emb, int64_t emb_stride, int dim, co
         smem_set.get() = smem;
     }
     unsigned char* ws = static_cast<unsigned char*>(workspace);
-    KGAT_CUDA(cudaMemsetAsync(fb_word, 0, sizeof(int), st));
+    KGAT_CUDA(cudaMemsetAsync(word, 0, 2 * sizeof(int), st));
+    KGAT_CUDA(cudaMemsetAsync(word + 3, 0x7f, sizeof(int), st));        // 0x7f7f7f7f: a huge finite float
     const int64_t chunks = static_cast<int64_t>(p.u_tiles + p.i_tiles) * p.nkb * 1024;
-    eval_split_kernel<<<static_cast<unsigned>((chunks + 255) / 256), 256, 0, st>>>(
-        emb, emb_stride, dim, user_ids, n_users, p.u_tiles, item_ids, n_items, p.i_tiles, p.nkb, ws + p.u_blob,
-        ws + p.i_blob, fb_word);
+    const unsigned pgrid = static_cast<unsigned>((chunks + 255) / 256);
+    eval_absmax_kernel<<<pgrid, 256, 0, st>>>(emb, emb_stride, dim, user_ids, n_users, p.u_tiles, item_ids, n_items,
+                                              p.i_tiles, p.nkb, word);
     KGAT_LAUNCH_CHECK();
-    int32_t* pidx = p.S > 1 ? reinterpret_cast<int32_t*>(ws + p.part_idx) : topk_idx;
-    float* pscore = p.S > 1 ? reinterpret_cast<float*>(ws + p.part_score) : topk_score;
+    eval_split_kernel<<<pgrid, 256, 0, st>>>(emb, emb_stride, dim, user_ids, n_users, p.u_tiles, item_ids, n_items,
+                                             p.i_tiles, p.nkb, ws + p.u_blob, ws + p.i_blob, word);
+    KGAT_LAUNCH_CHECK();
+    int32_t* pidx = reinterpret_cast<int32_t*>(ws + p.part_idx);
+    float* pscore = reinterpret_cast<float*>(ws + p.part_score);
     score_topk_f16_kernel<<<static_cast<unsigned>(p.u_tiles) * p.S, THREADS, smem, st>>>(
         ws + p.u_blob, ws + p.i_blob, n_users, n_items, p.nkb, p.n_ks, p.S, mask_ptr, mask_items, K, pidx, pscore,
-        err_word, fb_word);
+        err_word, word);
     KGAT_LAUNCH_CHECK();
-    if (p.S > 1) {
-        topk_merge_kernel<<<(n_users + 127) / 128, 128, 0, st>>>(pidx, pscore, n_users, p.S, K, topk_idx, topk_score,
-                                                                 fb_word);
-        KGAT_LAUNCH_CHECK();
-    }
+    topk_merge_kernel<<<(n_users + 127) / 128, 128, 0, st>>>(pidx, pscore, n_users, p.S * N_GRP, K, topk_idx, topk_score,
+                                                             word);
+    KGAT_LAUNCH_CHECK();
     return kgat_launch_score_topk_umma(emb, emb_stride, dim, user_ids, n_users, item_ids, n_items, mask_ptr, mask_items, K,
-                                       topk_idx, topk_score, fb_word, st);
+                                       topk_idx, topk_score, reinterpret_cast<int*>(word + 1), st);
 }
