@@ -63,7 +63,7 @@ constexpr int TARGET_EXP = 13;                    // operands are pre-scaled so 
 
 __host__ __device__ inline size_t smem_bytes(int nkb, int K) {
     return static_cast<size_t>(nkb) * BLK_BYTES + static_cast<size_t>(NSLOT) * ARR_BYTES +
-           static_cast<size_t>(N_GRP) * (K + CAP) * TM * 8 + 256;
+           static_cast<size_t>(N_GRP) * (K + CAP) * TM * 8 + N_GRP * TM * 4 + 256;
 }
 
 // instruction descriptor for kind::f16 with fp16 operands (a_format = b_format = 0), fp32 accumulate
@@ -241,7 +241,8 @@ score_topk_f16_kernel(const unsigned char* __restrict__ u_blob, const unsigned c
     unsigned long long* lk_all = reinterpret_cast<unsigned long long*>(sB + NSLOT * ARR_BYTES);   // per group: top-K keys [K][TM]
     float* cs_all = reinterpret_cast<float*>(lk_all + N_GRP * K * TM);    // per group: candidates [CAP][TM]
     int* ci_all = reinterpret_cast<int*>(cs_all + N_GRP * CAP * TM);
-    uint64_t* full = reinterpret_cast<uint64_t*>(ci_all + N_GRP * CAP * TM);   // [NSLOT]
+    float* thr_pub = reinterpret_cast<float*>(ci_all + N_GRP * CAP * TM);     // [N_GRP][TM] K-th best score per group and row
+    uint64_t* full = reinterpret_cast<uint64_t*>(thr_pub + N_GRP * TM);       // [NSLOT]
     uint64_t* empty = full + NSLOT;                                   // [NSLOT]
     uint64_t* acc_full = empty + NSLOT;                               // [N_ACC]
     uint64_t* acc_empty = acc_full + N_ACC;                           // [N_ACC]
@@ -353,6 +354,16 @@ score_topk_f16_kernel(const unsigned char* __restrict__ u_blob, const unsigned c
         float* const csr = cs_all + grp * CAP * TM + row;
         int* const cir = ci_all + grp * CAP * TM + row;
         int ncand = 0, minpos = 0;
+        // Both groups rank the SAME rows over disjoint tiles; the final list is the best K of their union, so a
+        // score below the OTHER group's K-th best can be dropped as well.  thr_own: K-th best of this group's list
+        // (candidates must beat it strictly: they come later in item order); thr: what the fast path tests,
+        // max(thr_own, just below the other group's published K-th best) - an equal score may still win its
+        // tie by index, so it is kept.
+        float thr_own = -INFINITY;
+        volatile float* const pub_mine = thr_pub + grp * TM + row;
+        volatile float* const pub_other = thr_pub + (grp ^ 1) * TM + row;
+        *pub_mine = -INFINITY;
+        asm volatile("bar.sync 1, %0;" ::"n"(N_GRP * N_EPI) : "memory");     // both groups have initialised
         // The row's K best so far are an UNSORTED set of 64-bit keys (order-preserving score bits, then the
         // complemented item index: the smallest key is the entry that ranks last - lowest score, and among
         // equal scores the highest index).  A candidate that beats the threshold replaces that entry and the
@@ -368,7 +379,12 @@ score_topk_f16_kernel(const unsigned char* __restrict__ u_blob, const unsigned c
                 if (k < mk) { mk = k; mp_ = p; }
             }
             minpos = mp_;
-            thr = key_score(mk);
+            thr_own = key_score(mk);
+            *pub_mine = thr_own;
+        };
+        auto refresh_thr = [&]() {
+            const float o = *pub_other;
+            thr = fmaxf(thr_own, o > -INFINITY ? nextafterf(o, -INFINITY) : o);
         };
         auto flush = [&]() {
             for (int t = 0; t < ncand; ++t) {
@@ -376,12 +392,13 @@ score_topk_f16_kernel(const unsigned char* __restrict__ u_blob, const unsigned c
                 if (cnt < K) {
                     lkr[cnt * TM] = make_key(sc, cir[t * TM]);
                     if (++cnt == K) rescan();
-                } else if (sc > thr) {
+                } else if (sc > thr_own) {
                     lkr[minpos * TM] = make_key(sc, cir[t * TM]);
                     rescan();
                 }
             }
             ncand = 0;
+            refresh_thr();
         };
         // One warp reads out 32 rows, so the steady state has to be cheap in ISSUE SLOTS: a 3-level max tree
         // and one compare decide whether any of the chunk's 8 scores can enter this row's list; only then are
