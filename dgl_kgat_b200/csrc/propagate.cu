@@ -268,22 +268,25 @@ layer_fwd_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict_
     }
     __syncthreads();
 
-    // phase 3: row norm, write un-normalised output and the normalised concat slice
+    // phase 3: row norm, write un-normalised output and the normalised concat slice - 128-bit accesses: lane l
+    // of the first DOUT / 4 lanes owns columns 4l .. 4l + 3 of the row (shared, global and peer stores alike)
+    constexpr int LPO = DOUT / 4;
     for (int rl = warp; rl < TM; rl += WARPS) {
         const int row = row0 + rl;
         if (row >= row_end) continue;
-        float ss = 0.f;
-        for (int j = lane; j < DOUT; j += 32) {
-            const float v = sY[rl * LDY + j];
-            ss = fmaf(v, v, ss);
-        }
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < LPO) v = *reinterpret_cast<const float4*>(sY + rl * LDY + lane * 4);
+        float ss = v.x * v.x;
+        ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
         ss = warp_sum(ss);
         const float denom = fmaxf(sqrtf(ss), NORM_EPS);
-        for (int j = lane; j < DOUT; j += 32) {
-            const float v = sY[rl * LDY + j];
-            h_out[static_cast<size_t>(row) * DOUT + j] = v;
-            if (PUSH) peer_store(po, static_cast<size_t>(row) * DOUT + j, v);
-            if (concat) concat[static_cast<size_t>(row) * cstride + out_off + j] = v / denom;
+        if (lane < LPO) {
+            const size_t o = static_cast<size_t>(row) * DOUT + lane * 4;
+            *reinterpret_cast<float4*>(h_out + o) = v;
+            if (PUSH) peer_store(po, o, v);
+            if (concat)
+                *reinterpret_cast<float4*>(concat + static_cast<size_t>(row) * cstride + out_off + lane * 4) =
+                    make_float4(v.x / denom, v.y / denom, v.z / denom, v.w / denom);
         }
     }
 }
@@ -482,17 +485,20 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                     mma_tf32_16x8x8(c, ah, bl);
                     mma_tf32_16x8x8(c, ah, bh);
                 }
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int row = row0 + 16 * mt + fg + 8 * half;
+                // pair the lanes (ft even, ft odd) so that each stores 128 bits: the even lane takes columns
+                // 8 nt + 2 ft .. + 3 of row fg (its own two and the partner's two), the odd lane those of row fg + 8
+                {
+                    const bool odd = ft & 1;
+                    const float s0 = odd ? c[0] : c[2], s1 = odd ? c[1] : c[3];
+                    const float r0 = __shfl_xor_sync(FULL_MASK, s0, 1), r1 = __shfl_xor_sync(FULL_MASK, s1, 1);
+                    const float4 d = odd ? make_float4(r0, r1, c[2], c[3]) : make_float4(c[0], c[1], r0, r1);
+                    const int row = row0 + 16 * mt + fg + (odd ? 8 : 0);
                     if (row < row_end) {
-                        const size_t o = static_cast<size_t>(row) * DIN + 8 * nt + 2 * ft;
-                        const float2 hn = __ldg(reinterpret_cast<const float2*>(h_nb + o));
-                        const float2 hi = __ldg(reinterpret_cast<const float2*>(h_in + o));
-                        const float d0 = c[2 * half], d1 = c[2 * half + 1];
-                        *reinterpret_cast<float2*>(dx_direct + o) = make_float2(d0 * hn.x, d1 * hn.y);
-                        const float2 dh = make_float2(d0 * hi.x, d1 * hi.y);
-                        *reinterpret_cast<float2*>(dh_nb + o) = dh;
+                        const size_t o = static_cast<size_t>(row) * DIN + 8 * nt + 4 * (ft >> 1);
+                        const float4 hn = ldg4(h_nb + o), hi = ldg4(h_in + o);
+                        *reinterpret_cast<float4*>(dx_direct + o) = make_float4(d.x * hn.x, d.y * hn.y, d.z * hn.z, d.w * hn.w);
+                        const float4 dh = make_float4(d.x * hi.x, d.y * hi.y, d.z * hi.z, d.w * hi.w);
+                        *reinterpret_cast<float4*>(dh_nb + o) = dh;
                         if (PUSH) peer_store(po, o, dh);
                     }
                 }

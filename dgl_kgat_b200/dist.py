@@ -349,11 +349,15 @@ class DistKGAT:
         with th.no_grad():
             if self.peer is not None:
                 # the softmax kernel writes this rank's slice of the all-edges vector (global CSR order)
-                # into every arena; after the barrier every rank holds the weights of ALL edges
+                # into every arena.  The forward pass only needs the weights of the OWN in-edges (local), so no
+                # barrier follows here: the peers' slices are first read when the CSC layout of the out-edges
+                # is built for the backward pass, and by then the barrier after the first layer's row exchange
+                # has already covered these stores (a release is cumulative over the stream) - one barrier less
+                # per step.  A single-layer model has no such barrier and gets an explicit one (finish_weights).
                 w_glob = self.peer.buf(("w",), (max(p.n_edges, 1),))[: p.n_edges]
                 _, w_csr = ops.attention(self.dg_in, m.entity_embed.weight, m.relation_embed.weight, m.W_R,
                                          rows=(p.r0, p.r1), want_eid=False, w_csr_out=w_glob[e0:e1], peer=self.peer)
-                self.peer.barrier()
+                w_csc = None
             else:
                 _, w_csr = ops.attention(self.dg_in, m.entity_embed.weight, m.relation_embed.weight, m.W_R,
                                          rows=(p.r0, p.r1), want_eid=False)
@@ -361,12 +365,13 @@ class DistKGAT:
                 w_glob = th.empty(p.n_edges, dtype=th.float32, device=self.device)
                 w_glob[e0:e1] = w_csr[: self.dg_in.n_edges]
                 exchange_rows(w_glob, p.edge_bounds, self.group)
-            _, w_csc = self.dg_out.edge_weights(w_glob[self._out_rank])
+                _, w_csc = self.dg_out.edge_weights(w_glob[self._out_rank])
         self._w_glob = w_glob
+        self._w_complete = self.peer is None
         self.w_full = None
         if self.peer is not None:
             self._plan = ops.PropagatePlan(self.dg_in, w_csr, w_csc, dg_bwd=self.dg_out, rows=(p.r0, p.r1),
-                                           peer=self.peer)
+                                           peer=self.peer, finish_weights=self._finish_weights)
         else:
             self._plan = ops.PropagatePlan(
                 self.dg_in, w_csr, w_csc, dg_bwd=self.dg_out, rows=(p.r0, p.r1),
@@ -374,8 +379,20 @@ class DistKGAT:
                 reduce=self._reduce_weight_grads)
         return self
 
+    def _finish_weights(self, barrier_done):
+        """Peer exchange: build the CSC layout of the out-edge weights once every rank's slice has arrived.
+        ``barrier_done``: a peer barrier has been enqueued since the softmax (the caller's row exchange)."""
+        with th.no_grad():
+            if not barrier_done:
+                self.peer.barrier()
+            self._w_complete = True
+            _, w_csc = self.dg_out.edge_weights(self._w_glob[self._out_rank])
+        return w_csc
+
     def attention_weights(self):
         """(E, 1) weights in original edge order (what Model.compute_attention returns)."""
+        if not self._w_complete:                      # peer exchange: the peers' slices need a barrier first
+            self._plan.w_csc = self._finish_weights(False)
         if self.w_full is None:
             self.w_full = self._w_glob[self._csr_rank].unsqueeze(1)
         return self.w_full

@@ -85,9 +85,13 @@ class PropagatePlan:
     is called: the exchanged buffers live in the arena, the ``*_push`` kernels store every owned row to
     all peers while they compute, and only a device-side barrier follows."""
 
-    def __init__(self, dg_fwd, w_csr, w_csc, dg_bwd=None, rows=None, exchange=None, reduce=None, peer=None):
+    def __init__(self, dg_fwd, w_csr, w_csc, dg_bwd=None, rows=None, exchange=None, reduce=None, peer=None,
+                 finish_weights=None):
         self.dg_fwd, self.dg_bwd = dg_fwd, dg_bwd if dg_bwd is not None else dg_fwd
         self.w_csr, self.w_csc = w_csr, w_csc
+        # peer exchange: w_csc (weights of the out-edges, heads owned by OTHER ranks) is built lazily, after a
+        # barrier that follows the softmax pushes: finish_weights(barrier_done) -> w_csc
+        self.finish_weights = finish_weights
         self.r0, self.r1 = (0, dg_fwd.n_nodes) if rows is None else rows
         self.exchange, self.reduce, self.peer = exchange, reduce, peer
 
@@ -164,10 +168,14 @@ class Propagate(th.autograd.Function):
                         _lib.check(lib.kgat_layer_fwd(*args, st), "kgat_layer_fwd")
                 if push:
                     peer.barrier()
+                    if plan.w_csc is None:          # this barrier also covered the peers' attention weights
+                        plan.w_csc = plan.finish_weights(True)
                 elif plan.distributed and l + 1 < L:
                     plan.exchange(h_out)
                 saved.append((h, h_nb, act, h_out))
                 h, off = h_out, off + d_out
+        if plan.w_csc is None and plan.finish_weights is not None:      # single-layer model: no row exchange above
+            plan.w_csc = plan.finish_weights(False)
         ctx.plan, ctx.masks, ctx.dims, ctx.single = plan, masks, dims, single_layer
         ctx.saved, ctx.weights, ctx.channel = saved, weights, channel
         ctx.generation = peer.generation if peer is not None else 0
