@@ -156,9 +156,11 @@ def algorithmic_bytes(N, E, R, dims):
     for l in range(len(dims) - 1):
         d_in, d_out = dims[l], dims[l + 1]
         out["layer_fwd_%dx%d" % (d_in, d_out)] = E * (8 + 4 * d_in) + N * 4 * d_in
-        # backward of layer l gathers the d_out-wide dh_nb of layer l+1 (none for the last layer)
-        gather = E * (8 + 4 * d_out) if l + 1 < len(dims) - 1 else 0
-        out["layer_bwd_%dx%d" % (d_in, d_out)] = gather + N * 4 * (4 * d_in + 3 * d_out)
+        # backward of layer l: the d_out-wide dh_nb of layer l+1 is gathered by csc_gather (none for the last
+        # layer), layer_bwd itself is the dense remainder
+        if l + 1 < len(dims) - 1:
+            out["csc_gather_%d" % d_out] = E * (8 + 4 * d_out) + N * 4 * 2 * d_out
+        out["layer_bwd_%dx%d" % (d_in, d_out)] = N * 4 * (4 * d_in + 3 * d_out)
     out["input_bwd_%d" % d0] = E * (8 + 4 * d0) + N * 4 * 3 * d0
     return out
 

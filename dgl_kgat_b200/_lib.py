@@ -60,6 +60,7 @@ SIGNATURES = {
                                  c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "kgat_input_bwd": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_i32p, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p,
                                  C.c_int, c_f32p, C.c_void_p]),
+    "kgat_csc_gather": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, C.c_void_p]),
     "kgat_bpr_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "kgat_bpr_loss_fwd": (C.c_int, [c_f32p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
                                     c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),

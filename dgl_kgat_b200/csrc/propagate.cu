@@ -629,6 +629,58 @@ reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int n
     }
 }
 
+// Transposed aggregation of one block of WARPS rows: warp w gathers row (first + w) over its CSC segment.
+// A row with more than LONG_ROW edges (a hot entity of a power-law KG) is gathered by ALL warps of the CTA
+// (gather_row_cta: fixed slices, partials added in warp order - deterministic) before the short rows, so no
+// single warp walks 10^4 edges while its CTA idles.  Returns this warp's row total (every lane group holds it).
+template <int D>
+__device__ __forceinline__ float4 gather_block_rows(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
+                                                    const float* __restrict__ w_csc, const float* __restrict__ feat,
+                                                    int first, int row_end, float4* sPart, int warp, int lane) {
+    const int row = first + warp;
+    int beg = 0, end = 0;
+    if (row < row_end) { beg = __ldg(csc_ptr + row); end = __ldg(csc_ptr + row + 1); }
+    const bool is_long = end - beg > LONG_ROW;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (__syncthreads_or(is_long ? 1 : 0)) {
+        for (int w = 0; w < WARPS; ++w) {                       // CTA-uniform: every thread re-reads the bounds
+            const int r = first + w;
+            if (r >= row_end) break;
+            const int b = __ldg(csc_ptr + r), e = __ldg(csc_ptr + r + 1);
+            if (e - b <= LONG_ROW) continue;
+            const float4 t = gather_row_cta<D>(csc_dst, w_csc, b, e, feat, sPart, warp, lane);
+            if (w == warp) g = t;
+        }
+    }
+    if (!is_long && row < row_end) g = gather_row<D>(csc_dst, w_csc, beg, end, feat, lane);
+    return g;
+}
+
+// out[v] = (add ? add[v] : 0) + sum_{k in CSC row v} w[k] * feat[dst[k]]: the gradient that reaches the output
+// of a layer through the NEXT layer (its direct term plus the transposed aggregation of its dh_nb).  A kernel
+// of its own in front of layer_bwd: as phase 1 of that kernel the gather ran at 4 CTAs per SM (64 registers,
+// persistent dW2 accumulators) in lockstep with the tile GEMMs - 0.235 ms for the 64 x 64 layer where this
+// kernel plus the dense remainder take less (measured, profiles/README.md).
+template <int D>
+__global__ void __launch_bounds__(THREADS)
+csc_gather_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
+                  const float* __restrict__ w_csc, int row_begin, int row_end, const float* __restrict__ add,
+                  const float* __restrict__ feat, float* __restrict__ out) {
+    constexpr int LP = D / 4;
+    __shared__ float4 sPart[WARPS * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int first = row_begin + blockIdx.x * WARPS, row = first + warp;
+    float4 g = gather_block_rows<D>(csc_ptr, csc_dst, w_csc, feat, first, row_end, sPart, warp, lane);
+    if (row < row_end && lane < LP) {
+        const size_t o = static_cast<size_t>(row) * D + lane * 4;
+        if (add) {
+            const float4 t = ldg4(add + o);
+            g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        }
+        *reinterpret_cast<float4*>(out + o) = g;
+    }
+}
+
 // d_entity[v] = d_concat[v, in_off:+D] + dx_direct[v] + sum_{k in CSC row v} w[k] * dh_nb[dst[k]]
 template <int D, bool PUSH>
 __global__ void __launch_bounds__(THREADS)
@@ -638,12 +690,11 @@ input_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                  int64_t in_off, const float* __restrict__ dx_direct, const float* __restrict__ dh_nb,
                  float* __restrict__ d_entity, PeerOut po) {
     constexpr int LP = D / 4;
-    const int lane = threadIdx.x & 31;
-    const int row = row_begin + blockIdx.x * WARPS + (threadIdx.x >> 5);
-    if (row >= row_end) return;
-    const int beg = __ldg(csc_ptr + row), end = __ldg(csc_ptr + row + 1);
-    float4 g = gather_row<D>(csc_dst, w_csc, beg, end, dh_nb, lane);
-    if (lane < LP) {
+    __shared__ float4 sPart[WARPS * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int first = row_begin + blockIdx.x * WARPS, row = first + warp;
+    float4 g = gather_block_rows<D>(csc_ptr, csc_dst, w_csc, dh_nb, first, row_end, sPart, warp, lane);
+    if (row < row_end && lane < LP) {
         const size_t o = static_cast<size_t>(row) * D + lane * 4;
         const float4 t = ldg4(dx_direct + o);
         g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
@@ -896,4 +947,26 @@ extern "C" int kgat_input_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t 
                               float* d_entity, kgat_stream_t stream) {
     return kgat_input_bwd_push(g, row_begin, row_end, d_concat, dc_row_slot, concat_stride, in_off, dx_direct, dh_nb,
                                w_csc, d, d_entity, nullptr, stream);
+}
+
+extern "C" int kgat_csc_gather(const kgat_graph_t* g, int64_t row_begin, int64_t row_end, const float* add,
+                               const float* feat, const float* w_csc, int d, float* out, kgat_stream_t stream) {
+    KGAT_REQUIRE(g && feat && out);
+    KGAT_REQUIRE(g->n_edges == 0 || w_csc);
+    KGAT_REQUIRE(row_begin >= 0 && row_end <= g->n_nodes && row_begin <= row_end);
+    KGAT_REQUIRE(aligned16(feat) && aligned16(out) && (!add || aligned16(add)));
+    if (row_begin == row_end) return KGAT_OK;
+    const int rows = static_cast<int>(row_end - row_begin);
+    const unsigned grid = (rows + WARPS - 1) / WARPS;
+    cudaStream_t st = as_stream(stream);
+#define LAUNCH(D)                                                                                          \
+    if (d == D) {                                                                                          \
+        csc_gather_kernel<D><<<grid, THREADS, 0, st>>>(g->csc_ptr, g->csc_dst, w_csc, (int)row_begin,      \
+                                                       (int)row_end, add, feat, out);                      \
+        KGAT_LAUNCH_CHECK();                                                                               \
+        return KGAT_OK;                                                                                    \
+    }
+    LAUNCH(128) LAUNCH(64) LAUNCH(32) LAUNCH(16) LAUNCH(8)
+#undef LAUNCH
+    return KGAT_ERR_UNSUPPORTED_DIM;
 }

@@ -5,12 +5,16 @@ number on the hot path is produced by the sm_100a kernels in ``csrc/``.
 """
 from __future__ import annotations
 
+import os
+
 import torch as th
 
 from . import _lib
 from .graph import DeviceGraph
 
 LEAKY_SLOPE = 0.01      # F.leaky_relu default used at reference models.py:66
+# KGAT_BWD_SPLIT=0 keeps the transposed aggregation inside layer_bwd (A/B measurements)
+SPLIT_BWD_GATHER = os.environ.get("KGAT_BWD_SPLIT", "1") != "0"
 
 
 def _f32c(t: th.Tensor, device) -> th.Tensor:
@@ -231,6 +235,16 @@ class Propagate(th.autograd.Function):
                 if ctx.single:
                     # bare KGATConv: the incoming gradient IS the gradient of the layer output
                     up_dx, up_dh = grad_out, None
+                elif nxt_dh is not None and SPLIT_BWD_GATHER:
+                    # the next layer's contribution to this layer's output gradient - its direct term plus the
+                    # transposed aggregation of its dh_nb - as a gather kernel of its own; layer_bwd then runs
+                    # its dense part only (nxt_dh_nb = NULL)
+                    gsum = th.empty(N, d_out, dtype=th.float32, device=dev)
+                    with _lib.record("csc_gather_%d" % d_out):
+                        _lib.check(lib.kgat_csc_gather(dg.ref, plan.r0, plan.r1, nxt_dx.data_ptr(), nxt_dh.data_ptr(),
+                                                       plan.w_csc.data_ptr(), d_out, gsum.data_ptr(), st),
+                                   "kgat_csc_gather")
+                    up_dx, up_dh = gsum, None
                 else:
                     up_dx, up_dh = nxt_dx, nxt_dh
                 with _lib.record("layer_bwd_%dx%d" % (d_in, d_out), 2):

@@ -168,6 +168,14 @@ KGAT_API int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t ro
 /* Gradient of the entity table (input of layer 0) for rows [row_begin,row_end):
  *   d_entity[v] = d_concat[v, in_off : in_off+d] + dx_direct[v]
  *               + sum_{k in CSC row v} w_csc[k] * dh_nb[csc_dst[k]] */
+/* (3c') transposed aggregation on its own: out[v] = (add ? add[v] : 0) + sum over the CSC row of v of
+ *       w_csc[k] * feat[csc_dst[k]], rows [row_begin, row_end), width d in {8, 16, 32, 64, 128} -- autograd of
+ *       update_all(u_mul_e, sum) (models.py:63; DGL's BackwardBinaryReduce with atomics), gather-only and
+ *       deterministic; rows above 512 edges are gathered by a whole CTA.  The host layer runs it in front of
+ *       kgat_layer_bwd (add = the next layer's dx_direct, feat = its dh_nb) and hands the sum to that call as
+ *       nxt_dx_direct with nxt_dh_nb = NULL. */
+KGAT_API int kgat_csc_gather(const kgat_graph_t* g, int64_t row_begin, int64_t row_end, const float* add,
+                    const float* feat, const float* w_csc, int d, float* out, kgat_stream_t stream);
 KGAT_API int kgat_input_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
                    const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride, int64_t in_off,
                    const float* dx_direct, const float* dh_nb, const float* w_csc, int d,
