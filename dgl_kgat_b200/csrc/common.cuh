@@ -82,9 +82,9 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // sum over the lanes of an aligned group of GROUP lanes (GROUP power of two <= 32)
 template <int GROUP>
-__device__ __forceinline__ float group_sum(float v) {
+__device__ __forceinline__ float group_sum(float v, unsigned mask = FULL_MASK) {
 #pragma unroll
-    for (int o = GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    for (int o = GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
     return v;
 }
 

@@ -360,10 +360,13 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
 
         // phase 1: dpre and z for every row of the tile
         // everything after the transposed aggregation: g = gathered next-layer term of this row
-        auto process_row = [&](int row, int rl, float4 g) {
+        // `ll`: this lane's index inside the group of lanes that shares the row (the whole warp when the row
+        // was gathered by the warp; LPR = max(DIN, DOUT) / 4 lanes when several rows share a warp)
+        // `gmask`: the lanes that share the row - the branches below are uniform across them, not across the warp
+        auto process_row = [&](int row, int rl, float4 g, int ll, unsigned gmask) {
             float4 dp = make_float4(0.f, 0.f, 0.f, 0.f), z = dp;
             if (row < row_end) {
-                const int lo = lane % LPO;
+                const int lo = ll % LPO;
                 const size_t oo = static_cast<size_t>(row) * DOUT + lo * 4;
                 if (nxt_dx_direct) {
                     const float4 t = ldg4(nxt_dx_direct + oo);
@@ -381,13 +384,13 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                     const float4 dc = ldg4(dcp);
                     float ss = y.x * y.x;
                     ss = fmaf(y.y, y.y, ss); ss = fmaf(y.z, y.z, ss); ss = fmaf(y.w, y.w, ss);
-                    ss = group_sum<LPO>(ss);
+                    ss = group_sum<LPO>(ss, gmask);
                     const float n = sqrtf(ss);
                     if (n >= NORM_EPS) {          // clamp_min passes the gradient to the norm
                         const float4 c = make_float4(y.x / n, y.y / n, y.z / n, y.w / n);
                         float dot = c.x * dc.x;
                         dot = fmaf(c.y, dc.y, dot); dot = fmaf(c.z, dc.z, dot); dot = fmaf(c.w, dc.w, dot);
-                        dot = group_sum<LPO>(dot);
+                        dot = group_sum<LPO>(dot, gmask);
                         g.x += (dc.x - c.x * dot) / n;
                         g.y += (dc.y - c.y * dot) / n;
                         g.z += (dc.z - c.z * dot) / n;
@@ -406,24 +409,37 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                 dp.y = a.y > 0.f ? g.y : g.y * slope;
                 dp.z = a.z > 0.f ? g.z : g.z * slope;
                 dp.w = a.w > 0.f ? g.w : g.w * slope;
-                const size_t oi = static_cast<size_t>(row) * DIN + (lane % LPI) * 4;
+                const size_t oi = static_cast<size_t>(row) * DIN + (ll % LPI) * 4;
                 const float4 x = ldg4(h_in + oi), hn = ldg4(h_nb + oi);
                 z = make_float4(x.x * hn.x, x.y * hn.y, x.z * hn.z, x.w * hn.w);
             }
-            if (lane < LPO) *reinterpret_cast<float4*>(sDP + rl * LDP + lane * 4) = dp;
-            if (lane < LPI) *reinterpret_cast<float4*>(sZ + rl * LDZ + lane * 4) = z;
+            if (ll < LPO) *reinterpret_cast<float4*>(sDP + rl * LDP + ll * 4) = dp;
+            if (ll < LPI) *reinterpret_cast<float4*>(sZ + rl * LDZ + ll * 4) = z;
         };
+        if (!nxt_dh_nb) {
+            // dense-only call (the transposed aggregation ran as csc_gather in front, or this is the last
+            // layer): no warp-wide gather, so a row needs only LPR = max(DIN, DOUT) / 4 lanes and 32 / LPR rows
+            // share a warp - twice (width 64) to four times (width 32) the loads in flight per warp and no
+            // lanes that merely duplicate their neighbours' work
+            constexpr int LPR = (LPI > LPO ? LPI : LPO);
+            constexpr int RPW = 32 / LPR;
+            const int sub = lane / LPR, ll = lane % LPR;
+            const unsigned gmask = (LPR == 32 ? FULL_MASK : ((1u << LPR) - 1u)) << (sub * LPR);
+            for (int rl = warp * RPW + sub; rl < TM; rl += WARPS * RPW)
+                process_row(row0 + rl, rl, make_float4(0.f, 0.f, 0.f, 0.f), ll, gmask);
+            __syncthreads();
+        } else {
         bool warp_long = false;
         for (int rl = warp; rl < TM; rl += WARPS) {
             const int row = row0 + rl;
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
             bool is_long = false;
-            if (row < row_end && nxt_dh_nb) {
+            if (row < row_end) {
                 const int beg = __ldg(csc_ptr + row), end = __ldg(csc_ptr + row + 1);
                 if (end - beg > LONG_ROW) is_long = true;
                 else g = gather_row<DOUT>(csc_dst, w_csc, beg, end, nxt_dh_nb, lane);
             }
-            if (!is_long) process_row(row, rl, g);
+            if (!is_long) process_row(row, rl, g, lane, FULL_MASK);
             if (lane == 0) sLong[rl] = is_long ? 1 : 0;
             warp_long |= is_long;
         }
@@ -434,9 +450,10 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                 const int row = row0 + rl;
                 const int beg = __ldg(csc_ptr + row), end = __ldg(csc_ptr + row + 1);
                 const float4 g = gather_row_cta<DOUT>(csc_dst, w_csc, beg, end, nxt_dh_nb, sPart, warp, lane);
-                if (warp == rl % WARPS) process_row(row, rl, g);
+                if (warp == rl % WARPS) process_row(row, rl, g, lane, FULL_MASK);
             }
             __syncthreads();
+        }
         }
 
         if constexpr (EPI == 1) {
