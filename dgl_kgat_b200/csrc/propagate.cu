@@ -312,8 +312,13 @@ struct BwdCfg {
     static constexpr size_t bytes = sizeof(float) * (DOUT * LDW + TM * LDP + TM * LDZ + COOP_FLOATS) + 16;
 };
 
+// resident CTAs per SM of the persistent grid (measured on B200: 5 beats 4 for the narrow layers - 51 registers
+// suffice -, 4 beats both 3 and 5 for 64 x 64, whose accumulators spill below 64 registers)
+template <int DIN, int DOUT>
+constexpr int bwd_ctas_per_sm() { return DIN * DOUT <= 2048 ? 5 : (DIN * DOUT <= 4096 ? 4 : 1); }
+
 template <int DIN, int DOUT, bool PUSH, int EPI>
-__global__ void __launch_bounds__(THREADS, (DIN * DOUT <= 4096 ? 4 : 1))   // persistent grid: 4 CTAs per SM (bwd_max_ctas)
+__global__ void __launch_bounds__(THREADS, (bwd_ctas_per_sm<DIN, DOUT>()))
 layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
                  const float* __restrict__ w_csc, int row_begin, int row_end, int n_tiles,
                  const float* __restrict__ d_concat, const int32_t* __restrict__ dc_slot, int64_t cstride,
@@ -787,7 +792,7 @@ struct BwdArgs {
     bool push; PeerOut po;
 };
 
-inline int bwd_max_ctas() { return 4 * num_sms(); }
+inline int bwd_max_ctas() { return 5 * num_sms(); }      // upper bound over the instantiations: sizes the partials
 
 // Tile GEMMs of layer_bwd: tensor cores (widths DIN >= 32, DOUT >= 16), single-GPU and partitioned (PUSH)
 // instantiations alike, so one GPU and N GPUs run the same arithmetic (tests/test_gpu_dist.py compares them
@@ -814,7 +819,8 @@ int launch_bwd_t(const BwdArgs& a) {
     }
     const int rows = a.row_end - a.row_begin;
     const int n_tiles = (rows + TM - 1) / TM;
-    const int grid = n_tiles < bwd_max_ctas() ? n_tiles : bwd_max_ctas();
+    const int cap = bwd_ctas_per_sm<DIN, DOUT>() * num_sms();
+    const int grid = n_tiles < cap ? n_tiles : cap;
     layer_bwd_kernel<DIN, DOUT, PUSH, EPI><<<grid, THREADS, smem, a.st>>>(
         a.g->csc_ptr, a.g->csc_dst, a.w_csc, a.row_begin, a.row_end, n_tiles, a.d_concat, a.dc_slot, a.cstride,
         a.out_off,
