@@ -26,6 +26,14 @@ class KgatGraph(C.Structure):
 
 GRAPH_ARRAYS = [name for name, _ in KgatGraph._fields_[3:]]
 
+
+class KgatRuns(C.Structure):
+    """Mirror of ``kgat_runs_t``."""
+    _fields_ = [(name, C.c_void_p) for name in ("bk_run", "run_ptr", "run_head", "rel_run_ptr", "n_runs")]
+
+
+RUN_ARRAYS = [name for name, _ in KgatRuns._fields_]
+
 MAX_RANKS = 8                   # KGAT_MAX_RANKS
 PEER_HEADER_BYTES = 1024        # KGAT_PEER_HEADER_BYTES
 IPC_HANDLE_BYTES = 64           # KGAT_IPC_HANDLE_BYTES
@@ -40,6 +48,7 @@ class KgatPeerGroup(C.Structure):
 # name -> (restype, argtypes); must list every KGAT_API symbol of the header
 _GP = C.POINTER(KgatGraph)
 _PG = C.POINTER(KgatPeerGroup)
+_RP = C.POINTER(KgatRuns)
 SIGNATURES = {
     "kgat_version": (C.c_int, []),
     "kgat_error_string": (C.c_char_p, [C.c_int]),
@@ -49,6 +58,9 @@ SIGNATURES = {
     "kgat_graph_build": (C.c_int, [_GP, c_i32p, c_i32p, c_i32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kgat_attention_logits": (C.c_int, [_GP, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     "kgat_attention_fallbacks": (C.c_int, []),
+    "kgat_runs_build_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "kgat_runs_build": (C.c_int, [_GP, _RP, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kgat_attention_logits_runs": (C.c_int, [_GP, _RP, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     "kgat_segment_softmax": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "kgat_edge_weights_from_eid": (C.c_int, [_GP, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "kgat_layer_fwd": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int,

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libkgat_b200.so")
-SOURCES = ["graph_build.cu", "attention.cu", "attention_umma.cu", "attention_umma16.cu", "propagate.cu", "bpr.cu", "transr.cu", "adam.cu", "peer.cu", "eval.cu", "eval_umma.cu", "eval_f16.cu", "selftest.cu"]
+SOURCES = ["graph_build.cu", "attention.cu", "attention_umma.cu", "attention_umma16.cu", "attention_runs.cu", "propagate.cu", "bpr.cu", "transr.cu", "adam.cu", "peer.cu", "eval.cu", "eval_umma.cu", "eval_f16.cu", "selftest.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
          "--expt-relaxed-constexpr"]

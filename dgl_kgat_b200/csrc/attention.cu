@@ -260,6 +260,9 @@ int kgat_launch_att_logits_umma(const kgat_graph_t* g, const float* entity, cons
 int kgat_launch_att_logits_umma16(const kgat_graph_t* g, const float* entity, const float* rel_emb,
                                   const float* W_R, float* logits_csr, int* fallback, cudaStream_t st);
 int kgat_launch_att_range(const float* W_R, int64_t n, int* word, cudaStream_t st);
+int kgat_launch_att_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
+                                const float* rel_emb, const float* W_R, float* logits_csr, int* fallback,
+                                cudaStream_t st);
 int* kgat_att_fallback_word();
 
 // KGAT_ATT_IMPL selects the kernel for d = rd = 64 (A/B runs): "f16" (default) tcgen05 split-fp16,
@@ -315,6 +318,25 @@ extern "C" int kgat_attention_logits(const kgat_graph_t* g, const float* entity,
     }
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
+}
+
+extern "C" int kgat_attention_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
+                                          const float* rel_emb, const float* W_R, int d, int rd, float* logits_csr,
+                                          kgat_stream_t stream) {
+    KGAT_REQUIRE(g && runs && entity && rel_emb && W_R && logits_csr);
+    KGAT_REQUIRE(runs->bk_run && runs->run_ptr && runs->run_head && runs->rel_run_ptr && runs->n_runs);
+    KGAT_REQUIRE(aligned16(entity) && aligned16(rel_emb) && aligned16(W_R));
+    if (d != 64 || rd != 64 || g->n_rel > 1024) return KGAT_ERR_UNSUPPORTED_DIM;
+    if (g->n_edges == 0) return KGAT_OK;
+    cudaStream_t st = as_stream(stream);
+    // same three-launch range protocol as kgat_attention_logits: range word, fp16 kernel, fp32-range kernel iff needed
+    int* word = kgat_att_fallback_word();
+    if (!word) return KGAT_ERR_CUDA;
+    int rc = kgat_launch_att_range(W_R, g->n_rel * static_cast<int64_t>(d) * rd, word, st);
+    if (rc != KGAT_OK) return rc;
+    rc = kgat_launch_att_logits_runs(g, runs, entity, rel_emb, W_R, logits_csr, word, st);
+    if (rc != KGAT_OK) return rc;
+    return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, word, st);
 }
 
 extern "C" int kgat_segment_softmax_push(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,

@@ -50,6 +50,22 @@ class DeviceGraph:
     def ref(self):
         return ctypes.byref(self.struct)
 
+    def runs(self):
+        """(head, relation) runs of the relation buckets (``kgat_runs_build``), built on first use."""
+        if getattr(self, "_runs", None) is None:
+            lib = _lib.load()
+            E, R = self.n_edges, self.n_rel
+            with th.cuda.device(self.device):
+                sizes = {"bk_run": max(E, 1), "run_ptr": E + 1, "run_head": max(E, 1), "rel_run_ptr": R + 1, "n_runs": 1}
+                self.run_arrays = {n: th.zeros(sizes[n], dtype=th.int32, device=self.device) for n in _lib.RUN_ARRAYS}
+                self._runs = _lib.KgatRuns(*[self.run_arrays[n].data_ptr() for n in _lib.RUN_ARRAYS])
+                ws_bytes = lib.kgat_runs_build_workspace_bytes(E)
+                ws = th.empty(max(ws_bytes, 16), dtype=th.uint8, device=self.device)
+                _lib.check(lib.kgat_runs_build(self.ref, ctypes.byref(self._runs), ws.data_ptr(), ws_bytes,
+                                               _lib.stream_ptr()), "kgat_runs_build")
+                th.cuda.current_stream().synchronize()      # ws must outlive the build
+        return ctypes.byref(self._runs)
+
     def edge_weights(self, w_eid: th.Tensor):
         """(w_csr, w_csc) for an (E,) or (E,1) weight tensor given in edge-id order."""
         lib = _lib.load()

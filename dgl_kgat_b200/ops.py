@@ -55,9 +55,18 @@ def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Te
     r0, r1 = (0, dg.n_nodes) if rows is None else rows
     with th.cuda.device(dev):
         st = _lib.stream_ptr()
-        with _lib.record("attention_logits"):
-            _lib.check(lib.kgat_attention_logits(dg.ref, entity.data_ptr(), rel_emb.data_ptr(), W_R.data_ptr(),
-                                                 d, rd, logits.data_ptr(), st), "kgat_attention_logits")
+        # default for 64-wide embeddings: the (head, relation)-run shortcut; KGAT_ATT_IMPL = f16 / tf32 / ffma select
+        # the per-edge kernels (A/B runs)
+        use_runs = d == 64 and rd == 64 and dg.n_rel <= 1024 and os.environ.get("KGAT_ATT_IMPL", "runs") == "runs"
+        runs = dg.runs() if use_runs else None           # built (and synchronised) once per graph, outside any capture
+        with _lib.record("attention_logits", 3):
+            if use_runs:
+                _lib.check(lib.kgat_attention_logits_runs(dg.ref, runs, entity.data_ptr(), rel_emb.data_ptr(),
+                                                          W_R.data_ptr(), d, rd, logits.data_ptr(), st),
+                           "kgat_attention_logits_runs")
+            else:
+                _lib.check(lib.kgat_attention_logits(dg.ref, entity.data_ptr(), rel_emb.data_ptr(), W_R.data_ptr(),
+                                                     d, rd, logits.data_ptr(), st), "kgat_attention_logits")
         with _lib.record("segment_softmax"):
             we = w_eid.data_ptr() if (want_eid and dg.n_edges) else None
             if peer is not None:

@@ -112,6 +112,31 @@ KGAT_API int kgat_attention_logits(const kgat_graph_t* g, const float* entity, c
  * last call of this function (then cleared).  Synchronises the device. */
 KGAT_API int kgat_attention_fallbacks(void);
 
+/* (2') the same logits through the (head, relation)-run shortcut:
+ *      pi(h,r,t) = e_t . (W_r tanh(e_h W_r + e_r)), and the bracket depends on (h, r) only.  Inside a relation
+ *      bucket the edges are head-sorted, so the edges of one (h, r) pair - a run - are contiguous.
+ *      kgat_runs_build derives the runs from a built graph, once per graph (deterministic; bit-exact against
+ *      oracle/graph_ref.build_runs): bk_run[p] = run of bucket position p, run_ptr[k] = first bucket position of
+ *      run k (run_ptr[n_runs] = E), run_head[k] = its head node, rel_run_ptr[r] = first run of relation r,
+ *      n_runs[0] = the run count (device scalar).  The caller allocates bk_run[E], run_ptr[E + 1], run_head[E],
+ *      rel_run_ptr[n_rel + 1], n_runs[1].
+ *      kgat_attention_logits_runs computes two 64 x 64 mat-vecs per RUN on the tensor cores (tcgen05 split-fp16
+ *      grouped GEMMs over 128-run tiles) and a 64-wide dot per edge; d = rd = 64 only (KGAT_ERR_UNSUPPORTED_DIM
+ *      otherwise), same operand-range protocol and fallback as kgat_attention_logits. */
+typedef struct kgat_runs_t {
+    int32_t *bk_run;        /* [E] */
+    int32_t *run_ptr;       /* [E+1] */
+    int32_t *run_head;      /* [E] */
+    int32_t *rel_run_ptr;   /* [n_rel+1] */
+    int32_t *n_runs;        /* [1] */
+} kgat_runs_t;
+KGAT_API size_t kgat_runs_build_workspace_bytes(int64_t n_edges);
+KGAT_API int kgat_runs_build(const kgat_graph_t* g, const kgat_runs_t* runs, void* workspace, size_t workspace_bytes,
+                    kgat_stream_t stream);
+KGAT_API int kgat_attention_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
+                               const float* rel_emb, const float* W_R, int d, int rd, float* logits_csr,
+                               kgat_stream_t stream);
+
 /* (3a) softmax over the in-edges of every destination row -- replaces
  *      edge_softmax (models.py:153).  Rows [row_begin,row_end).  Writes the weights
  *      in CSR order and, when non-null, scattered to original edge-id order

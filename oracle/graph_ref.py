@@ -65,3 +65,23 @@ def partition_rows(csr_ptr: np.ndarray, n_parts: int) -> np.ndarray:
     b = np.searchsorted(csr_ptr, targets, side="left").astype(np.int64)
     b[0], b[-1] = 0, len(csr_ptr) - 1
     return np.maximum.accumulate(b)
+
+
+def build_runs(struct, n_rel):
+    """(head, relation) runs of the relation buckets: maximal groups of consecutive bucket positions with the
+    same relation and head (the bucket order is relation, head, edge id).  Restates what
+    kgat_runs_build produces: bk_run, run_ptr (n_runs + 1 entries), run_head, rel_run_ptr, n_runs."""
+    import numpy as np
+    bk_pos, bk_head, rel_ptr = struct["bk_pos"], struct["bk_head"], struct["rel_ptr"]
+    E = len(bk_pos)
+    rel = struct["csr_rel"][bk_pos] if E else np.zeros(0, np.int32)
+    flags = np.ones(E, dtype=np.int32)
+    if E > 1:
+        flags[1:] = ((bk_head[1:] != bk_head[:-1]) | (rel[1:] != rel[:-1])).astype(np.int32)
+    bk_run = (np.cumsum(flags) - 1).astype(np.int32)
+    n_runs = int(flags.sum())
+    starts = np.flatnonzero(flags).astype(np.int32)
+    run_ptr = np.append(starts, E).astype(np.int32)
+    run_head = bk_head[starts].astype(np.int32) if E else np.zeros(0, np.int32)
+    rel_run_ptr = np.array([bk_run[p] if p < E else n_runs for p in rel_ptr[: n_rel + 1]], dtype=np.int32)
+    return {"bk_run": bk_run, "run_ptr": run_ptr, "run_head": run_head, "rel_run_ptr": rel_run_ptr, "n_runs": n_runs}

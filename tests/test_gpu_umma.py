@@ -75,7 +75,7 @@ def test_attention_umma_vs_ffma_vs_oracle(dev):
     g = CKGraph(N, trip, n_rel=R)
     w64 = kgat_ref.compute_attention({k: v.detach().cpu().double() for k, v in m.state_dict().items()}, trip, N).numpy()
     out = {}
-    for impl in ("ffma", "tf32", "f16"):
+    for impl in ("ffma", "tf32", "f16", "runs"):
         os.environ["KGAT_ATT_IMPL"] = impl
         try:
             w = m.compute_attention(g).cpu().numpy().astype(np.float64)
@@ -105,14 +105,19 @@ def test_attention_logits_precision_by_magnitude(dev, scale):
     dg = g.device_graph(dev)
     eid = dg.arrays["csr_eid"].cpu().numpy().astype(np.int64)
     out = {}
-    for impl in ("ffma", "tf32", "f16"):
+    for impl in ("ffma", "tf32", "f16", "runs"):
         os.environ["KGAT_ATT_IMPL"] = impl
         try:
             lib = _lib.load()
             logits = th.empty(len(trip), device=dev)
-            _lib.check(lib.kgat_attention_logits(dg.ref, m.entity_embed.weight.data_ptr(),
-                                                 m.relation_embed.weight.data_ptr(), m.W_R.data_ptr(), 64, 64,
-                                                 logits.data_ptr(), _lib.stream_ptr()), "kgat_attention_logits")
+            if impl == "runs":
+                _lib.check(lib.kgat_attention_logits_runs(dg.ref, dg.runs(), m.entity_embed.weight.data_ptr(),
+                                                          m.relation_embed.weight.data_ptr(), m.W_R.data_ptr(), 64, 64,
+                                                          logits.data_ptr(), _lib.stream_ptr()), "kgat_attention_logits_runs")
+            else:
+                _lib.check(lib.kgat_attention_logits(dg.ref, m.entity_embed.weight.data_ptr(),
+                                                     m.relation_embed.weight.data_ptr(), m.W_R.data_ptr(), 64, 64,
+                                                     logits.data_ptr(), _lib.stream_ptr()), "kgat_attention_logits")
             th.cuda.synchronize()
         finally:
             os.environ.pop("KGAT_ATT_IMPL", None)
@@ -157,7 +162,7 @@ def test_attention_operand_range_guard(dev, case):
     assert lib.kgat_umma_error_flag() == 0
 
 
-@pytest.mark.parametrize("impl", ["tf32", "f16"])
+@pytest.mark.parametrize("impl", ["tf32", "f16", "runs"])
 def test_attention_umma_ragged_tiles(dev, impl, monkeypatch):
     """Relation buckets that are empty, smaller than a tile, or one edge over a tile boundary."""
     monkeypatch.setenv("KGAT_ATT_IMPL", impl)
@@ -299,3 +304,57 @@ def test_eval_f16_range_guard(dev, outlier, expect_fallback):
             tol = 2e-6 * np.abs(s).max()
             assert np.allclose(np.sort(s[got[j]])[::-1], s[want[j]], rtol=0, atol=tol), j
     assert lib.kgat_umma_error_flag() == 0
+
+
+@pytest.mark.parametrize("case", ["tiny", "multigraph", "single_edge", "empty", "hot_pairs", "many_relations"])
+def test_runs_structure_bit_exact_and_logits(dev, case):
+    """(head, relation) runs (kgat_runs_build) bit-exact against the numpy restatement, and the run-shortcut
+    logits on the same graph against the fp64 oracle: runs of one edge, runs far longer than a 16-edge batch of the
+    edge walk, runs that straddle the 32-run slices of the read-out warps, empty relations."""
+    from oracle import graph_ref
+    rng = np.random.default_rng(3)
+    if case == "tiny":
+        ck = synth_ckg("tiny")
+        trip, N, R = ck.triplets, ck.cfg.n_nodes, ck.cfg.n_relations
+    elif case == "multigraph":
+        trip = np.array([(1, 0, 2), (1, 0, 2), (1, 1, 2), (2, 1, 1), (1, 0, 2), (0, 2, 0)], np.int32)
+        N, R = 4, 3
+    elif case == "single_edge":
+        trip, N, R = np.array([(3, 1, 0)], np.int32), 5, 2
+    elif case == "empty":
+        trip, N, R = np.zeros((0, 3), np.int32), 5, 2
+    elif case == "hot_pairs":            # few distinct (head, relation) pairs, hundreds of edges each
+        E = 20000
+        trip = np.stack([rng.integers(0, 40, E), rng.integers(0, 3, E), rng.integers(0, 3000, E)], 1).astype(np.int32)
+        N, R = 3000, 4
+    else:                                # runs of ~1 edge, 300 relations (most tiles are partial), some empty
+        E = 30000
+        trip = np.stack([rng.integers(0, 5000, E), rng.integers(0, 300, E) * 3 % 301, rng.integers(0, 5000, E)], 1).astype(np.int32)
+        N, R = 5000, 301
+    g = CKGraph(N, trip, n_rel=R)
+    dg = g.device_graph(dev)
+    dg.runs()
+    want = graph_ref.build_runs({k: v.cpu().numpy() for k, v in dg.arrays.items()}, R)
+    n_runs = int(dg.run_arrays["n_runs"].item())
+    assert n_runs == want["n_runs"]
+    E = len(trip)
+    assert np.array_equal(dg.run_arrays["bk_run"].cpu().numpy()[:E], want["bk_run"])
+    assert np.array_equal(dg.run_arrays["run_ptr"].cpu().numpy()[: n_runs + 1], want["run_ptr"])
+    assert np.array_equal(dg.run_arrays["run_head"].cpu().numpy()[:n_runs], want["run_head"])
+    assert np.array_equal(dg.run_arrays["rel_run_ptr"].cpu().numpy(), want["rel_run_ptr"])
+    if E == 0:
+        return
+    th.manual_seed(9)
+    m = models.Model(True, 64, "kgat", 1, 64, 0.0, n_entities=N, n_relations=R, relation_dim=64).to(dev)
+    sd = {k: v.detach().cpu().double() for k, v in m.state_dict().items()}
+    ref = kgat_ref.att_logits(sd, trip).numpy().reshape(-1)
+    logits = th.empty(E, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.kgat_attention_logits_runs(dg.ref, dg.runs(), m.entity_embed.weight.data_ptr(),
+                                              m.relation_embed.weight.data_ptr(), m.W_R.data_ptr(), 64, 64,
+                                              logits.data_ptr(), _lib.stream_ptr()), "kgat_attention_logits_runs")
+    th.cuda.synchronize()
+    eid = dg.arrays["csr_eid"].cpu().numpy().astype(np.int64)[:E]
+    got = logits.cpu().numpy().astype(np.float64)
+    assert float(np.abs(got - ref[eid]).max() / np.abs(ref).max()) < 1e-5
+    assert lib.kgat_umma_error_flag() == 0 and lib.kgat_attention_fallbacks() == 0
