@@ -60,7 +60,8 @@ SIGNATURES = {
     "kgat_attention_fallbacks": (C.c_int, []),
     "kgat_runs_build_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "kgat_runs_build": (C.c_int, [_GP, _RP, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "kgat_attention_logits_runs": (C.c_int, [_GP, _RP, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, C.c_void_p]),
+    "kgat_attention_logits_runs": (C.c_int, [_GP, _RP, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p,
+                                             C.c_void_p]),
     "kgat_segment_softmax": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "kgat_edge_weights_from_eid": (C.c_int, [_GP, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "kgat_layer_fwd": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int,

@@ -261,7 +261,7 @@ int kgat_launch_att_logits_umma16(const kgat_graph_t* g, const float* entity, co
                                   const float* W_R, float* logits_csr, int* fallback, cudaStream_t st);
 int kgat_launch_att_range(const float* W_R, int64_t n, int* word, cudaStream_t st);
 int kgat_launch_att_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
-                                const float* rel_emb, const float* W_R, float* logits_csr, int* fallback,
+                                const float* rel_emb, const float* W_R, float* logits_csr, float* v_rows, int* fallback,
                                 cudaStream_t st);
 int* kgat_att_fallback_word();
 
@@ -322,7 +322,7 @@ extern "C" int kgat_attention_logits(const kgat_graph_t* g, const float* entity,
 
 extern "C" int kgat_attention_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
                                           const float* rel_emb, const float* W_R, int d, int rd, float* logits_csr,
-                                          kgat_stream_t stream) {
+                                          float* v_rows, kgat_stream_t stream) {
     KGAT_REQUIRE(g && runs && entity && rel_emb && W_R && logits_csr);
     KGAT_REQUIRE(runs->bk_run && runs->run_ptr && runs->run_head && runs->rel_run_ptr && runs->n_runs);
     KGAT_REQUIRE(aligned16(entity) && aligned16(rel_emb) && aligned16(W_R));
@@ -334,7 +334,8 @@ extern "C" int kgat_attention_logits_runs(const kgat_graph_t* g, const kgat_runs
     if (!word) return KGAT_ERR_CUDA;
     int rc = kgat_launch_att_range(W_R, g->n_rel * static_cast<int64_t>(d) * rd, word, st);
     if (rc != KGAT_OK) return rc;
-    rc = kgat_launch_att_logits_runs(g, runs, entity, rel_emb, W_R, logits_csr, word, st);
+    KGAT_REQUIRE(!v_rows || aligned16(v_rows));
+    rc = kgat_launch_att_logits_runs(g, runs, entity, rel_emb, W_R, logits_csr, v_rows, word, st);
     if (rc != KGAT_OK) return rc;
     return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, word, st);
 }

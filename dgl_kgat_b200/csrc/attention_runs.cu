@@ -64,6 +64,7 @@ struct Smem {
     uint64_t acc1_full[NTS], a2_full[NTS], acc2_full[NTS], slot_empty[NTS];
     uint64_t b_free, b_full, drain;
     uint32_t tmem_base;
+    int t_range[2];
     volatile int abort_flag;
     volatile int skip;
 };
@@ -125,7 +126,7 @@ att_logits_runs_kernel(const int32_t* __restrict__ rel_run_ptr, int n_rel, const
                        const int32_t* __restrict__ bk_tail, const int32_t* __restrict__ bk_pos,
                        const float* __restrict__ ent, const float* __restrict__ rel_emb,
                        const float* __restrict__ W_R, float* __restrict__ logits_csr,
-                       int* __restrict__ err, int* __restrict__ fallback) {
+                       float* __restrict__ v_out, int* __restrict__ err, int* __restrict__ fallback) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -178,9 +179,40 @@ att_logits_runs_kernel(const int32_t* __restrict__ rel_run_ptr, int n_rel, const
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = s.tmem_base;
-    const int n_tiles = s.prefix[n_rel];
-    const int t0 = static_cast<int>(static_cast<long long>(n_tiles) * blockIdx.x / gridDim.x);
-    const int t1 = static_cast<int>(static_cast<long long>(n_tiles) * (blockIdx.x + 1) / gridDim.x);
+    // Contiguous tile ranges of equal COST, not equal tile count: a tile is 128 runs, but its edge walk is
+    // proportional to its edges, and the runs of one relation can be 20 x longer than those of another (every item
+    // row of the interaction relation vs a KG relation) - with equal counts the two CTAs that got the item
+    // relation ran 13 x longer than the rest (measured: 4.5 ms instead of 0.35).  cost(boundary k) = RUN_COST *
+    // runs before tile k + edges before tile k, monotone in k: two binary searches per CTA.
+    if (tid == 0) {
+        const int n_tiles = s.prefix[n_rel];
+        const long long RUN_COST = v_out ? 1000 : 3;       // split mode: no edge walk in this kernel
+        auto runs_before = [&](int k) {                    // global index of the first run of tile k
+            if (k >= n_tiles) return s.rstart[n_rel];
+            int lo = 0, hi = n_rel - 1;                    // last relation with prefix[rel] <= k
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s.prefix[mid] <= k) lo = mid; else hi = mid - 1;
+            }
+            return s.rstart[lo] + (k - s.prefix[lo]) * TILE;
+        };
+        auto cost_at = [&](int k) {
+            const int r = runs_before(k);
+            return RUN_COST * r + static_cast<long long>(__ldg(run_ptr + r));
+        };
+        const long long total = cost_at(n_tiles);
+        for (int side = 0; side < 2; ++side) {
+            const long long target = total * (blockIdx.x + side) / gridDim.x;
+            int lo = 0, hi = n_tiles;                      // smallest k with cost_at(k) >= target
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cost_at(mid) >= target) hi = mid; else lo = mid + 1;
+            }
+            s.t_range[side] = (blockIdx.x + side == gridDim.x) ? n_tiles : lo;
+        }
+    }
+    __syncthreads();
+    const int t0 = s.t_range[0], t1 = s.t_range[1];
 
     if (warp < 4) {
         // =========================================================== producers (head rows of the runs, W_r)
@@ -399,10 +431,18 @@ att_logits_runs_kernel(const int32_t* __restrict__ rel_run_ptr, int n_rel, const
                 }
             }
             __syncwarp();
-            // ---- step 3: the edges of this warp's 32 runs; 16 lanes per edge
             const int w_first = ti.r0 + q * 32;
             const int w_last = min(w_first + 32, ti.r0 + ti.n_r);
-            if (w_first < w_last) {
+            if (v_out) {
+                // ---- step 3 (split mode): v rows -> global memory, coalesced (16 lanes per 256-byte row); the edge
+                // dots run as a kernel of their own at full occupancy (edge_dot_kernel)
+                for (int r = w_first + half; r < w_last; r += 2) {
+                    const int rl = r - ti.r0;
+                    const float4 vv = *reinterpret_cast<const float4*>(V + rl * D + ((l16 ^ (rl & 15)) << 2));
+                    *reinterpret_cast<float4*>(v_out + static_cast<size_t>(r) * D + l16 * 4) = vv;
+                }
+            } else if (w_first < w_last) {
+                // ---- step 3 (fused mode): the edges of this warp's 32 runs; 16 lanes per edge
                 const int e_beg = __ldg(run_ptr + w_first), e_end = __ldg(run_ptr + w_last);
                 // lane L < 16 holds the metadata of edge pbase + L of the current batch of 16
                 int m_tail = 0, m_run = 0, m_pos = -1;
@@ -453,6 +493,44 @@ att_logits_runs_kernel(const int32_t* __restrict__ rel_run_ptr, int n_rel, const
     __syncthreads();
     if (tid == 0 && s.abort_flag) atomicExch(err, 1);
     if (warp == MMA_WARP) umma::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// logit[bk_pos[p]] = e_tail(p) . v[bk_run[p]]  for every bucket position p: 16 lanes per edge (128-bit coalesced row
+// reads), 4 edges per lane group in flight, 16-lane shuffle reduction.  The v rows of consecutive edges are the same
+// row for a whole run, so their reads are L1 / L2 hits.
+__global__ void __launch_bounds__(256)
+edge_dot_kernel(const int32_t* __restrict__ bk_run, const int32_t* __restrict__ bk_tail,
+                const int32_t* __restrict__ bk_pos, int64_t E, const float* __restrict__ ent,
+                const float* __restrict__ v, float* __restrict__ logits_csr, int* __restrict__ fallback) {
+    const int l16 = threadIdx.x & 15;
+    const int64_t grp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 4;
+    const int64_t p0 = grp * 4;
+    if (p0 >= E) return;                                  // whole 16-lane groups leave together
+    int tail[4], run[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool ok = p0 + j < E;
+        tail[j] = ok ? __ldg(bk_tail + p0 + j) : 0;
+        run[j] = ok ? __ldg(bk_run + p0 + j) : 0;
+    }
+    float4 a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        a[j] = ldg4(ent + static_cast<size_t>(tail[j]) * D + l16 * 4);
+        b[j] = ldg4(v + static_cast<size_t>(run[j]) * D + l16 * 4);
+    }
+    const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float p = a[j].x * b[j].x;
+        p = fmaf(a[j].y, b[j].y, p); p = fmaf(a[j].z, b[j].z, p); p = fmaf(a[j].w, b[j].w, p);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) p += __shfl_xor_sync(gmask, p, o);
+        if (l16 == j && p0 + j < E) {
+            logits_csr[__ldg(bk_pos + p0 + j)] = p;
+            if (!(fabsf(p) < INFINITY)) *reinterpret_cast<volatile int*>(fallback) = 1;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -619,7 +697,7 @@ int* kgat_umma_error_word();      // attention_umma.cu
 
 // Launcher used by kgat_attention_logits_runs (attention.cu) for d = rd = 64.
 int kgat_launch_att_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
-                                const float* rel_emb, const float* W_R, float* logits_csr, int* fallback,
+                                const float* rel_emb, const float* W_R, float* logits_csr, float* v_rows, int* fallback,
                                 cudaStream_t st) {
     static PerDeviceOnce configured;
     int* err_flag = kgat_umma_error_word();
@@ -634,7 +712,13 @@ int kgat_launch_att_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, 
     const int grid = static_cast<int>(max_tiles < num_sms() ? max_tiles : num_sms());
     att_logits_runs_kernel<<<grid, THREADS, sizeof(Smem), st>>>(
         runs->rel_run_ptr, static_cast<int>(g->n_rel), runs->run_ptr, runs->run_head, runs->bk_run, g->bk_tail, g->bk_pos,
-        entity, rel_emb, W_R, logits_csr, err_flag, fallback);
+        entity, rel_emb, W_R, logits_csr, v_rows, err_flag, fallback);
     KGAT_LAUNCH_CHECK();
+    if (v_rows) {
+        const int64_t groups = (g->n_edges + 3) / 4;
+        edge_dot_kernel<<<static_cast<unsigned>((groups * 16 + 255) / 256), 256, 0, st>>>(
+            runs->bk_run, g->bk_tail, g->bk_pos, g->n_edges, entity, v_rows, logits_csr, fallback);
+        KGAT_LAUNCH_CHECK();
+    }
     return KGAT_OK;
 }

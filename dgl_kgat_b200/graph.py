@@ -64,6 +64,7 @@ class DeviceGraph:
                 _lib.check(lib.kgat_runs_build(self.ref, ctypes.byref(self._runs), ws.data_ptr(), ws_bytes,
                                                _lib.stream_ptr()), "kgat_runs_build")
                 th.cuda.current_stream().synchronize()      # ws must outlive the build
+                self.n_runs = int(self.run_arrays["n_runs"].item())
         return ctypes.byref(self._runs)
 
     def edge_weights(self, w_eid: th.Tensor):

@@ -55,14 +55,22 @@ def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Te
     r0, r1 = (0, dg.n_nodes) if rows is None else rows
     with th.cuda.device(dev):
         st = _lib.stream_ptr()
-        # default for 64-wide embeddings: the (head, relation)-run shortcut; KGAT_ATT_IMPL = f16 / tf32 / ffma select
-        # the per-edge kernels (A/B runs)
-        use_runs = d == 64 and rd == 64 and dg.n_rel <= 1024 and os.environ.get("KGAT_ATT_IMPL", "runs") == "runs"
+        # 64-wide embeddings: pi = e_t . (W_r tanh(e_h W_r + e_r)) needs the two projections once per (head,
+        # relation) RUN, not per edge (kgat_attention_logits_runs).  It pays when runs are much fewer than edges -
+        # always on a real CKG (every user row is one run), 12.7 x on the Last-FM shape - and not on a KG with
+        # uniformly random heads (Amazon-book synthetic: 0.52 runs per edge), where the per-edge kernel stays the
+        # default.  KGAT_ATT_IMPL = runs / runs_fused / f16 / tf32 / ffma forces a kernel (A/B runs).
+        impl = os.environ.get("KGAT_ATT_IMPL", "auto")
+        can_runs = d == 64 and rd == 64 and dg.n_rel <= 1024 and dg.n_edges > 0
+        use_runs = can_runs and impl in ("auto", "runs", "runs_fused")
         runs = dg.runs() if use_runs else None           # built (and synchronised) once per graph, outside any capture
-        with _lib.record("attention_logits", 3):
+        if use_runs and impl == "auto" and 3 * dg.n_runs > dg.n_edges:
+            use_runs = False
+        with _lib.record("attention_logits", 4 if use_runs else 3):
             if use_runs:
+                v_rows = None if impl == "runs_fused" else th.empty(max(dg.n_runs, 1), d, dtype=th.float32, device=dev)
                 _lib.check(lib.kgat_attention_logits_runs(dg.ref, runs, entity.data_ptr(), rel_emb.data_ptr(),
-                                                          W_R.data_ptr(), d, rd, logits.data_ptr(), st),
+                                                          W_R.data_ptr(), d, rd, logits.data_ptr(), _lib.ptr(v_rows), st),
                            "kgat_attention_logits_runs")
             else:
                 _lib.check(lib.kgat_attention_logits(dg.ref, entity.data_ptr(), rel_emb.data_ptr(), W_R.data_ptr(),

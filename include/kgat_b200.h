@@ -122,7 +122,11 @@ KGAT_API int kgat_attention_fallbacks(void);
  *      rel_run_ptr[n_rel + 1], n_runs[1].
  *      kgat_attention_logits_runs computes two 64 x 64 mat-vecs per RUN on the tensor cores (tcgen05 split-fp16
  *      grouped GEMMs over 128-run tiles) and a 64-wide dot per edge; d = rd = 64 only (KGAT_ERR_UNSUPPORTED_DIM
- *      otherwise), same operand-range protocol and fallback as kgat_attention_logits. */
+ *      otherwise), same operand-range protocol and fallback as kgat_attention_logits.
+ *      v_rows: scratch for the per-run vectors, fp32 [n_runs <= E][64], 16-byte aligned - the run kernel writes
+ *      them and a second, full-occupancy kernel computes the edge dots (the right split when runs are much
+ *      fewer than edges: the rows stay in L2); NULL fuses the edge walk into the run kernel (no scratch, no
+ *      extra traffic; latency-bound on the read-out warps, see profiles/README.md). */
 typedef struct kgat_runs_t {
     int32_t *bk_run;        /* [E] */
     int32_t *run_ptr;       /* [E+1] */
@@ -135,7 +139,7 @@ KGAT_API int kgat_runs_build(const kgat_graph_t* g, const kgat_runs_t* runs, voi
                     kgat_stream_t stream);
 KGAT_API int kgat_attention_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
                                const float* rel_emb, const float* W_R, int d, int rd, float* logits_csr,
-                               kgat_stream_t stream);
+                               float* v_rows, kgat_stream_t stream);
 
 /* (3a) softmax over the in-edges of every destination row -- replaces
  *      edge_softmax (models.py:153).  Rows [row_begin,row_end).  Writes the weights

@@ -75,7 +75,7 @@ def test_attention_umma_vs_ffma_vs_oracle(dev):
     g = CKGraph(N, trip, n_rel=R)
     w64 = kgat_ref.compute_attention({k: v.detach().cpu().double() for k, v in m.state_dict().items()}, trip, N).numpy()
     out = {}
-    for impl in ("ffma", "tf32", "f16", "runs"):
+    for impl in ("ffma", "tf32", "f16", "runs", "runs_fused"):
         os.environ["KGAT_ATT_IMPL"] = impl
         try:
             w = m.compute_attention(g).cpu().numpy().astype(np.float64)
@@ -105,15 +105,18 @@ def test_attention_logits_precision_by_magnitude(dev, scale):
     dg = g.device_graph(dev)
     eid = dg.arrays["csr_eid"].cpu().numpy().astype(np.int64)
     out = {}
-    for impl in ("ffma", "tf32", "f16", "runs"):
+    for impl in ("ffma", "tf32", "f16", "runs", "runs_fused"):
         os.environ["KGAT_ATT_IMPL"] = impl
         try:
             lib = _lib.load()
             logits = th.empty(len(trip), device=dev)
-            if impl == "runs":
-                _lib.check(lib.kgat_attention_logits_runs(dg.ref, dg.runs(), m.entity_embed.weight.data_ptr(),
+            if impl.startswith("runs"):
+                runs = dg.runs()
+                vr = th.empty(max(dg.n_runs, 1), 64, device=dev) if impl == "runs" else None
+                _lib.check(lib.kgat_attention_logits_runs(dg.ref, runs, m.entity_embed.weight.data_ptr(),
                                                           m.relation_embed.weight.data_ptr(), m.W_R.data_ptr(), 64, 64,
-                                                          logits.data_ptr(), _lib.stream_ptr()), "kgat_attention_logits_runs")
+                                                          logits.data_ptr(), _lib.ptr(vr), _lib.stream_ptr()),
+                           "kgat_attention_logits_runs")
             else:
                 _lib.check(lib.kgat_attention_logits(dg.ref, m.entity_embed.weight.data_ptr(),
                                                      m.relation_embed.weight.data_ptr(), m.W_R.data_ptr(), 64, 64,
@@ -162,7 +165,7 @@ def test_attention_operand_range_guard(dev, case):
     assert lib.kgat_umma_error_flag() == 0
 
 
-@pytest.mark.parametrize("impl", ["tf32", "f16", "runs"])
+@pytest.mark.parametrize("impl", ["tf32", "f16", "runs", "runs_fused"])
 def test_attention_umma_ragged_tiles(dev, impl, monkeypatch):
     """Relation buckets that are empty, smaller than a tile, or one edge over a tile boundary."""
     monkeypatch.setenv("KGAT_ATT_IMPL", impl)
@@ -334,10 +337,12 @@ def test_runs_structure_bit_exact_and_logits(dev, case):
     g = CKGraph(N, trip, n_rel=R)
     dg = g.device_graph(dev)
     dg.runs()
-    want = graph_ref.build_runs({k: v.cpu().numpy() for k, v in dg.arrays.items()}, R)
+    E = len(trip)
+    host = {k: v.cpu().numpy() for k, v in dg.arrays.items()}
+    host = {k: (v if k.endswith("_ptr") else v[:E]) for k, v in host.items()}      # arrays are allocated with >= 1 entry
+    want = graph_ref.build_runs(host, R)
     n_runs = int(dg.run_arrays["n_runs"].item())
     assert n_runs == want["n_runs"]
-    E = len(trip)
     assert np.array_equal(dg.run_arrays["bk_run"].cpu().numpy()[:E], want["bk_run"])
     assert np.array_equal(dg.run_arrays["run_ptr"].cpu().numpy()[: n_runs + 1], want["run_ptr"])
     assert np.array_equal(dg.run_arrays["run_head"].cpu().numpy()[:n_runs], want["run_head"])
@@ -348,13 +353,16 @@ def test_runs_structure_bit_exact_and_logits(dev, case):
     m = models.Model(True, 64, "kgat", 1, 64, 0.0, n_entities=N, n_relations=R, relation_dim=64).to(dev)
     sd = {k: v.detach().cpu().double() for k, v in m.state_dict().items()}
     ref = kgat_ref.att_logits(sd, trip).numpy().reshape(-1)
-    logits = th.empty(E, device=dev)
     lib = _lib.load()
-    _lib.check(lib.kgat_attention_logits_runs(dg.ref, dg.runs(), m.entity_embed.weight.data_ptr(),
-                                              m.relation_embed.weight.data_ptr(), m.W_R.data_ptr(), 64, 64,
-                                              logits.data_ptr(), _lib.stream_ptr()), "kgat_attention_logits_runs")
-    th.cuda.synchronize()
     eid = dg.arrays["csr_eid"].cpu().numpy().astype(np.int64)[:E]
-    got = logits.cpu().numpy().astype(np.float64)
-    assert float(np.abs(got - ref[eid]).max() / np.abs(ref).max()) < 1e-5
+    for fused in (False, True):
+        logits = th.full((E,), float("nan"), device=dev)
+        vr = None if fused else th.empty(max(n_runs, 1), 64, device=dev)
+        _lib.check(lib.kgat_attention_logits_runs(dg.ref, dg.runs(), m.entity_embed.weight.data_ptr(),
+                                                  m.relation_embed.weight.data_ptr(), m.W_R.data_ptr(), 64, 64,
+                                                  logits.data_ptr(), _lib.ptr(vr), _lib.stream_ptr()),
+                   "kgat_attention_logits_runs")
+        th.cuda.synchronize()
+        got = logits.cpu().numpy().astype(np.float64)
+        assert float(np.abs(got - ref[eid]).max() / np.abs(ref).max()) < 1e-5, fused
     assert lib.kgat_umma_error_flag() == 0 and lib.kgat_attention_fallbacks() == 0
