@@ -326,6 +326,16 @@ class DistKGAT:
         # order edge_weights() of the local out-graph expects them (its local edge-id order)
         self._csr_rank = th.from_numpy(p.csr_rank).to(self.device)
         self._out_rank = th.from_numpy(p.csr_rank[p.eid_out]).to(self.device)
+        # the logits kernel is chosen from the GLOBAL (head, relation)-run count (runs never straddle ranks: a rank
+        # owns whole head rows), so every rank and the single-GPU step run the same arithmetic
+        self.att_impl = None
+        d0 = model.entity_embed.weight.shape[1]
+        if d0 == 64 and model.relation_embed.weight.shape[1] == 64 and self.part.n_edges > 0 and n_rel <= 1024 \
+                and self.device.type == "cuda":
+            self.dg_in.runs()
+            n_runs = th.tensor([self.dg_in.n_runs], dtype=th.int64, device=self.device)
+            tdist.all_reduce(n_runs, group=group)
+            self.att_impl = ops.attention_impl_for(int(n_runs.item()), self.part.n_edges)
         self.w_full = None
         self._plan = None
         self._dw_views = None
@@ -356,11 +366,12 @@ class DistKGAT:
                 # per step.  A single-layer model has no such barrier and gets an explicit one (finish_weights).
                 w_glob = self.peer.buf(("w",), (max(p.n_edges, 1),))[: p.n_edges]
                 _, w_csr = ops.attention(self.dg_in, m.entity_embed.weight, m.relation_embed.weight, m.W_R,
-                                         rows=(p.r0, p.r1), want_eid=False, w_csr_out=w_glob[e0:e1], peer=self.peer)
+                                         rows=(p.r0, p.r1), want_eid=False, w_csr_out=w_glob[e0:e1], peer=self.peer,
+                                         impl=self.att_impl)
                 w_csc = None
             else:
                 _, w_csr = ops.attention(self.dg_in, m.entity_embed.weight, m.relation_embed.weight, m.W_R,
-                                         rows=(p.r0, p.r1), want_eid=False)
+                                         rows=(p.r0, p.r1), want_eid=False, impl=self.att_impl)
                 # one uneven all-gather assembles the weights of ALL edges in global CSR order
                 w_glob = th.empty(p.n_edges, dtype=th.float32, device=self.device)
                 w_glob[e0:e1] = w_csr[: self.dg_in.n_edges]

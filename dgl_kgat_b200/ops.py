@@ -25,8 +25,17 @@ def _f32c(t: th.Tensor, device) -> th.Tensor:
     return t.contiguous()
 
 
+def attention_impl_for(n_runs: int, n_edges: int) -> str:
+    """The logits kernel the library picks for a graph with ``n_runs`` (head, relation) runs: the run shortcut
+    when runs are at most a third of the edges, the per-edge kernel otherwise (KGAT_ATT_IMPL overrides)."""
+    impl = os.environ.get("KGAT_ATT_IMPL", "auto")
+    if impl != "auto":
+        return impl
+    return "runs" if 3 * n_runs <= n_edges else "f16"
+
+
 def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Tensor, rows=None, want_eid=True,
-              w_csr_out=None, peer=None):
+              w_csr_out=None, peer=None, impl=None):
     """Logits + per-destination softmax (reference models.py:146-154).
 
     Returns ``(w_eid, w_csr)``: ``w_eid`` is the (E, 1) tensor ``compute_attention``
@@ -60,12 +69,16 @@ def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Te
         # always on a real CKG (every user row is one run), 12.7 x on the Last-FM shape - and not on a KG with
         # uniformly random heads (Amazon-book synthetic: 0.52 runs per edge), where the per-edge kernel stays the
         # default.  KGAT_ATT_IMPL = runs / runs_fused / f16 / tf32 / ffma forces a kernel (A/B runs).
-        impl = os.environ.get("KGAT_ATT_IMPL", "auto")
+        # ``impl``: the caller's choice (dist.DistKGAT decides from the GLOBAL run count so that every rank - and the
+        # single-GPU step - runs the same arithmetic); None: decide from this graph
         can_runs = d == 64 and rd == 64 and dg.n_rel <= 1024 and dg.n_edges > 0
-        use_runs = can_runs and impl in ("auto", "runs", "runs_fused")
+        if impl is None:
+            impl = os.environ.get("KGAT_ATT_IMPL", "auto")
+            if impl == "auto" and can_runs:
+                dg.runs()
+                impl = attention_impl_for(dg.n_runs, dg.n_edges)
+        use_runs = can_runs and impl in ("runs", "runs_fused")
         runs = dg.runs() if use_runs else None           # built (and synchronised) once per graph, outside any capture
-        if use_runs and impl == "auto" and 3 * dg.n_runs > dg.n_edges:
-            use_runs = False
         with _lib.record("attention_logits", 4 if use_runs else 3):
             if use_runs:
                 v_rows = None if impl == "runs_fused" else th.empty(max(dg.n_runs, 1), d, dtype=th.float32, device=dev)
