@@ -309,7 +309,8 @@ struct BwdCfg {
     static constexpr int LDW = EPI ? DIN + 8 : DIN;         // sW (W2 as given, [DOUT][DIN])
     static constexpr int WT = (DOUT / 16) * (DIN / 8);      // 16 x 8 tiles of dW2
     static constexpr int TPW = WT > 0 ? (WT + WARPS - 1) / WARPS : 1;    // ... per warp
-    static constexpr size_t bytes = sizeof(float) * (DOUT * LDW + TM * LDP + TM * LDZ + COOP_FLOATS) + 16;
+    static constexpr int LDD = DIN + 4;                     // dz tile of the tensor-core path (row-coalesced write-out)
+    static constexpr size_t bytes = sizeof(float) * (DOUT * LDW + TM * LDP + TM * LDZ + COOP_FLOATS + (EPI ? TM * LDD : 0)) + 16;
 };
 
 // resident CTAs per SM of the persistent grid (measured on B200: 5 beats 4 for the narrow layers - 51 registers
@@ -339,6 +340,8 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
     float* sW = sZ + TM * LDZ;                           // [DOUT][LDW], W2 as given
     float4* sPart = reinterpret_cast<float4*>(sW + DOUT * LDW);
     int* sLong = reinterpret_cast<int*>(sPart + WARPS * 32);
+    float* sDZ = reinterpret_cast<float*>(sLong + TM);      // EPI 1: [TM][LDD]  (COOP_FLOATS = 4 * WARPS * 32 + TM floats above)
+    constexpr int LDD = C::LDD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int idx = tid; idx < DOUT * DIN / 4; idx += THREADS)
@@ -507,16 +510,23 @@ layer_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                     mma_tf32_16x8x8(c, ah, bl);
                     mma_tf32_16x8x8(c, ah, bh);
                 }
-                // pair the lanes (ft even, ft odd) so that each stores 128 bits: the even lane takes columns
-                // 8 nt + 2 ft .. + 3 of row fg (its own two and the partner's two), the odd lane those of row fg + 8
-                {
-                    const bool odd = ft & 1;
-                    const float s0 = odd ? c[0] : c[2], s1 = odd ? c[1] : c[3];
-                    const float r0 = __shfl_xor_sync(FULL_MASK, s0, 1), r1 = __shfl_xor_sync(FULL_MASK, s1, 1);
-                    const float4 d = odd ? make_float4(r0, r1, c[2], c[3]) : make_float4(c[0], c[1], r0, r1);
-                    const int row = row0 + 16 * mt + fg + (odd ? 8 : 0);
+                // dz fragment -> shared memory; the write-out below is row-coalesced
+                *reinterpret_cast<float2*>(sDZ + (16 * mt + fg) * LDD + 8 * nt + 2 * ft) = make_float2(c[0], c[1]);
+                *reinterpret_cast<float2*>(sDZ + (16 * mt + fg + 8) * LDD + 8 * nt + 2 * ft) = make_float2(c[2], c[3]);
+            }
+            __syncthreads();
+            // phase 2c: dx_direct = dz (.) h_nb, dh_nb = dz (.) h_in, whole rows per lane group: every global (and
+            // peer) store instruction covers complete 128-byte lines of a row (the fragment layout stored 32-byte
+            // pieces of 16 rows - over NVLink that is one packet per 32 bytes; measured at 4 GPUs: the dense kernel
+            // of a rank took LONGER than the single-GPU one although it owned a quarter of the rows)
+            {
+                constexpr int RPW2 = 32 / LPI;
+                const int sub = lane / LPI, ll = lane % LPI;
+                for (int rl = warp * RPW2 + sub; rl < TM; rl += WARPS * RPW2) {
+                    const int row = row0 + rl;
                     if (row < row_end) {
-                        const size_t o = static_cast<size_t>(row) * DIN + 8 * nt + 4 * (ft >> 1);
+                        const float4 d = *reinterpret_cast<const float4*>(sDZ + rl * LDD + ll * 4);
+                        const size_t o = static_cast<size_t>(row) * DIN + ll * 4;
                         const float4 hn = ldg4(h_nb + o), hi = ldg4(h_in + o);
                         *reinterpret_cast<float4*>(dx_direct + o) = make_float4(d.x * hn.x, d.y * hn.y, d.z * hn.z, d.w * hn.w);
                         const float4 dh = make_float4(d.x * hi.x, d.y * hi.y, d.z * hi.z, d.w * hi.w);
