@@ -544,6 +544,17 @@ def run_ours(args):
         if distributed:
             roofline["scope"] = "rank 0 (%d of %d rows, %d of %d in-edges); step_frac is whole-job" % (n_loc, N, e_loc, E)
 
+    # ---- N > 1: every rank's share and its kernel time (what the partition cost model is calibrated on) ----
+    by_rank = None
+    if distributed:
+        mine = {"rank": rank, "rows": int(dk.part.r1 - dk.part.r0), "in_edges": int(dk.dg_in.n_edges),
+                "out_edges": int(dk.dg_out.n_edges),
+                "kernel_ms_sum": round(sum(v for k, v in kernel_ms.items() if k != "peer_barrier"), 4),
+                "barrier_wait_ms": round(kernel_ms.get("peer_barrier", 0.0) * 7, 4)}
+        gathered = [None] * world
+        tdist.all_gather_object(gathered, mine)
+        by_rank = gathered
+
     # ---- the two halves of the step and the epoch mix -------------------
     # from the per-call CUDA events of the eager pass: attention = logits + softmax + CSC re-layout, gnn = the rest;
     # one Amazon-book epoch refreshes the attention once and runs 108 CF iterations (kgat.py:139-168)
@@ -654,6 +665,7 @@ def run_ours(args):
                            "shape (tests/test_gpu_parity.py::test_full_size_step_matches_fp64_oracle); weight gradients "
                            "may use 2x the fp32 reference's own error; top-K is bit-exact outside fp32-unresolvable ties",
             # the keys a reader wants first are LAST: the driver keeps the tail of this line
+            "ranks": by_rank,
             "eval": eval_info, "roofline_eval": roofline_eval, "dist_parity": dist_parity, "scale_10x": scale_10x,
         }
         emit(line)

@@ -42,7 +42,7 @@ IPC_HANDLE_BYTES = 64           # KGAT_IPC_HANDLE_BYTES
 class KgatPeerGroup(C.Structure):
     """Mirror of ``kgat_peer_group_t``."""
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("arena_bytes", C.c_uint64),
-                ("arena", C.c_void_p * MAX_RANKS)]
+                ("arena", C.c_void_p * MAX_RANKS), ("multicast", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every KGAT_API symbol of the header

@@ -66,32 +66,75 @@ class PeerArena:
         self.timeout_ms = int(timeout_ms) or int(os.environ.get("KGAT_PEER_TIMEOUT_MS", "0"))
         self.generation = 0
         self._bufs, self._top, self._closed = {}, _lib.PEER_HEADER_BYTES, False
-        own = ctypes.c_void_p()
-        handle = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
         self._pg = _lib.KgatPeerGroup()
         self._pg.world, self._pg.rank, self._pg.arena_bytes = self.world, self.rank, self.nbytes
-        self._mapped = []
+        self._pg.multicast = None
+        self._mapped, self._symm = [], None
+        want_mc = os.environ.get("KGAT_PEER_MULTICAST", "1") != "0" and self.world > 1
         with th.cuda.device(self.device):
-            _lib.check(lib.kgat_peer_arena_create(self.nbytes, ctypes.byref(own), handle), "kgat_peer_arena_create")
-            self._own = own.value
-            infos = [None] * self.world
-            tdist.all_gather_object(infos, (bytes(handle.raw), self.nbytes, socket.gethostname()), group=group)
-            if len({host for _, _, host in infos}) != 1:
-                raise _lib.KgatError("the peer exchange maps the other ranks' memory with cudaIpc and needs all ranks "
-                                     "on one NVLink box; ranks span %s - use exchange='nccl'"
-                                     % sorted({host for _, _, host in infos}))
-            if any(n != self.nbytes for _, n, _ in infos):
-                raise _lib.KgatError("peer arenas differ in size across ranks: %s" % [n for _, n, _ in infos])
-            for k, (h, _, _) in enumerate(infos):
-                if k == self.rank:
-                    self._pg.arena[k] = self._own
-                    continue
-                p = ctypes.c_void_p()
-                _lib.check(lib.kgat_peer_arena_open(h, ctypes.byref(p)), "kgat_peer_arena_open (rank %d)" % k)
-                self._pg.arena[k] = p.value
-                self._mapped.append(p.value)
+            if want_mc and self._try_symmetric(group):
+                pass
+            else:
+                self._ipc_arena(lib, group)
             self.ref = ctypes.byref(self._pg)
             tdist.barrier(group=group)       # nobody pushes before every rank has mapped every arena
+
+    def _try_symmetric(self, group):
+        """Arena from torch's symmetric memory: the rendezvous maps every rank's allocation into this process AND
+        binds them to one NVSwitch multicast object, whose address lets a single ``multimem.st`` reach all ranks
+        (include/kgat_b200.h, kgat_peer_group_t.multicast).  torch is the plumbing here (VMM allocation, handle
+        exchange); returns False when this build / fabric offers no multicast, and the cudaIpc arena is used."""
+        t = h = None
+        mc, ptrs = 0, []
+        try:
+            import torch.distributed._symmetric_memory as symm
+            g = group if group is not None else tdist.group.WORLD
+            t = symm.empty(self.nbytes, dtype=th.uint8, device=self.device)
+            t.zero_()
+            th.cuda.synchronize()
+            h = symm.rendezvous(t, g.group_name)
+            mc = int(getattr(h, "multicast_ptr", 0) or 0)
+            ptrs = [int(x) for x in h.buffer_ptrs]
+        except Exception:            # no symmetric memory in this torch / no fabric support: unicast pushes
+            mc = 0
+        # every rank reaches this vote, whatever happened above
+        ok = th.tensor([1 if (mc != 0 and len(ptrs) == self.world and ptrs[self.rank] == t.data_ptr()) else 0],
+                       device=self.device)
+        tdist.all_reduce(ok, op=tdist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            return False
+        self._symm = (t, h)
+        self._own = t.data_ptr()
+        for k in range(self.world):
+            self._pg.arena[k] = ptrs[k]
+        self._pg.multicast = mc
+        return True
+
+    def _ipc_arena(self, lib, group):
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        _lib.check(lib.kgat_peer_arena_create(self.nbytes, ctypes.byref(own), handle), "kgat_peer_arena_create")
+        self._own = own.value
+        infos = [None] * self.world
+        tdist.all_gather_object(infos, (bytes(handle.raw), self.nbytes, socket.gethostname()), group=group)
+        if len({host for _, _, host in infos}) != 1:
+            raise _lib.KgatError("the peer exchange maps the other ranks' memory with cudaIpc and needs all ranks "
+                                 "on one NVLink box; ranks span %s - use exchange='nccl'"
+                                 % sorted({host for _, _, host in infos}))
+        if any(n != self.nbytes for _, n, _ in infos):
+            raise _lib.KgatError("peer arenas differ in size across ranks: %s" % [n for _, n, _ in infos])
+        for k, (h, _, _) in enumerate(infos):
+            if k == self.rank:
+                self._pg.arena[k] = self._own
+                continue
+            p = ctypes.c_void_p()
+            _lib.check(lib.kgat_peer_arena_open(h, ctypes.byref(p)), "kgat_peer_arena_open (rank %d)" % k)
+            self._pg.arena[k] = p.value
+            self._mapped.append(p.value)
+
+    @property
+    def multicast(self):
+        return bool(self._pg.multicast)
 
     def buf(self, name, shape):
         t = self._bufs.get(name)
@@ -144,6 +187,10 @@ class PeerArena:
             th.cuda.synchronize()
             tdist.barrier(group=self.group)
             self._bufs.clear()
+            if self._symm is not None:
+                tdist.barrier(group=self.group)
+                self._symm = None                   # the symmetric allocation is released with its tensor
+                return
             for p in self._mapped:
                 lib.kgat_peer_arena_close(p)
             tdist.barrier(group=self.group)
@@ -206,6 +253,40 @@ def partition_rows_minmax(edge_cost: np.ndarray, n_parts: int, row_ns: float, ed
     return np.asarray(best[1], dtype=np.int64)
 
 
+def partition_rows_blended(row_cost: np.ndarray, n_parts: int) -> np.ndarray:
+    """Boundaries b[0..n_parts] of contiguous ranges minimising the LARGEST range cost, cost = sum of ``row_cost``
+    over the range (bisection on the bound, greedy left-to-right packing decides feasibility exactly).
+
+    Measured on 4 B200s (profiles/README.md): the step time of the partitioned step is the kernel time of its
+    slowest rank, and a rank's kernel time is linear in its rows and edges (12 ns per row with unicast pushes to 3
+    peers, 0.29 ns per in-edge) - minimising the per-phase maxima separately (partition_rows_minmax) left one
+    rank with both the most rows and the most edges."""
+    n = len(row_cost)
+    if n_parts <= 1 or n == 0:
+        return np.array([0] + [n] * max(n_parts, 1), dtype=np.int64)
+    ptr = np.zeros(n + 1, dtype=np.float64)
+    np.cumsum(row_cost, out=ptr[1:])
+    total, heaviest = float(ptr[-1]), float(row_cost.max())
+
+    def pack(bound):
+        b = [0]
+        for _ in range(n_parts):
+            a = b[-1]
+            b.append(max(a, int(np.searchsorted(ptr, ptr[a] + bound, side="right")) - 1))
+        return b if b[-1] >= n else None
+
+    lo, hi = max(heaviest, total / n_parts), total
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if pack(mid) is None:
+            lo = mid
+        else:
+            hi = mid
+    b = pack(hi)
+    b[-1] = n
+    return np.asarray(b, dtype=np.int64)
+
+
 class Partition:
     """The slice of the CKG owned by ``rank``: edge subsets and the two local graphs.
 
@@ -216,12 +297,15 @@ class Partition:
     Amazon-book CKG) half of all rows at 4 ranks - measured: its push kernels were NVLink-egress bound
     (1.7 ns per 256-byte row and 3 peers) while the other ranks idled at the barriers."""
 
-    def __init__(self, n_nodes, triplets, n_rel, rank, world, row_ns=0.0, edge_ns=0.36):
+    def __init__(self, n_nodes, triplets, n_rel, rank, world, row_ns=0.0, edge_ns=0.36, blended=False):
         trip = np.ascontiguousarray(triplets, dtype=np.int32)
         self.n_nodes, self.n_rel, self.n_edges = int(n_nodes), int(n_rel), trip.shape[0]
         self.rank, self.world = rank, world
         indeg = np.bincount(trip[:, 0], minlength=n_nodes).astype(np.int64)
-        if row_ns > 0 and world > 1:
+        if row_ns > 0 and world > 1 and blended:
+            both = indeg + np.bincount(trip[:, 2], minlength=n_nodes)
+            self.bounds = partition_rows_blended(row_ns + 0.5 * edge_ns * both, world)
+        elif row_ns > 0 and world > 1:
             both = indeg + np.bincount(trip[:, 2], minlength=n_nodes)
             self.bounds = partition_rows_minmax(both, world, row_ns, edge_ns / 2)
         else:
@@ -301,16 +385,27 @@ class DistKGAT:
         # cost model of the partition (measured on B200, Amazon-book shape, ns per step): an edge costs ~0.36
         # (all gathers of a step), a row ~1 for its dense work plus, with the peer exchange, ~2.9 per peer for
         # the NVLink copies of its exchanged rows (6 buffers, 1.3 KB per row and peer at ~450 GB/s)
-        row_ns = os.environ.get("KGAT_DIST_ROW_NS")
-        row_ns = float(row_ns) if row_ns is not None else 1.0 + (2.9 * (self.world - 1) if exchange == "peer" else 0.0)
-        self.part = Partition(n_nodes, triplets, n_rel, self.rank, self.world, row_ns=row_ns)
         self.peer = None
         if exchange == "peer":
             dims = [model.entity_embed.weight.shape[1]] + [l.res_fc_2.weight.shape[0] for l in model.layers]
-            N, E, L = int(n_nodes), self.part.n_edges, len(dims) - 1
+            N, E, L = int(n_nodes), int(np.asarray(triplets).shape[0]), len(dims) - 1
             floats = E + N * sum(dims[1:L]) + N * sum(dims[:L]) + N * dims[0] \
                 + self.world * sum(dims[l] * dims[l + 1] for l in range(L)) + 3 * int(max_batch) * sum(dims)
             self.peer = PeerArena(4 * floats + 256 * (2 * L + 8), self.device, group)
+        # cost model of the partition, per step (measured on B200s, Amazon-book shape, profiles/README.md): a rank's
+        # kernel time is ~3 ns per owned row of dense work + ~3 ns per row and DESTINATION of its exchanged rows
+        # (1.3 KB per row: one destination with the NVSwitch multicast, world - 1 with unicast pushes) + 0.29 ns per
+        # in-edge, and the step takes as long as its slowest rank
+        row_ns = os.environ.get("KGAT_DIST_ROW_NS")
+        if row_ns is not None:
+            row_ns = float(row_ns)
+        elif self.peer is None:
+            row_ns = 3.0
+        else:
+            row_ns = 3.0 + 3.0 * (1 if self.peer.multicast else self.world - 1)
+        self.part = Partition(n_nodes, triplets, n_rel, self.rank, self.world, row_ns=row_ns, edge_ns=0.29,
+                              blended=os.environ.get("KGAT_DIST_PARTITION", "blended") == "blended")
+        if exchange == "peer":
             # fixed allocation order = identical offsets on every rank
             self.peer.buf(("w",), (max(E, 1),))
             for l in range(L - 1):

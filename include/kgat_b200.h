@@ -325,6 +325,11 @@ typedef struct kgat_peer_group {
     int32_t  world, rank;
     uint64_t arena_bytes;                 /* the same on every rank */
     void*    arena[KGAT_MAX_RANKS];       /* arena[k]: address, in THIS process, of rank k's arena */
+    void*    multicast;                   /* NVSwitch multicast mapping of the arenas of ALL ranks (one store
+                                           * reaches every rank: multimem.st), or NULL: the *_push kernels then
+                                           * store to every peer separately.  How the mapping is created is the
+                                           * host's business (cuMulticastCreate / cuMulticastBindMem; the Python
+                                           * host takes it from torch's symmetric-memory rendezvous). */
 } kgat_peer_group_t;
 
 /* cudaMalloc + zero-fill an arena on the current device and export it: handle_out_host receives the

@@ -62,9 +62,10 @@ def test_peer_group_struct_layout_matches_header():
     assert "#define KGAT_PEER_HEADER_BYTES %d" % _lib.PEER_HEADER_BYTES in text
     assert "#define KGAT_IPC_HANDLE_BYTES %d" % _lib.IPC_HANDLE_BYTES in text
     body = text[text.index("typedef struct kgat_peer_group {"): text.index("} kgat_peer_group_t;")]
-    assert [f for f in re.findall(r"(\w+)(?:\[\w+\])?;", body)] == ["rank", "arena_bytes", "arena"]
-    assert [n for n, _ in _lib.KgatPeerGroup._fields_] == ["world", "rank", "arena_bytes", "arena"]
-    assert ctypes.sizeof(_lib.KgatPeerGroup) == 4 + 4 + 8 + 8 * _lib.MAX_RANKS
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    assert [f for f in re.findall(r"(\w+)(?:\[\w+\])?;", body)] == ["rank", "arena_bytes", "arena", "multicast"]
+    assert [n for n, _ in _lib.KgatPeerGroup._fields_] == ["world", "rank", "arena_bytes", "arena", "multicast"]
+    assert ctypes.sizeof(_lib.KgatPeerGroup) == 4 + 4 + 8 + 8 * _lib.MAX_RANKS + 8
 
 
 def test_graph_struct_layout_matches_header():
