@@ -118,6 +118,25 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def nvlink_tx_rx_kib(gpu_index):
+    """Sum over the links of one GPU of the NVLink data counters (`nvidia-smi nvlink -gt d`), in KiB:
+    (tx, rx), or None when the tool / counters are not available."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu_index)], capture_output=True,
+                             text=True, timeout=20).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return None
+    tx = rx = 0
+    seen = False
+    for line in out.splitlines():
+        parts = line.replace(":", " ").split()
+        if "Tx" in parts and "KiB" in parts:
+            tx += int(parts[parts.index("KiB") - 1]); seen = True
+        elif "Rx" in parts and "KiB" in parts:
+            rx += int(parts[parts.index("KiB") - 1]); seen = True
+    return (tx, rx) if seen else None
+
+
 def measured_tensor_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -126,14 +145,28 @@ def measured_tensor_peak():
     return 1650.0, "fallback (B200_PROFILING.md)"
 
 
+TRAFFIC_FILES = ("traffic_r2.json", "traffic_r1.json")     # newest capture first
+
+
+def traffic_source(kernel):
+    for name in TRAFFIC_FILES:
+        try:
+            json.load(open(os.path.join(ROOT, "profiles", name)))["kernels"][kernel]
+            return "profiles/%s (ncu --set full, same workload)" % name
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
+
+
 def measured_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
-    `ncu --set full` capture of this workload (profiles/traffic_r1.json); None if not captured."""
-    path = os.path.join(ROOT, "profiles", "traffic_r1.json")
-    try:
-        return float(json.load(open(path))["kernels"][kernel]["dram_bytes"])
-    except (OSError, KeyError, ValueError):
-        return None
+    `ncu --set full` capture of this workload (profiles/traffic_r*.json, newest first); None if not captured."""
+    for name in TRAFFIC_FILES:
+        try:
+            return float(json.load(open(os.path.join(ROOT, "profiles", name)))["kernels"][kernel]["dram_bytes"])
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
 def workload_config(cfg, world=1, work_mb=None, exchange=None):
@@ -476,6 +509,8 @@ def run_ours(args):
         run_value(0)
     with ClockSampler(local) as clocks:
         barrier()
+        nv0 = nvlink_tx_rx_kib(local) if (distributed and rank == 0) else None
+        barrier()
         e0.record()
         for i in range(args.steps):
             run_value(i)
@@ -484,6 +519,16 @@ def run_ours(args):
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         ms_step = ms_total / args.steps
         value = E / (ms_step * 1e-3)
+        nvlink = None
+        if nv0 is not None:
+            nv1 = nvlink_tx_rx_kib(local)
+            if nv1 is not None:
+                # measured, not derived: what rank 0's GPU sent / received over NVLink during the K timed steps
+                nvlink = {"scope": "rank 0 GPU, all links, the %d timed steps (nvidia-smi nvlink -gt d)" % args.steps,
+                          "tx_MB_per_step": (nv1[0] - nv0[0]) * 1024 / 1e6 / args.steps,
+                          "rx_MB_per_step": (nv1[1] - nv0[1]) * 1024 / 1e6 / args.steps,
+                          "multicast": bool(dk.peer is not None and dk.peer.multicast)}
+        barrier()
 
         # ---- e2e: host batch ids in, loss out, every step (public API) ---------------------------
         if graphed is None:
@@ -527,7 +572,7 @@ def run_ours(args):
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": None if distributed else measured_traffic(top), "peak_source": peak_src,
                     "launch_ms": kernel_ms[top],
-                    "traffic_source": None if distributed else "profiles/traffic_r1.json (ncu --set full, same workload)",
+                    "traffic_source": None if distributed else traffic_source(top),
                     "algorithmic_bytes": alg[top],
                     # what the kernel really moved through HBM (ncu dram bytes of the committed capture) over its
                     # live launch time: the E-model counts L2 hits, this one does not
@@ -666,7 +711,7 @@ def run_ours(args):
                            "may use 2x the fp32 reference's own error; top-K is bit-exact outside fp32-unresolvable ties",
             # the keys a reader wants first are LAST: the driver keeps the tail of this line
             "ranks": by_rank,
-            "eval": eval_info, "roofline_eval": roofline_eval, "dist_parity": dist_parity, "scale_10x": scale_10x,
+            "eval": eval_info, "roofline_eval": roofline_eval, "dist_parity": dist_parity, "scale_10x": scale_10x, "nvlink": nvlink,
         }
         emit(line)
     if distributed:
