@@ -21,10 +21,14 @@ class KgatGraph(C.Structure):
         (name, C.c_void_p) for name in (
             "csr_ptr", "csr_src", "csr_dst", "csr_rel", "csr_eid",
             "csc_ptr", "csc_dst", "csc_pos", "csc_eid",
-            "rel_ptr", "bk_pos", "bk_head", "bk_tail")]
+            "rel_ptr", "bk_pos", "bk_head", "bk_tail")] + [
+        # row splitting (kgat_graph_split_build): segment tables, partial-sum scratch, host copies of the sizes
+        ("split", C.c_void_p), ("split_scratch", C.c_void_p),
+        ("n_csr_seg", C.c_int32), ("n_csr_long", C.c_int32), ("n_csc_seg", C.c_int32), ("n_csc_long", C.c_int32)]
 
 
-GRAPH_ARRAYS = [name for name, _ in KgatGraph._fields_[3:]]
+GRAPH_ARRAYS = [name for name, _ in KgatGraph._fields_[3:16]]
+SPLIT_ROW, SPLIT_SEG, SPLIT_SCRATCH_WIDTH = 2048, 1024, 128     # KGAT_SPLIT_* of the header
 
 
 class KgatRuns(C.Structure):
@@ -56,6 +60,8 @@ SIGNATURES = {
     "kgat_device_check": (C.c_int, []),
     "kgat_graph_build_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
     "kgat_graph_build": (C.c_int, [_GP, c_i32p, c_i32p, c_i32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kgat_graph_split_ints": (C.c_size_t, [C.c_int64]),
+    "kgat_graph_split_build": (C.c_int, [_GP, C.POINTER(C.c_int32), C.c_void_p]),
     "kgat_attention_logits": (C.c_int, [_GP, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     "kgat_attention_fallbacks": (C.c_int, []),
     "kgat_runs_build_workspace_bytes": (C.c_size_t, [C.c_int64]),

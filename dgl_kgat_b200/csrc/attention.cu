@@ -7,9 +7,10 @@
 // ever reaches HBM.  fp32 FFMA throughout: the parity bar is 1e-5 relative against the fp32/fp64
 // reference, which a single TF32/BF16 tensor-core pass cannot meet.
 //
-// Softmax: one warp per destination row of the CSR, max and sum by warp shuffles, exp(x - max) / sum
-// like DGL's edge_softmax (reference models.py:153).
+// Softmax: exp(x - max) / sum over the in-edges of a destination row like DGL's edge_softmax (reference
+// models.py:153), with the parallelism matched to the row length (see segment_softmax_kernel).
 #include "peer.cuh"
+#include "split.cuh"
 
 namespace kgat {
 namespace {
@@ -198,46 +199,156 @@ __global__ void att_logits_generic_kernel(const int32_t* __restrict__ csr_src, c
 // ------------------------------------------------------------------------------------------------
 // segment softmax: warp per destination row
 // ------------------------------------------------------------------------------------------------
-// PUSH (multi-GPU): every weight is also stored to the peers' copies of the all-edges vector (peer.cuh);
-// the single-GPU instantiation carries no trace of it (the extra stores kept the long-row loop from
-// being unrolled: 0.049 -> 0.082 ms at Amazon-book when they were merely predicated off).
+// Segment softmax (reference models.py:153, DGL edge_softmax: exp(x - max) / sum over the in-edges of a row).
+// Rows come at three sizes and each size gets the parallelism that fits it:
+//   deg <= 32           eight lanes per row, four rows per warp (44 % of the rows of a CKG are users with ~8
+//                       interactions: a full warp per row left three quarters of the lanes idle); the <= 4
+//                       logits of a lane stay in registers, max and sum by 8-lane shuffles - one pass over memory;
+//   32 < deg            the whole warp, ONLINE max / sum (one pass: a lane keeps a running maximum m and the sum
+//                       of exp(x - m), rescaled when m grows; lanes are merged by shuffles), then the write pass;
+//   deg > SPLIT_ROW     (split.cuh) one CTA per segment: segment (max, sum) -> per-row merge -> write, three small
+//                       kernels that run only when the graph has such rows.
+// PUSH (multi-GPU): every weight is also stored to the peers' copies of the all-edges vector (peer.cuh); the
+// single-GPU instantiation carries no trace of it.
+constexpr int SM_ROWS_PER_WARP = 4;
+constexpr int SM_ROWS_PER_CTA = 8 * SM_ROWS_PER_WARP;
+
 template <bool PUSH>
 __global__ void __launch_bounds__(256)
 segment_softmax_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict__ csr_eid,
                        int64_t row_begin, int64_t row_end, const float* __restrict__ logits,
-                       float* __restrict__ w_csr, float* __restrict__ w_eid, PeerOut po) {
-    const int64_t row = row_begin + ((blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= row_end) return;
-    const int beg = csr_ptr[row], end = csr_ptr[row + 1];
-    if (end - beg <= 32) {
-        const int c = beg + lane;
-        const bool ok = c < end;
-        const float x = ok ? logits[c] : -INFINITY;
-        const float m = warp_max(x);
-        const float ex = ok ? expf(x - m) : 0.f;
-        const float den = warp_sum(ex);
-        if (ok) {
-            const float w = ex / den;
+                       float* __restrict__ w_csr, float* __restrict__ w_eid, int split_done, PeerOut po) {
+    const int lane = threadIdx.x & 31, sub = lane >> 3, sl = lane & 7;
+    const int64_t warp_row = row_begin + (blockIdx.x * 8 + (threadIdx.x >> 5)) * static_cast<int64_t>(SM_ROWS_PER_WARP);
+    if (warp_row >= row_end) return;
+    const int64_t row = warp_row + sub;
+    int beg = 0, end = 0;
+    if (row < row_end) { beg = __ldg(csr_ptr + row); end = __ldg(csr_ptr + row + 1); }
+    const int deg = end - beg;
+    if (deg <= 32) {
+        // the branch is uniform over the 8 lanes of a row; the shuffles name exactly those lanes
+        const unsigned gmask = 0xffu << (sub * 8);
+        float x[4];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = beg + sl + 8 * j;
+            x[j] = c < end ? __ldg(logits + c) : -INFINITY;
+            m = fmaxf(m, x[j]);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o));
+        float den = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            x[j] = beg + sl + 8 * j < end ? expf(x[j] - m) : 0.f;
+            den += x[j];
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) den += __shfl_xor_sync(gmask, den, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = beg + sl + 8 * j;
+            if (c < end) {
+                const float w = x[j] / den;
+                w_csr[c] = w;
+                if (PUSH) peer_store(po, c, w);
+                if (w_eid) w_eid[__ldg(csr_eid + c)] = w;
+            }
+        }
+    }
+    // rows above 32 edges: one after the other, by the whole warp
+    unsigned todo = __ballot_sync(FULL_MASK, deg > 32 && sl == 0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int b = __shfl_sync(FULL_MASK, beg, src), e = __shfl_sync(FULL_MASK, end, src);
+        if (split_done && e - b > SPLIT_ROW) continue;        // the segment kernels own this row
+        float m = -INFINITY, sum = 0.f;
+        for (int c = b + lane; c < e; c += 32) {
+            const float x = __ldg(logits + c);
+            if (x > m) {                    // exp(-inf) = 0 covers the first element
+                sum = sum * expf(m - x) + 1.f;
+                m = x;
+            } else {
+                sum += expf(x - m);
+            }
+        }
+        const float M = warp_max(m);        // every lane holds at least one element (deg > 32): m is finite
+        const float den = warp_sum(sum * expf(m - M));
+        for (int c = b + lane; c < e; c += 32) {
+            const float w = expf(__ldg(logits + c) - M) / den;
             w_csr[c] = w;
             if (PUSH) peer_store(po, c, w);
-            if (w_eid) w_eid[csr_eid[c]] = w;
+            if (w_eid) w_eid[__ldg(csr_eid + c)] = w;
         }
-        return;
     }
+}
+
+// one CTA per segment of a split row: (max, sum of exp(x - max)) of the segment
+__global__ void __launch_bounds__(256)
+softmax_seg_stats_kernel(SplitSide sp, const float* __restrict__ logits, int64_t row_begin, int64_t row_end,
+                         float2* __restrict__ stats) {
+    __shared__ float s_red[8];
+    const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = __ldg(sp.seg_row + s);
+    if (row < row_begin || row >= row_end) return;
+    const int beg = __ldg(sp.seg_beg + s), end = __ldg(sp.seg_end + s);
     float m = -INFINITY;
-    for (int c = beg + lane; c < end; c += 32) m = fmaxf(m, logits[c]);
+    for (int c = beg + threadIdx.x; c < end; c += 256) m = fmaxf(m, __ldg(logits + c));
     m = warp_max(m);
-    float den = 0.f;
-    for (int c = beg + lane; c < end; c += 32) den += expf(logits[c] - m);
-    den = warp_sum(den);
-    for (int c = beg + lane; c < end; c += 32) {
-        const float w = expf(logits[c] - m) / den;
-        w_csr[c] = w;
-        if (w_eid) w_eid[csr_eid[c]] = w;
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    float M = s_red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) M = fmaxf(M, s_red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int c = beg + threadIdx.x; c < end; c += 256) sum += expf(__ldg(logits + c) - M);
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = s_red[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t += s_red[w];
+        stats[s] = make_float2(M, t);
     }
-    if (PUSH) {     // second pass over the row (each lane re-reads its own stores) so the loop above still unrolls
-        for (int c = beg + lane; c < end; c += 32) peer_store(po, c, w_csr[c]);
+}
+
+// one CTA per segment: merge the row's segment statistics (every CTA of the row repeats the same fixed-order
+// merge, a few hundred values at most), then write this segment's weights
+template <bool PUSH>
+__global__ void __launch_bounds__(256)
+softmax_seg_write_kernel(SplitSide sp, const float2* __restrict__ stats, const float* __restrict__ logits,
+                         const int32_t* __restrict__ csr_eid, int64_t row_begin, int64_t row_end,
+                         float* __restrict__ w_csr, float* __restrict__ w_eid, PeerOut po) {
+    __shared__ float s_M, s_den;
+    const int s = blockIdx.x, lane = threadIdx.x & 31;
+    const int row = __ldg(sp.seg_row + s);
+    if (row < row_begin || row >= row_end) return;
+    if (threadIdx.x < 32) {
+        const int li = __ldg(sp.seg_long + s);
+        const int s0 = __ldg(sp.long_seg0 + li), n = __ldg(sp.long_nseg + li);
+        float m = -INFINITY;
+        for (int i = lane; i < n; i += 32) m = fmaxf(m, stats[s0 + i].x);
+        const float M = warp_max(m);
+        float t = 0.f;
+        for (int i = lane; i < n; i += 32) {
+            const float2 q = stats[s0 + i];
+            t += q.y * expf(q.x - M);
+        }
+        t = warp_sum(t);
+        if (lane == 0) { s_M = M; s_den = t; }
+    }
+    __syncthreads();
+    const float M = s_M, den = s_den;
+    const int beg = __ldg(sp.seg_beg + s), end = __ldg(sp.seg_end + s);
+    for (int c = beg + threadIdx.x; c < end; c += 256) {
+        const float w = expf(__ldg(logits + c) - M) / den;
+        w_csr[c] = w;
+        if (PUSH) peer_store(po, c, w);
+        if (w_eid) w_eid[__ldg(csr_eid + c)] = w;
     }
 }
 
@@ -349,14 +460,29 @@ extern "C" int kgat_segment_softmax_push(const kgat_graph_t* g, int64_t row_begi
     if (pg && g->n_edges > 0) KGAT_REQUIRE(peer_aliases(pg, w_csr, sizeof(float) * g->n_edges, &po));
     if (row_begin == row_end || g->n_edges == 0) return KGAT_OK;
     const int64_t rows = row_end - row_begin;
-    const int64_t blocks = (rows * 32 + 255) / 256;
+    const int64_t blocks = (rows + SM_ROWS_PER_CTA - 1) / SM_ROWS_PER_CTA;
+    cudaStream_t st = as_stream(stream);
+    const bool split = split_active(g, 0);
     if (pg)
-        segment_softmax_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
-            g->csr_ptr, g->csr_eid, row_begin, row_end, logits_csr, w_csr, w_eid, po);
+        segment_softmax_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+            g->csr_ptr, g->csr_eid, row_begin, row_end, logits_csr, w_csr, w_eid, split ? 1 : 0, po);
     else
-        segment_softmax_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
-            g->csr_ptr, g->csr_eid, row_begin, row_end, logits_csr, w_csr, w_eid, po);
+        segment_softmax_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+            g->csr_ptr, g->csr_eid, row_begin, row_end, logits_csr, w_csr, w_eid, split ? 1 : 0, po);
     KGAT_LAUNCH_CHECK();
+    if (split) {
+        const SplitSide sp = split_side(g, 0);
+        float2* stats = reinterpret_cast<float2*>(g->split_scratch);
+        softmax_seg_stats_kernel<<<sp.n_seg, 256, 0, st>>>(sp, logits_csr, row_begin, row_end, stats);
+        KGAT_LAUNCH_CHECK();
+        if (pg)
+            softmax_seg_write_kernel<true><<<sp.n_seg, 256, 0, st>>>(sp, stats, logits_csr, g->csr_eid, row_begin,
+                                                                   row_end, w_csr, w_eid, po);
+        else
+            softmax_seg_write_kernel<false><<<sp.n_seg, 256, 0, st>>>(sp, stats, logits_csr, g->csr_eid, row_begin,
+                                                                    row_end, w_csr, w_eid, po);
+        KGAT_LAUNCH_CHECK();
+    }
     return KGAT_OK;
 }
 

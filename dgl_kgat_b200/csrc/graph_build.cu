@@ -7,6 +7,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
+#include "split.cuh"
 
 namespace kgat {
 
@@ -129,10 +130,88 @@ int sort_edges_by_head_rel(const kgat_graph_t* g, const int32_t* head, const int
     return KGAT_OK;
 }
 
+// Segment table of one side (split.cuh): one CTA walks the row pointer in chunks of 1024 rows; a block-wide
+// exclusive scan of (segments, split rows) per chunk gives every split row its slots, so rows appear in
+// ascending order and the segments of a row in edge order - the table is a pure function of the pointer.
+// A row of deg > SPLIT_ROW edges gets n = ceil(deg / SPLIT_SEG) segments of ceil(deg / n) edges rounded up
+// to a multiple of 32 (the per-warp slices of gather_row_cta stay 32-aligned).
+__global__ void __launch_bounds__(1024)
+split_table_kernel(const int32_t* __restrict__ ptr, int n_rows, SplitSide sp, int32_t* __restrict__ counts) {
+    __shared__ int s_ws[32], s_wl[32];
+    __shared__ int s_base_s, s_base_l;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_base_s = 0; s_base_l = 0; }
+    __syncthreads();
+    for (int r0 = 0; r0 < n_rows; r0 += 1024) {
+        const int r = r0 + tid;
+        int beg = 0, deg = 0;
+        if (r < n_rows) { beg = ptr[r]; deg = ptr[r + 1] - beg; }
+        const int is_long = deg > SPLIT_ROW ? 1 : 0;
+        const int nseg = is_long ? (deg + SPLIT_SEG - 1) / SPLIT_SEG : 0;
+        if (!__syncthreads_or(is_long)) continue;           // chunks without a split row (nearly all) cost one barrier
+        int is = nseg, il = is_long;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(FULL_MASK, is, o), b = __shfl_up_sync(FULL_MASK, il, o);
+            if (lane >= o) { is += a; il += b; }
+        }
+        if (lane == 31) { s_ws[warp] = is; s_wl[warp] = il; }
+        __syncthreads();
+        if (warp == 0) {
+            int a = s_ws[lane], b = s_wl[lane], ia = a, ib = b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int x = __shfl_up_sync(FULL_MASK, ia, o), y = __shfl_up_sync(FULL_MASK, ib, o);
+                if (lane >= o) { ia += x; ib += y; }
+            }
+            s_ws[lane] = ia - a;
+            s_wl[lane] = ib - b;
+        }
+        __syncthreads();
+        const int s0 = s_base_s + s_ws[warp] + is - nseg, li = s_base_l + s_wl[warp] + il - is_long;
+        if (is_long) {
+            sp.long_row[li] = r;
+            sp.long_seg0[li] = s0;
+            sp.long_nseg[li] = nseg;
+            const int per = (((deg + nseg - 1) / nseg) + 31) & ~31;
+            for (int i = 0; i < nseg; ++i) {
+                const int b = min(beg + deg, beg + i * per), e = min(beg + deg, b + per);
+                sp.seg_row[s0 + i] = r;
+                sp.seg_beg[s0 + i] = b;
+                sp.seg_end[s0 + i] = e;
+                sp.seg_long[s0 + i] = li;
+            }
+        }
+        __syncthreads();
+        if (tid == 1023) { s_base_s = s0 + nseg; s_base_l = li + is_long; }
+        __syncthreads();
+    }
+    if (tid == 0) { counts[0] = s_base_s; counts[1] = s_base_l; }
+}
+
 }  // namespace
 }  // namespace kgat
 
 using namespace kgat;
+
+extern "C" size_t kgat_graph_split_ints(int64_t n_edges) {
+    if (n_edges < 0) return 0;
+    return static_cast<size_t>(SPLIT_HEADER + 2 * split_side_ints(n_edges));
+}
+
+extern "C" int kgat_graph_split_build(const kgat_graph_t* g, int32_t* counts_out_host, kgat_stream_t stream) {
+    KGAT_REQUIRE(g && counts_out_host && g->split && g->csr_ptr && g->csc_ptr);
+    KGAT_REQUIRE(g->n_nodes > 0 && g->n_nodes < (int64_t(1) << 31) && g->n_edges >= 0);
+    cudaStream_t st = as_stream(stream);
+    KGAT_CUDA(cudaMemsetAsync(g->split, 0, sizeof(int32_t) * SPLIT_HEADER, st));
+    split_table_kernel<<<1, 1024, 0, st>>>(g->csr_ptr, static_cast<int>(g->n_nodes), split_side(g, 0), g->split);
+    KGAT_LAUNCH_CHECK();
+    split_table_kernel<<<1, 1024, 0, st>>>(g->csc_ptr, static_cast<int>(g->n_nodes), split_side(g, 1), g->split + 2);
+    KGAT_LAUNCH_CHECK();
+    KGAT_CUDA(cudaMemcpyAsync(counts_out_host, g->split, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    KGAT_CUDA(cudaStreamSynchronize(st));
+    return KGAT_OK;
+}
 
 extern "C" size_t kgat_graph_build_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t n_rel) {
     (void)n_nodes; (void)n_rel;

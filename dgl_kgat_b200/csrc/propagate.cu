@@ -22,6 +22,7 @@
 #include <cstring>
 
 #include "peer.cuh"
+#include "split.cuh"
 
 namespace kgat {
 namespace {
@@ -98,6 +99,59 @@ __device__ __forceinline__ float4 gather_row_cta(const int32_t* __restrict__ idx
     return t;
 }
 
+// Rows with more than SPLIT_ROW edges (split.cuh; the hottest entities of a power-law graph: 10^5..10^6 edges)
+// are gathered by a PRE-PASS in front of the kernel that owns the row: one CTA per segment of <= SPLIT_SEG
+// edges writes a partial sum, one warp per split row adds the partials in segment order into the row of `out`
+// where the main kernel picks the total up instead of walking the row (fixed order: deterministic).
+template <int W>
+__global__ void __launch_bounds__(THREADS)
+split_gather_kernel(SplitSide sp, const int32_t* __restrict__ idx, const float* __restrict__ wgt,
+                    const float* __restrict__ feat, int row_begin, int row_end, float* __restrict__ partial) {
+    __shared__ float4 sPart[WARPS * 32];
+    const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = __ldg(sp.seg_row + s);
+    if (row < row_begin || row >= row_end) return;            // CTA-uniform
+    const float4 t = gather_row_cta<W>(idx, wgt, __ldg(sp.seg_beg + s), __ldg(sp.seg_end + s), feat, sPart, warp, lane);
+    if (warp == 0 && lane < W / 4) *reinterpret_cast<float4*>(partial + static_cast<size_t>(s) * W + lane * 4) = t;
+}
+
+template <int W>
+__global__ void __launch_bounds__(THREADS)
+split_combine_kernel(SplitSide sp, int n_long, const float* __restrict__ partial, int row_begin, int row_end,
+                     float* __restrict__ out) {
+    const int li = blockIdx.x * WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (li >= n_long || lane >= W / 4) return;
+    const int row = __ldg(sp.long_row + li);
+    if (row < row_begin || row >= row_end) return;
+    const int s0 = __ldg(sp.long_seg0 + li), n = __ldg(sp.long_nseg + li);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+        const float4 v = ldg4(partial + static_cast<size_t>(s0 + i) * W + lane * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * W + lane * 4) = acc;
+}
+
+// side 0: CSR (idx = csr_src), side 1: CSC (idx = csc_dst).  Returns true when the rows above SPLIT_ROW edges of
+// [row_begin, row_end) now hold their gathered sums in `out` ((n_nodes, W) row-major).
+template <int W>
+int split_prepass(const kgat_graph_t* g, int side, const float* wgt, const float* feat, int row_begin, int row_end,
+                  float* out, cudaStream_t st, bool* ran) {
+    *ran = false;
+    if (!split_active(g, side)) return KGAT_OK;
+    static_assert(W <= KGAT_SPLIT_SCRATCH_WIDTH, "scratch rows are KGAT_SPLIT_SCRATCH_WIDTH floats");
+    const SplitSide sp = split_side(g, side);
+    const int32_t* idx = side == 0 ? g->csr_src : g->csc_dst;
+    split_gather_kernel<W><<<sp.n_seg, THREADS, 0, st>>>(sp, idx, wgt, feat, row_begin, row_end, g->split_scratch);
+    KGAT_LAUNCH_CHECK();
+    split_combine_kernel<W><<<(sp.n_long + WARPS - 1) / WARPS, THREADS, 0, st>>>(sp, sp.n_long, g->split_scratch,
+                                                                                 row_begin, row_end, out);
+    KGAT_LAUNCH_CHECK();
+    *ran = true;
+    return KGAT_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -137,7 +191,7 @@ layer_fwd_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict_
                  const float* __restrict__ h_in, const float* __restrict__ W2,
                  const float* __restrict__ drop_mask, float slope, float* __restrict__ h_nb,
                  float* __restrict__ act, float* __restrict__ h_out, float* __restrict__ concat,
-                 int64_t cstride, int64_t out_off, int64_t in_off, PeerOut po) {
+                 int64_t cstride, int64_t out_off, int64_t in_off, int split_done, PeerOut po) {
     using S = FwdSmem<DIN, DOUT, EPI>;
     constexpr int LDW = S::LDW, LDZ = S::LDZ, LDY = S::LDY;
     constexpr int LPI = DIN / 4;
@@ -195,6 +249,12 @@ layer_fwd_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict_
             if (!sLong[rl]) continue;                     // CTA-uniform
             const int row = row0 + rl;
             const int beg = __ldg(csr_ptr + row), end = __ldg(csr_ptr + row + 1);
+            if (split_done && end - beg > SPLIT_ROW) {    // gathered by the pre-pass (split_prepass) into h_nb
+                if (warp == rl % WARPS)
+                    finish_row(row, rl, *reinterpret_cast<const float4*>(h_nb + static_cast<size_t>(row) * DIN +
+                                                                         (lane % LPI) * 4));
+                continue;
+            }
             const float4 hn = gather_row_cta<DIN>(csr_src, w_csr, beg, end, h_in, sPart, warp, lane);
             if (warp == rl % WARPS) finish_row(row, rl, hn);
         }
@@ -668,7 +728,8 @@ reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int n
 template <int D>
 __device__ __forceinline__ float4 gather_block_rows(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
                                                     const float* __restrict__ w_csc, const float* __restrict__ feat,
-                                                    int first, int row_end, float4* sPart, int warp, int lane) {
+                                                    int first, int row_end, float4* sPart, int warp, int lane,
+                                                    const float* pre) {
     const int row = first + warp;
     int beg = 0, end = 0;
     if (row < row_end) { beg = __ldg(csc_ptr + row); end = __ldg(csc_ptr + row + 1); }
@@ -680,6 +741,10 @@ __device__ __forceinline__ float4 gather_block_rows(const int32_t* __restrict__ 
             if (r >= row_end) break;
             const int b = __ldg(csc_ptr + r), e = __ldg(csc_ptr + r + 1);
             if (e - b <= LONG_ROW) continue;
+            if (pre && e - b > SPLIT_ROW) {      // gathered by the pre-pass (split_prepass) into row r of `pre`
+                if (w == warp) g = *reinterpret_cast<const float4*>(pre + static_cast<size_t>(r) * D + (lane % (D / 4)) * 4);
+                continue;
+            }
             const float4 t = gather_row_cta<D>(csc_dst, w_csc, b, e, feat, sPart, warp, lane);
             if (w == warp) g = t;
         }
@@ -697,12 +762,13 @@ template <int D>
 __global__ void __launch_bounds__(THREADS)
 csc_gather_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
                   const float* __restrict__ w_csc, int row_begin, int row_end, const float* __restrict__ add,
-                  const float* __restrict__ feat, float* __restrict__ out) {
+                  const float* __restrict__ feat, float* __restrict__ out, int split_done) {
     constexpr int LP = D / 4;
     __shared__ float4 sPart[WARPS * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int first = row_begin + blockIdx.x * WARPS, row = first + warp;
-    float4 g = gather_block_rows<D>(csc_ptr, csc_dst, w_csc, feat, first, row_end, sPart, warp, lane);
+    float4 g = gather_block_rows<D>(csc_ptr, csc_dst, w_csc, feat, first, row_end, sPart, warp, lane,
+                                    split_done ? out : nullptr);
     if (row < row_end && lane < LP) {
         const size_t o = static_cast<size_t>(row) * D + lane * 4;
         if (add) {
@@ -720,12 +786,13 @@ input_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict_
                  const float* __restrict__ w_csc, int row_begin, int row_end,
                  const float* __restrict__ d_concat, const int32_t* __restrict__ dc_slot, int64_t cstride,
                  int64_t in_off, const float* __restrict__ dx_direct, const float* __restrict__ dh_nb,
-                 float* __restrict__ d_entity, PeerOut po) {
+                 float* __restrict__ d_entity, int split_done, PeerOut po) {
     constexpr int LP = D / 4;
     __shared__ float4 sPart[WARPS * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int first = row_begin + blockIdx.x * WARPS, row = first + warp;
-    float4 g = gather_block_rows<D>(csc_ptr, csc_dst, w_csc, dh_nb, first, row_end, sPart, warp, lane);
+    float4 g = gather_block_rows<D>(csc_ptr, csc_dst, w_csc, dh_nb, first, row_end, sPart, warp, lane,
+                                    split_done ? d_entity : nullptr);
     if (row < row_end && lane < LP) {
         const size_t o = static_cast<size_t>(row) * D + lane * 4;
         const float4 t = ldg4(dx_direct + o);
@@ -781,9 +848,12 @@ int launch_fwd_t(const FwdArgs& a) {
     }
     const int rows = a.row_end - a.row_begin;
     const unsigned grid = (rows + TM - 1) / TM;
+    bool split_done = false;
+    const int rc = split_prepass<DIN>(a.g, 0, a.w_csr, a.h_in, a.row_begin, a.row_end, a.h_nb, a.st, &split_done);
+    if (rc != KGAT_OK) return rc;
     layer_fwd_kernel<DIN, DOUT, PUSH, EPI><<<grid, THREADS, smem, a.st>>>(
         a.g->csr_ptr, a.g->csr_src, a.w_csr, a.row_begin, a.row_end, a.h_in, a.W2, a.drop_mask, a.slope,
-        a.h_nb, a.act, a.h_out, a.concat, a.cstride, a.out_off, a.in_off, a.po);
+        a.h_nb, a.act, a.h_out, a.concat, a.cstride, a.out_off, a.in_off, split_done ? 1 : 0, a.po);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }
@@ -958,12 +1028,16 @@ extern "C" int kgat_input_bwd_push(const kgat_graph_t* g, int64_t row_begin, int
     const int rows = static_cast<int>(row_end - row_begin);
     const unsigned grid = (rows + WARPS - 1) / WARPS;
     cudaStream_t st = as_stream(stream);
+    bool split_done = false;
 #define LAUNCH_T(D, P)                                                                                     \
     input_bwd_kernel<D, P><<<grid, THREADS, 0, st>>>(g->csc_ptr, g->csc_dst, w_csc, (int)row_begin,        \
                                                      (int)row_end, d_concat, dc_row_slot, concat_stride,   \
-                                                     in_off, dx_direct, dh_nb, d_entity, po)
+                                                     in_off, dx_direct, dh_nb, d_entity, split_done ? 1 : 0, po)
 #define LAUNCH(D)                                                                                          \
     if (d == D) {                                                                                          \
+        const int rc = split_prepass<D>(g, 1, w_csc, dh_nb, (int)row_begin, (int)row_end, d_entity, st,    \
+                                        &split_done);                                                      \
+        if (rc != KGAT_OK) return rc;                                                                      \
         if (pg) LAUNCH_T(D, true); else LAUNCH_T(D, false);                                                \
         KGAT_LAUNCH_CHECK();                                                                               \
         return KGAT_OK;                                                                                    \
@@ -992,10 +1066,14 @@ extern "C" int kgat_csc_gather(const kgat_graph_t* g, int64_t row_begin, int64_t
     const int rows = static_cast<int>(row_end - row_begin);
     const unsigned grid = (rows + WARPS - 1) / WARPS;
     cudaStream_t st = as_stream(stream);
+    bool split_done = false;
 #define LAUNCH(D)                                                                                          \
     if (d == D) {                                                                                          \
+        const int rc = split_prepass<D>(g, 1, w_csc, feat, (int)row_begin, (int)row_end, out, st,          \
+                                        &split_done);                                                      \
+        if (rc != KGAT_OK) return rc;                                                                      \
         csc_gather_kernel<D><<<grid, THREADS, 0, st>>>(g->csc_ptr, g->csc_dst, w_csc, (int)row_begin,      \
-                                                       (int)row_end, add, feat, out);                      \
+                                                       (int)row_end, add, feat, out, split_done ? 1 : 0);  \
         KGAT_LAUNCH_CHECK();                                                                               \
         return KGAT_OK;                                                                                    \
     }

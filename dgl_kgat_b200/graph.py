@@ -11,6 +11,7 @@ on the device (include/kgat_b200.h).  Edge id == triplet row, src = tail, dst = 
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch as th
@@ -38,13 +39,27 @@ class DeviceGraph:
                 self.arrays[name] = th.empty(n, dtype=th.int32, device=device)
             self.struct = _lib.KgatGraph(self.n_nodes, E, self.n_rel,
                                          *[self.arrays[n].data_ptr() for n in _lib.GRAPH_ARRAYS])
+            self.struct.split = self.struct.split_scratch = None
             ws_bytes = lib.kgat_graph_build_workspace_bytes(self.n_nodes, E, self.n_rel)
             ws = th.empty(max(ws_bytes, 16), dtype=th.uint8, device=device)
             _lib.check(lib.kgat_graph_build(ctypes.byref(self.struct), cols[0].data_ptr(), cols[1].data_ptr(),
                                             cols[2].data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()),
                        "kgat_graph_build")
-            # the build reads cols / ws asynchronously; keep them alive until it has run
-            th.cuda.current_stream().synchronize()
+            # Rows of more than SPLIT_ROW edges (hot entities of a power-law KG) are cut into segments that the
+            # aggregation / softmax kernels hand to one CTA each; the tables are tiny and usually empty.  The call
+            # synchronises, which also keeps cols / ws alive until the asynchronous build has read them.
+            self.split_table = th.empty(lib.kgat_graph_split_ints(E), dtype=th.int32, device=device)
+            self.struct.split = self.split_table.data_ptr()
+            counts = (ctypes.c_int32 * 4)()
+            _lib.check(lib.kgat_graph_split_build(ctypes.byref(self.struct), counts, _lib.stream_ptr()),
+                       "kgat_graph_split_build")
+            self.split_counts = tuple(int(c) for c in counts)
+            (self.struct.n_csr_seg, self.struct.n_csr_long, self.struct.n_csc_seg,
+             self.struct.n_csc_long) = self.split_counts
+            n_seg = max(self.struct.n_csr_seg, self.struct.n_csc_seg)
+            if n_seg > 0 and os.environ.get("KGAT_SPLIT_ROWS", "1") != "0":
+                self.split_scratch = th.empty(n_seg * _lib.SPLIT_SCRATCH_WIDTH, dtype=th.float32, device=device)
+                self.struct.split_scratch = self.split_scratch.data_ptr()
 
     @property
     def ref(self):

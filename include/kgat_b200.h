@@ -83,7 +83,20 @@ typedef struct kgat_graph {
     int32_t *bk_pos;    /* [E] CSR position */
     int32_t *bk_head;   /* [E] */
     int32_t *bk_tail;   /* [E] */
+    /* Row splitting for power-law graphs (filled by kgat_graph_split_build; all NULL / 0 = never split).
+     * A hot entity of a real KG has 10^4..10^6 edges (dataset.py:84-93 stacks every interaction of an
+     * item onto the item's row); such a row must not be walked by one warp or one CTA.  Rows with more
+     * than KGAT_SPLIT_ROW in-edges (CSR side) / out-edges (CSC side) are cut into segments of at most
+     * KGAT_SPLIT_SEG edges; the aggregation and softmax entry points handle them in a pre-pass with one
+     * CTA per SEGMENT and add the partial results in segment order (deterministic). */
+    int32_t *split;          /* [kgat_graph_split_ints(E)] segment tables of both sides */
+    float   *split_scratch;  /* [max(n_csr_seg, n_csc_seg) * KGAT_SPLIT_SCRATCH_WIDTH] partial sums */
+    int32_t  n_csr_seg, n_csr_long, n_csc_seg, n_csc_long;   /* host copies of the table sizes */
 } kgat_graph_t;
+
+#define KGAT_SPLIT_ROW 2048
+#define KGAT_SPLIT_SEG 1024
+#define KGAT_SPLIT_SCRATCH_WIDTH 128
 
 /* (1) graph construction -- replaces DGLGraph()/add_nodes/add_edges/readonly
  *     (dataset.py:112-130, :203-211) and the per-relation filter_edges scans
@@ -94,6 +107,14 @@ KGAT_API size_t kgat_graph_build_workspace_bytes(int64_t n_nodes, int64_t n_edge
 KGAT_API int    kgat_graph_build(const kgat_graph_t* g, const int32_t* head, const int32_t* rel,
                         const int32_t* tail, void* workspace, size_t workspace_bytes,
                         kgat_stream_t stream);
+
+/* (1') segment tables of the rows that are split (see kgat_graph_t).  Reads g->csr_ptr / g->csc_ptr,
+ *      fills g->split (caller-allocated, kgat_graph_split_ints(E) int32) and returns the four table
+ *      sizes {n_csr_seg, n_csr_long, n_csc_seg, n_csc_long} in counts_out_host - the caller stores them in
+ *      its kgat_graph_t and allocates split_scratch when any is non-zero.  Synchronises the stream
+ *      (one-off per graph).  Deterministic: rows ascending, segments of a row in edge order. */
+KGAT_API size_t kgat_graph_split_ints(int64_t n_edges);
+KGAT_API int    kgat_graph_split_build(const kgat_graph_t* g, int32_t* counts_out_host, kgat_stream_t stream);
 
 /* (2) TransR attention logits pi(h,r,t) = (e_t W_r) . tanh(e_h W_r + e_r) for every
  *     edge, relation-grouped -- replaces the loop of apply_edges(_att_score)

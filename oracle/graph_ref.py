@@ -85,3 +85,28 @@ def build_runs(struct, n_rel):
     run_head = bk_head[starts].astype(np.int32) if E else np.zeros(0, np.int32)
     rel_run_ptr = np.array([bk_run[p] if p < E else n_runs for p in rel_ptr[: n_rel + 1]], dtype=np.int32)
     return {"bk_run": bk_run, "run_ptr": run_ptr, "run_head": run_head, "rel_run_ptr": rel_run_ptr, "n_runs": n_runs}
+
+
+def split_table(ptr, split_row, split_seg):
+    """Segment table of one side of the graph (kgat_graph_split_build, include/kgat_b200.h): every row with more
+    than ``split_row`` edges, ascending, is cut into n = ceil(deg / split_seg) segments of ceil(deg / n) edges
+    rounded up to a multiple of 32, in edge order.  This structure is not in the reference (DGL's kernels walk
+    a row with one thread block at most); it only decides which CTA sums which edges."""
+    ptr = np.asarray(ptr, dtype=np.int64)
+    deg = np.diff(ptr)
+    rows = np.flatnonzero(deg > split_row)
+    out = {k: [] for k in ("seg_row", "seg_beg", "seg_end", "seg_long", "long_row", "long_seg0", "long_nseg")}
+    for li, r in enumerate(rows):
+        d, beg = int(deg[r]), int(ptr[r])
+        n = -(-d // split_seg)
+        per = (-(-d // n) + 31) & ~31
+        out["long_row"].append(int(r))
+        out["long_seg0"].append(len(out["seg_row"]))
+        out["long_nseg"].append(n)
+        for i in range(n):
+            b = min(beg + d, beg + i * per)
+            out["seg_row"].append(int(r))
+            out["seg_beg"].append(b)
+            out["seg_end"].append(min(beg + d, b + per))
+            out["seg_long"].append(li)
+    return {k: np.asarray(v, dtype=np.int32) for k, v in out.items()}

@@ -67,13 +67,36 @@ def check_structure(trip, N, R, dev):
             ref = want[name]
         n = len(ref)
         assert np.array_equal(got[:n], ref), "structure array %s differs" % name
+    check_split_tables(dg, want)
     return dg
 
 
-@pytest.mark.parametrize("case", ["tiny", "golden", "multigraph", "single_edge", "empty", "isolated_nodes"])
+def check_split_tables(dg, want):
+    """kgat_graph_split_build against oracle/graph_ref.split_table, both sides, bit-exact."""
+    E = dg.n_edges
+    cap_l = E // _lib.SPLIT_ROW + 1
+    cap_s = E // _lib.SPLIT_SEG + cap_l + 1
+    side_ints = 4 * cap_s + 3 * cap_l
+    tab = dg.split_table.cpu().numpy()
+    assert len(tab) == 8 + 2 * side_ints
+    for side, ptr in enumerate((want["csr_ptr"], want["csc_ptr"])):
+        ref = graph_ref.split_table(ptr, _lib.SPLIT_ROW, _lib.SPLIT_SEG)
+        n_seg, n_long = len(ref["seg_row"]), len(ref["long_row"])
+        assert dg.split_counts[2 * side: 2 * side + 2] == (n_seg, n_long)
+        assert tuple(tab[2 * side: 2 * side + 2]) == (n_seg, n_long)
+        base = 8 + side * side_ints
+        for k, name in enumerate(("seg_row", "seg_beg", "seg_end", "seg_long")):
+            assert np.array_equal(tab[base + k * cap_s: base + k * cap_s + n_seg], ref[name]), (side, name)
+        base += 4 * cap_s
+        for k, name in enumerate(("long_row", "long_seg0", "long_nseg")):
+            assert np.array_equal(tab[base + k * cap_l: base + k * cap_l + n_long], ref[name]), (side, name)
+
+
+@pytest.mark.parametrize("case", ["tiny", "tiny_skew", "golden", "multigraph", "single_edge", "empty",
+                                  "isolated_nodes"])
 def test_graph_build_bit_exact(dev, golden_small, case):
-    if case == "tiny":
-        ck = synth_ckg("tiny")
+    if case in ("tiny", "tiny_skew"):
+        ck = synth_ckg("tiny", skew=case == "tiny_skew")       # skew: rows above SPLIT_ROW edges on both sides
         trip, N, R = ck.triplets, ck.cfg.n_nodes, ck.cfg.n_relations
     elif case == "golden":
         trip, N, R = golden_small["trip"], int(golden_small["n_nodes"]), int(golden_small["n_rel"])
@@ -217,12 +240,17 @@ def test_cf_step_tiny_vs_fp64_oracle(dev, d, hidden, layers):
     emb, loss = run_cf_step(m, g, w, *[i.to(dev) for i in ids])
     p64 = cpu_params(m)
     loss64, emb64, grads64 = kgat_ref.cf_step(p64, trip, w.cpu().double(), N, *ids, 1e-4)
-    # The bar is 1e-5 relative; where the fp32 REFERENCE itself is noisier than that against fp64
-    # (narrow layers: 3-4e-5 on the weight gradients at width 16), twice its own error is allowed.
+    # The bar is 1e-5 relative.  Where the fp32 REFERENCE itself is noisier than that against fp64, the bound is a
+    # multiple of the reference's own error.  That happens at width 16 (3-4e-5 on the weight gradients) and it is
+    # conditioning, not arithmetic: the second layer has output rows of norm 1e-4 (a cancelling sum of terms of
+    # size 1e-2), F.normalize divides their gradient by that norm, and every fp32 evaluation order lands somewhere
+    # else inside the same noise band (the fp32 oracle moves from 4e-5 to 5e-6 when the attention weights are
+    # perturbed by 6e-8; no LeakyReLU sign flips are involved).  Two samples of one noise band differ by more than
+    # a factor of two now and then, so the factor is three.
     _, emb32, grads32 = kgat_ref.cf_step(cpu_params(m, th.float32), trip, w.cpu(), N, *ids, 1e-4)
 
     def bound(ref32, ref64):
-        return max(RTOL, 2.0 * max_rel(ref32.numpy(), ref64.numpy()))
+        return max(RTOL, 3.0 * max_rel(ref32.numpy(), ref64.numpy()))
     assert max_rel(emb.cpu().numpy(), emb64.numpy()) < RTOL
     assert abs(loss.item() - loss64.item()) < 1e-5 * abs(loss64.item())
     k = "entity_embed.weight"
@@ -330,6 +358,33 @@ def test_long_rows_and_skew(dev):
     loss64, emb64, grads64 = kgat_ref.cf_step(cpu_params(m), trip, w.cpu().double(), N, *ids, 1e-4)
     assert max_rel(emb.cpu().numpy(), emb64.numpy()) < RTOL
     assert max_rel(m.entity_embed.weight.grad.cpu().numpy(), grads64["entity_embed.weight"].numpy()) < RTOL
+
+
+def test_split_rows_match_unsplit_and_repeat_bit_identically(dev, monkeypatch):
+    """Rows above SPLIT_ROW edges are summed by one CTA per segment (pre-pass) instead of one CTA per row: same
+    numbers to fp32 re-association noise, bit-identical from run to run (fixed segment order, no atomics)."""
+    ck = synth_ckg("tiny", skew=True)
+    N, R, trip = ck.cfg.n_nodes, ck.cfg.n_relations, ck.triplets
+    m = make_model(N, R, dev)
+    rng = np.random.default_rng(0)
+    ids = [th.as_tensor(rng.integers(0, N, 512), device=dev) for _ in range(3)]
+
+    def run(split):
+        monkeypatch.setenv("KGAT_SPLIT_ROWS", "1" if split else "0")
+        g = CKGraph(N, trip, n_rel=R)
+        dg = g.device_graph(dev)
+        assert (dg.struct.split_scratch is not None) == split and dg.split_counts[0] > 0 and dg.split_counts[2] > 0
+        m.zero_grad(set_to_none=True)
+        w = m.compute_attention(g)
+        emb, loss = run_cf_step(m, g, w, *ids)
+        return [w.detach().clone(), emb.detach().clone(), m.entity_embed.weight.grad.clone()] + \
+            [l.res_fc_2.weight.grad.clone() for l in m.layers]
+    a, b, c = run(True), run(True), run(False)
+    for x, y in zip(a, b):
+        assert th.equal(x, y)
+    for x, y in zip(a, c):
+        assert max_rel(x.cpu().numpy(), y.cpu().numpy()) < 5e-6
+    assert abs(a[0].sum().item() - (np.bincount(trip[:, 0], minlength=N) > 0).sum()) < 1e-2      # rows sum to 1
 
 
 # =================================================================================== evaluation

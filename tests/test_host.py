@@ -71,9 +71,36 @@ def test_peer_group_struct_layout_matches_header():
 def test_graph_struct_layout_matches_header():
     text = open(os.path.join(ROOT, "include", "kgat_b200.h")).read()
     body = text[text.index("typedef struct kgat_graph {"): text.index("} kgat_graph_t;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = re.findall(r"\*(\w+);", body)
-    assert fields == _lib.GRAPH_ARRAYS
-    assert ctypes.sizeof(_lib.KgatGraph) == 3 * 8 + len(fields) * 8
+    assert fields == _lib.GRAPH_ARRAYS + ["split", "split_scratch"]
+    names = [n for n, _ in _lib.KgatGraph._fields_]
+    assert names == ["n_nodes", "n_edges", "n_rel"] + fields + ["n_csr_seg", "n_csr_long", "n_csc_seg", "n_csc_long"]
+    assert re.search(r"int32_t\s+n_csr_seg, n_csr_long, n_csc_seg, n_csc_long;", body)
+    assert ctypes.sizeof(_lib.KgatGraph) == 3 * 8 + len(fields) * 8 + 4 * 4
+    assert _lib.KgatGraph.split.offset == 3 * 8 + len(_lib.GRAPH_ARRAYS) * 8
+    for name, val in (("ROW", _lib.SPLIT_ROW), ("SEG", _lib.SPLIT_SEG), ("SCRATCH_WIDTH", _lib.SPLIT_SCRATCH_WIDTH)):
+        assert "#define KGAT_SPLIT_%s %d" % (name, val) in text
+
+
+def test_split_table_oracle_on_a_power_law_pointer():
+    """The segment tables of kgat_graph_split_build restated in numpy (oracle/graph_ref.split_table): rows above
+    SPLIT_ROW edges ascending, ceil(deg / SPLIT_SEG) segments of equal 32-aligned length, in edge order."""
+    from oracle import graph_ref
+    deg = np.array([0, 5, 2048, 2049, 7, 100000, 1, 4096, 3000], dtype=np.int64)
+    ptr = np.concatenate([[0], np.cumsum(deg)])
+    t = graph_ref.split_table(ptr, _lib.SPLIT_ROW, _lib.SPLIT_SEG)
+    assert t["long_row"].tolist() == [3, 5, 7, 8]
+    assert t["long_nseg"].tolist() == [3, 98, 4, 3]
+    assert t["long_seg0"].tolist() == [0, 3, 101, 105]
+    for li, row in enumerate(t["long_row"]):
+        s0, n = t["long_seg0"][li], t["long_nseg"][li]
+        segs = [(t["seg_beg"][s], t["seg_end"][s]) for s in range(s0, s0 + n)]
+        assert segs[0][0] == ptr[row] and segs[-1][1] == ptr[row + 1]
+        assert all(a[1] == b[0] for a, b in zip(segs, segs[1:]))                # contiguous, in edge order
+        assert all(0 < e - b <= _lib.SPLIT_SEG for b, e in segs)
+        assert all((b - ptr[row]) % 32 == 0 for b, _ in segs)
+        assert (t["seg_row"][s0:s0 + n] == row).all() and (t["seg_long"][s0:s0 + n] == li).all()
 
 
 def test_no_cpu_fallback():
