@@ -56,6 +56,9 @@ def parse():
     p.add_argument("--ref-budget-s", type=float, default=150.0, help="time budget of --impl reference")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-eval", action="store_true")
+    p.add_argument("--no-skew", action="store_true", help="skip the Zipf-skewed graph (N = 1)")
+    p.add_argument("--skew", action="store_true", help="diagnostic: run the WHOLE bench on the Zipf-skewed graph "
+                                                       "(per-kernel table of the skewed step; not the headline config)")
     return p.parse_args()
 
 
@@ -398,6 +401,47 @@ def run_10x(dev, rank, world, barrier, max_over_ranks, no_eval=False, steps=5, w
     return out
 
 
+def run_skew(config, dev, ms_uniform, steps=5, warmup=2):
+    """The same step on the Zipf-skewed graph of the same size (synth_ckg(..., skew=True): item popularity and KG
+    tails drawn from zipf(1.5), so single rows hold 10^5..10^6 edges, as the hot entities of a real KG do).
+    Reported next to the uniform graph's step: the long rows are split across CTAs (include/kgat_b200.h,
+    kgat_graph_split_build), so the step should cost about the same per edge."""
+    from dgl_kgat_b200 import models
+    from dgl_kgat_b200.graph import CKGraph
+    from dgl_kgat_b200.graphed import GraphedCFStep
+    from dgl_kgat_b200.synth import synth_ckg
+    ck = synth_ckg(config, seed=1234, skew=True)
+    cfg = ck.cfg
+    N, E, R = cfg.n_nodes, cfg.n_edges, cfg.n_relations
+    th.manual_seed(1234)
+    model = models.Model(True, 64, "kgat", 3, 64, 0.0, n_entities=N, n_relations=R, relation_dim=64,
+                         reg_lambda_kg=REG, reg_lambda_gnn=REG).to(dev)
+    g = CKGraph(N, ck.triplets, n_rel=R)
+    g.ndata["id"] = g.ndata["id"].to(dev)
+    dg = g.device_graph(dev)
+    ids = [b.to(dev) for b in make_batches(cfg, 1)[0]]
+    step = GraphedCFStep(model, g, BATCH, refresh_attention=True)
+    for dst, src in zip(step.ids, ids):
+        dst.copy_(src)
+    for _ in range(warmup):
+        step.graph.replay()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    th.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step.graph.replay()
+    e1.record()
+    th.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    indeg = np.bincount(ck.triplets[:, 0], minlength=N)
+    outdeg = np.bincount(ck.triplets[:, 2], minlength=N)
+    return {"config": cfg.name + ", zipf(1.5) tails / items", "edges": E, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "edges_per_s": E / (ms * 1e-3), "vs_uniform_step": ms / ms_uniform,
+            "max_in_degree": int(indeg.max()), "max_out_degree": int(outdeg.max()),
+            "rows_split": {"csr": dg.split_counts[1], "csc": dg.split_counts[3]},
+            "segments": {"csr": dg.split_counts[0], "csc": dg.split_counts[2]}, "loss": float(step.loss.item())}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch.distributed as tdist
@@ -417,7 +461,7 @@ def run_ours(args):
         tdist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().kgat_device_check(), "kgat_device_check")
 
-    ck = synth_ckg(args.config, seed=1234)
+    ck = synth_ckg(args.config, seed=1234, skew=args.skew)
     cfg = ck.cfg
     N, E, R = cfg.n_nodes, cfg.n_edges, cfg.n_relations
     th.manual_seed(1234)
@@ -520,6 +564,17 @@ def run_ours(args):
         ms_step = ms_total / args.steps
         value = E / (ms_step * 1e-3)
         nvlink = None
+        if distributed and rank == 0 and nv0 is None:
+            # no counters: DERIVED from the buffers the push kernels store (weights of the owned in-edges, owned
+            # rows of h_1..h_{L-1}, of every dh_nb and of d_entity; the 3B loss rows and the dW2 slots are small)
+            mc = bool(dk.peer is not None and dk.peer.multicast)
+            rows0, e0_ = dk.part.r1 - dk.part.r0, dk.dg_in.n_edges
+            per_dest = 4 * (e0_ + rows0 * (sum(dims[1:-1]) + sum(dims[:-1]) + dims[0]))
+            nvlink = {"unavailable": "nvidia-smi nvlink -gt d reports N/A for every link on this box",
+                      "multicast": mc,
+                      "derived_tx_MB_per_step_rank0": per_dest * (1 if mc else world - 1) / 1e6,
+                      "derived_note": "bytes of rank 0's pushed rows x destinations (one with the NVSwitch "
+                                      "multicast, world - 1 with unicast stores)"}
         if nv0 is not None:
             nv1 = nvlink_tx_rx_kib(local)
             if nv1 is not None:
@@ -687,6 +742,12 @@ def run_ours(args):
         th.cuda.empty_cache()
         scale_10x = run_10x(dev, rank, world, barrier, max_over_ranks, no_eval=args.no_eval)
 
+    # ---- N = 1: the Zipf-skewed graph of the same size (long rows split across CTAs) -----------------
+    skew = None
+    if not distributed and not args.no_skew and not args.skew:
+        graphed = None
+        skew = run_skew(args.config, dev, ms_step)
+
     # ---- CPU baseline (rank 0, N = 1) ---------------------------------------------------------
     cpu = None
     if rank == 0 and not distributed and not args.no_cpu_baseline:
@@ -701,7 +762,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cfg, world, work_mb, exchange_name),
+            "config": dict(workload_config(cfg, world, work_mb, exchange_name),
+                           **({"skew": "zipf(1.5) tails / items (diagnostic run, not the headline config)"}
+                              if args.skew else {})),
             "e2e": e2e, "gpu_launches": launches, "eager_ms_per_step": ms_eager,
             "value_path": value_path,
             "clocks": clocks.summary(),
@@ -711,7 +774,7 @@ def run_ours(args):
                            "may use 2x the fp32 reference's own error; top-K is bit-exact outside fp32-unresolvable ties",
             # the keys a reader wants first are LAST: the driver keeps the tail of this line
             "ranks": by_rank,
-            "eval": eval_info, "roofline_eval": roofline_eval, "dist_parity": dist_parity, "scale_10x": scale_10x, "nvlink": nvlink,
+            "eval": eval_info, "roofline_eval": roofline_eval, "dist_parity": dist_parity, "scale_10x": scale_10x, "nvlink": nvlink, "skew": skew,
         }
         emit(line)
     if distributed:

@@ -28,7 +28,7 @@ class KgatGraph(C.Structure):
 
 
 GRAPH_ARRAYS = [name for name, _ in KgatGraph._fields_[3:16]]
-SPLIT_ROW, SPLIT_SEG, SPLIT_SCRATCH_WIDTH = 2048, 1024, 128     # KGAT_SPLIT_* of the header
+SPLIT_ROW, SPLIT_SEG, SPLIT_SCRATCH_WIDTH = 256, 512, 128     # KGAT_SPLIT_* of the header
 
 
 class KgatRuns(C.Structure):
@@ -74,6 +74,7 @@ SIGNATURES = {
                                  C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int64,
                                  C.c_void_p]),
     "kgat_layer_bwd_partials": (C.c_int, []),
+    "kgat_layer_bwd_reduce": (C.c_int, [C.c_int64, C.c_int, C.c_int, c_f32p, c_f32p, C.c_void_p]),
     "kgat_layer_bwd": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_i32p, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p,
                                  c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_float,
                                  c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
@@ -112,6 +113,7 @@ SIGNATURES = {
     "kgat_peer_gather_rows_push": (C.c_int, [c_f32p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                              c_f32p, _PG, C.c_void_p]),
     "kgat_peer_push_slot": (C.c_int, [c_f32p, C.c_int64, c_f32p, _PG, C.c_void_p]),
+    "kgat_peer_push_buffer": (C.c_int, [c_f32p, C.c_int64, c_f32p, _PG, C.c_void_p]),
     "kgat_peer_sum_slots": (C.c_int, [c_f32p, C.c_int64, C.c_int, c_f32p, C.c_void_p]),
     "kgat_umma_error_flag": (C.c_int, []),
     "kgat_selftest_umma": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

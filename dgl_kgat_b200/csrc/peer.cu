@@ -96,6 +96,18 @@ __global__ void push_slot_kernel(const float* __restrict__ src, int64_t n, float
     }
 }
 
+// dst[i] = src[i] in the own arena and in every peer's (n4 float4 elements, grid-stride): the plain all-gather
+// push of a contiguous buffer, and the kernel profiles/push_bw.py times to see what one rank can push
+__global__ void __launch_bounds__(256)
+push_buffer_kernel(const float4* __restrict__ src, int64_t n4, float4* __restrict__ dst, PeerOut po, int local) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        if (local) dst[i] = v;
+        peer_store(po, static_cast<size_t>(i) * 4, v);
+    }
+}
+
 __global__ void sum_slots_kernel(const float* __restrict__ slots, int64_t n, int world, float* __restrict__ out) {
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (i >= n) return;
@@ -196,6 +208,20 @@ extern "C" int kgat_peer_push_slot(const float* src, int64_t n, float* slots, co
     if (n == 0) return KGAT_OK;
     const unsigned grid = static_cast<unsigned>(n + 255) / 256 < 64u ? static_cast<unsigned>(n + 255) / 256 : 64u;
     push_slot_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, n, own_slot, po);
+    KGAT_LAUNCH_CHECK();
+    return KGAT_OK;
+}
+
+extern "C" int kgat_peer_push_buffer(const float* src, int64_t n, float* dst, const kgat_peer_group_t* pg,
+                                     kgat_stream_t stream) {
+    KGAT_REQUIRE(src && dst && n >= 0 && n % 4 == 0 && aligned16(src) && aligned16(dst) && peer_group_ok(pg));
+    PeerOut po;
+    KGAT_REQUIRE(peer_aliases(pg, dst, sizeof(float) * static_cast<size_t>(n), &po));
+    if (n == 0) return KGAT_OK;
+    const int64_t n4 = n / 4, want = (n4 + 255) / 256, cap = 8ll * num_sms();
+    // with the multicast mapping the switch writes the own copy too: no separate local store
+    push_buffer_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(src), n4, reinterpret_cast<float4*>(dst), po, po.mc ? 0 : 1);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }

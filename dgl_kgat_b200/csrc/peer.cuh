@@ -8,6 +8,8 @@
 // overlaps its math row by row.  What is left of the collective is a barrier (peer.cu).
 #pragma once
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace kgat {
@@ -80,6 +82,10 @@ inline bool peer_aliases(const kgat_peer_group_t* pg, const void* local, size_t 
         out->base[out->n++] = reinterpret_cast<float*>(static_cast<char*>(pg->arena[k]) + off);
     }
     if (pg->multicast && pg->world > 1) out->mc = reinterpret_cast<float*>(static_cast<char*>(pg->multicast) + off);
+    // MEASUREMENT ONLY (results are wrong): KGAT_DEBUG_NO_REMOTE=1 drops every remote store, so the *_push kernels
+    // can be timed without their NVLink traffic (profiles/README.md, what the pushes cost)
+    static const bool no_remote = [] { const char* e = std::getenv("KGAT_DEBUG_NO_REMOTE"); return e && e[0] == '1'; }();
+    if (no_remote) { out->n = 0; out->mc = nullptr; }
     return true;
 }
 

@@ -115,22 +115,50 @@ split_gather_kernel(SplitSide sp, const int32_t* __restrict__ idx, const float* 
     if (warp == 0 && lane < W / 4) *reinterpret_cast<float4*>(partial + static_cast<size_t>(s) * W + lane * 4) = t;
 }
 
+// One CTA per split row: the hottest row of a Zipf graph has > 1000 segments, and one warp adding them one after
+// the other was a 200 us chain of dependent loads.  Warp w takes the w-th contiguous slice of the row's partials
+// (32 / (W / 4) partial rows per warp instruction, 4x unrolled), the lane groups meet by shuffle, the warps in
+// shared memory in warp order - the order of the additions depends on the segment count only.
 template <int W>
 __global__ void __launch_bounds__(THREADS)
-split_combine_kernel(SplitSide sp, int n_long, const float* __restrict__ partial, int row_begin, int row_end,
+split_combine_kernel(SplitSide sp, const float* __restrict__ partial, int row_begin, int row_end,
                      float* __restrict__ out) {
-    const int li = blockIdx.x * WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (li >= n_long || lane >= W / 4) return;
+    constexpr int LPE = W / 4, EPW = 32 / LPE;
+    __shared__ float4 sPart[WARPS * 32];
+    const int li = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = __ldg(sp.long_row + li);
-    if (row < row_begin || row >= row_end) return;
+    if (row < row_begin || row >= row_end) return;            // CTA-uniform
     const int s0 = __ldg(sp.long_seg0 + li), n = __ldg(sp.long_nseg + li);
+    const int per = (((n + WARPS - 1) / WARPS) + EPW - 1) / EPW * EPW;
+    const int b = min(n, warp * per), e = min(n, b + per);
+    const int sub = lane / LPE;
+    const float* base = partial + static_cast<size_t>(s0) * W + (lane % LPE) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int i = 0; i < n; ++i) {
-        const float4 v = ldg4(partial + static_cast<size_t>(s0 + i) * W + lane * 4);
+    int i = b + sub;
+    for (; i + 3 * EPW < e; i += 4 * EPW) {
+        const float4 v0 = ldg4(base + static_cast<size_t>(i) * W), v1 = ldg4(base + static_cast<size_t>(i + EPW) * W);
+        const float4 v2 = ldg4(base + static_cast<size_t>(i + 2 * EPW) * W),
+                     v3 = ldg4(base + static_cast<size_t>(i + 3 * EPW) * W);
+        acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+        acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+        acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+        acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+    }
+    for (; i < e; i += EPW) {
+        const float4 v = ldg4(base + static_cast<size_t>(i) * W);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * W + lane * 4) = acc;
+    sPart[warp * 32 + lane] = across_groups_sum<LPE>(acc);
+    __syncthreads();
+    if (warp == 0 && lane < LPE) {
+        float4 t = sPart[lane];
+#pragma unroll
+        for (int w = 1; w < WARPS; ++w) {
+            const float4 q = sPart[w * 32 + lane];
+            t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+        }
+        *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * W + lane * 4) = t;
+    }
 }
 
 // side 0: CSR (idx = csr_src), side 1: CSC (idx = csc_dst).  Returns true when the rows above SPLIT_ROW edges of
@@ -145,8 +173,7 @@ int split_prepass(const kgat_graph_t* g, int side, const float* wgt, const float
     const int32_t* idx = side == 0 ? g->csr_src : g->csc_dst;
     split_gather_kernel<W><<<sp.n_seg, THREADS, 0, st>>>(sp, idx, wgt, feat, row_begin, row_end, g->split_scratch);
     KGAT_LAUNCH_CHECK();
-    split_combine_kernel<W><<<(sp.n_long + WARPS - 1) / WARPS, THREADS, 0, st>>>(sp, sp.n_long, g->split_scratch,
-                                                                                 row_begin, row_end, out);
+    split_combine_kernel<W><<<sp.n_long, THREADS, 0, st>>>(sp, g->split_scratch, row_begin, row_end, out);
     KGAT_LAUNCH_CHECK();
     *ran = true;
     return KGAT_OK;
@@ -888,6 +915,14 @@ inline int bwd_epilogue(int d_in, int d_out, bool push) {
     return (want == 1 && d_in >= 32 && d_out >= 16) ? 1 : 0;
 }
 
+// CTAs (= dW2 partials) of the persistent layer_bwd grid over `rows` rows
+template <int DIN, int DOUT>
+int bwd_grid(int rows) {
+    const int n_tiles = (rows + TM - 1) / TM;
+    const int cap = bwd_ctas_per_sm<DIN, DOUT>() * num_sms();
+    return n_tiles < cap ? n_tiles : cap;
+}
+
 template <int DIN, int DOUT, bool PUSH, int EPI>
 int launch_bwd_t(const BwdArgs& a) {
     constexpr size_t smem = BwdCfg<DIN, DOUT, EPI>::bytes;
@@ -899,14 +934,14 @@ int launch_bwd_t(const BwdArgs& a) {
     }
     const int rows = a.row_end - a.row_begin;
     const int n_tiles = (rows + TM - 1) / TM;
-    const int cap = bwd_ctas_per_sm<DIN, DOUT>() * num_sms();
-    const int grid = n_tiles < cap ? n_tiles : cap;
+    const int grid = bwd_grid<DIN, DOUT>(rows);
     layer_bwd_kernel<DIN, DOUT, PUSH, EPI><<<grid, THREADS, smem, a.st>>>(
         a.g->csc_ptr, a.g->csc_dst, a.w_csc, a.row_begin, a.row_end, n_tiles, a.d_concat, a.dc_slot, a.cstride,
         a.out_off,
         a.nxt_dx_direct, a.nxt_dh_nb, a.h_in, a.h_nb, a.act, a.h_out, a.drop_mask, a.W2, a.slope, a.dx_direct,
         a.dh_nb, a.partials, a.po);
     KGAT_LAUNCH_CHECK();
+    if (!a.dW2) return KGAT_OK;          // the caller reduces the partials itself (kgat_layer_bwd_reduce)
     const int n_elem = DIN * DOUT;
     reduce_partials_kernel<<<(n_elem + 31) / 32, 256, 0, a.st>>>(a.partials, grid, n_elem, a.dW2);
     KGAT_LAUNCH_CHECK();
@@ -978,7 +1013,7 @@ extern "C" int kgat_layer_bwd_push(const kgat_graph_t* g, int64_t row_begin, int
                                    const float* h_out, const float* drop_mask, const float* W2, int d_in, int d_out,
                                    float slope, float* dx_direct, float* dh_nb, float* dW2, float* dW2_partials,
                                    const kgat_peer_group_t* pg, kgat_stream_t stream) {
-    KGAT_REQUIRE(g && h_in && h_nb && h_out && W2 && dx_direct && dh_nb && dW2 && dW2_partials);
+    KGAT_REQUIRE(g && h_in && h_nb && h_out && W2 && dx_direct && dh_nb && dW2_partials);
     KGAT_REQUIRE(row_begin >= 0 && row_end <= g->n_nodes && row_begin <= row_end);
     KGAT_REQUIRE(!nxt_dh_nb || g->n_edges == 0 || w_csc);
     KGAT_REQUIRE(!drop_mask || act);
@@ -989,7 +1024,7 @@ extern "C" int kgat_layer_bwd_push(const kgat_graph_t* g, int64_t row_begin, int
     if (pg) KGAT_REQUIRE(d_in > 0 && peer_aliases(pg, dh_nb, sizeof(float) * g->n_nodes * d_in, &po));
     cudaStream_t st = as_stream(stream);
     if (row_begin == row_end) {
-        KGAT_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * d_in * d_out, st));
+        if (dW2) KGAT_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * d_in * d_out, st));
         return KGAT_OK;
     }
     KGAT_REQUIRE(!dc_row_slot || d_concat);
@@ -1011,6 +1046,25 @@ extern "C" int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t 
     return kgat_layer_bwd_push(g, row_begin, row_end, d_concat, dc_row_slot, concat_stride, out_off, nxt_dx_direct,
                                nxt_dh_nb, w_csc, h_in, h_nb, act, h_out, drop_mask, W2, d_in, d_out, slope, dx_direct,
                                dh_nb, dW2, dW2_partials, nullptr, stream);
+}
+
+extern "C" int kgat_layer_bwd_reduce(int64_t rows, int d_in, int d_out, const float* dW2_partials, float* dW2,
+                                     kgat_stream_t stream) {
+    KGAT_REQUIRE(rows >= 0 && rows < (int64_t(1) << 31) && dW2_partials && dW2 && aligned16(dW2_partials));
+    cudaStream_t st = as_stream(stream);
+    if (rows == 0) {
+        KGAT_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * d_in * d_out, st));
+        return KGAT_OK;
+    }
+    int grid = -1;
+#define X(DI, DO) if (d_in == DI && d_out == DO) grid = bwd_grid<DI, DO>(static_cast<int>(rows));
+    KGAT_DIM_PAIRS(X)
+#undef X
+    if (grid < 0) return KGAT_ERR_UNSUPPORTED_DIM;
+    const int n_elem = d_in * d_out;
+    reduce_partials_kernel<<<(n_elem + 31) / 32, 256, 0, st>>>(dW2_partials, grid, n_elem, dW2);
+    KGAT_LAUNCH_CHECK();
+    return KGAT_OK;
 }
 
 extern "C" int kgat_input_bwd_push(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,

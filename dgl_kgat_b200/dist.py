@@ -70,7 +70,11 @@ class PeerArena:
         self._pg.world, self._pg.rank, self._pg.arena_bytes = self.world, self.rank, self.nbytes
         self._pg.multicast = None
         self._mapped, self._symm = [], None
-        want_mc = os.environ.get("KGAT_PEER_MULTICAST", "1") != "0" and self.world > 1
+        # NVSwitch multicast pays from three ranks on (measured, profiles/README.md: 0.71 vs 0.80 ms per step at 4
+        # ranks); at two ranks a unicast store already leaves the GPU once, and the multicast would send the own
+        # copy through the switch and back on top (0.98 vs 0.91 ms).  KGAT_PEER_MULTICAST=1 / 0 forces it.
+        mc_env = os.environ.get("KGAT_PEER_MULTICAST", "auto")
+        want_mc = self.world > 1 and (mc_env == "1" or (mc_env not in ("0", "1") and self.world > 2))
         with th.cuda.device(self.device):
             if want_mc and self._try_symmetric(group):
                 pass

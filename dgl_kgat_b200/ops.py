@@ -15,6 +15,15 @@ from .graph import DeviceGraph
 LEAKY_SLOPE = 0.01      # F.leaky_relu default used at reference models.py:66
 # KGAT_BWD_SPLIT=0 keeps the transposed aggregation inside layer_bwd (A/B measurements)
 SPLIT_BWD_GATHER = os.environ.get("KGAT_BWD_SPLIT", "1") != "0"
+REDUCE_OVERLAP = os.environ.get("KGAT_BWD_REDUCE_OVERLAP", "1") != "0"      # dW2 reductions on a second stream
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    s = _SIDE_STREAMS.get(dev)
+    if s is None:
+        s = _SIDE_STREAMS[dev] = th.cuda.Stream(device=dev)
+    return s
 
 
 def _f32c(t: th.Tensor, device) -> th.Tensor:
@@ -254,6 +263,8 @@ class Propagate(th.autograd.Function):
             st = _lib.stream_ptr()
             # peer exchange: every layer's dW2 is a view of one flat buffer that travels as one slot
             dw_flat = th.empty(w_off[-1], dtype=th.float32, device=dev) if peer is not None else None
+            side = _side_stream(dev) if (not plan.distributed and REDUCE_OVERLAP) else None
+            keep = []            # partial buffers stay alive until the side stream has been joined
             for l in reversed(range(L)):
                 d_in, d_out = dims[l], dims[l + 1]
                 h_in, h_nb, act, h_out = ctx.saved[l]
@@ -277,16 +288,27 @@ class Propagate(th.autograd.Function):
                     up_dx, up_dh = gsum, None
                 else:
                     up_dx, up_dh = nxt_dx, nxt_dh
-                with _lib.record("layer_bwd_%dx%d" % (d_in, d_out), 2):
+                with _lib.record("layer_bwd_%dx%d" % (d_in, d_out), 1 if side is not None else 2):
                     args = (dg.ref, plan.r0, plan.r1, _lib.ptr(d_concat), _lib.ptr(dc_slot), cstride, offs[l + 1],
                             _lib.ptr(up_dx), _lib.ptr(up_dh), plan.w_csc.data_ptr(),
                             h_in.data_ptr(), h_nb.data_ptr(), _lib.ptr(act), h_out.data_ptr(), _lib.ptr(ctx.masks[l]),
                             ctx.weights[l].data_ptr(), d_in, d_out, LEAKY_SLOPE,
-                            dx.data_ptr(), dh.data_ptr(), dW.data_ptr(), part.data_ptr())
+                            dx.data_ptr(), dh.data_ptr(), None if side is not None else dW.data_ptr(), part.data_ptr())
                     if peer is not None:
                         _lib.check(lib.kgat_layer_bwd_push(*args, peer.ref, st), "kgat_layer_bwd_push")
                     else:
                         _lib.check(lib.kgat_layer_bwd(*args, st), "kgat_layer_bwd")
+                if side is not None:
+                    # nothing in the rest of the backward pass reads dW2: its fixed-order reduction over the per-CTA
+                    # partials (a 16..128-CTA kernel, ~10 us of latency) runs on a second stream next to the
+                    # following gather kernels and is joined before the gradients are handed back
+                    side.wait_stream(th.cuda.current_stream())
+                    with th.cuda.stream(side):
+                        with _lib.record("dW2_reduce", 1):
+                            _lib.check(lib.kgat_layer_bwd_reduce(plan.r1 - plan.r0, d_in, d_out, part.data_ptr(),
+                                                                 dW.data_ptr(), _lib.stream_ptr()),
+                                       "kgat_layer_bwd_reduce")
+                    keep.append(part)
                 # dh_nb rows of every rank feed the transposed gather of the next kernel
                 if peer is not None:
                     peer.barrier()
@@ -324,6 +346,8 @@ class Propagate(th.autograd.Function):
                     d_entity = d_entity.clone()         # the arena buffer is overwritten by the next backward
             elif plan.distributed:
                 plan.reduce(d_weights)                  # one all-reduce for every layer's dW2
+            if side is not None:
+                th.cuda.current_stream().wait_stream(side)
         return (None, None, None, None, d_entity, *d_weights)
 
 

@@ -88,14 +88,17 @@ typedef struct kgat_graph {
      * item onto the item's row); such a row must not be walked by one warp or one CTA.  Rows with more
      * than KGAT_SPLIT_ROW in-edges (CSR side) / out-edges (CSC side) are cut into segments of at most
      * KGAT_SPLIT_SEG edges; the aggregation and softmax entry points handle them in a pre-pass with one
-     * CTA per SEGMENT and add the partial results in segment order (deterministic). */
+     * CTA per SEGMENT and add the partial results in segment order (deterministic).  The threshold is low
+     * on purpose: hot rows come in clusters (popular items / entities have neighbouring ids), and a tile of
+     * 32 consecutive rows with a few hundred edges each kept one CTA busy long after the rest of the grid
+     * had finished (measured on the Zipf graph of bench.py: 0.46 ms instead of 0.15 for the first layer). */
     int32_t *split;          /* [kgat_graph_split_ints(E)] segment tables of both sides */
     float   *split_scratch;  /* [max(n_csr_seg, n_csc_seg) * KGAT_SPLIT_SCRATCH_WIDTH] partial sums */
     int32_t  n_csr_seg, n_csr_long, n_csc_seg, n_csc_long;   /* host copies of the table sizes */
 } kgat_graph_t;
 
-#define KGAT_SPLIT_ROW 2048
-#define KGAT_SPLIT_SEG 1024
+#define KGAT_SPLIT_ROW 256
+#define KGAT_SPLIT_SEG 512
 #define KGAT_SPLIT_SCRATCH_WIDTH 128
 
 /* (1) graph construction -- replaces DGLGraph()/add_nodes/add_edges/readonly
@@ -205,8 +208,13 @@ KGAT_API int kgat_layer_fwd(const kgat_graph_t* g, int64_t row_begin, int64_t ro
  * then pushed through dropout / LeakyReLU / Linear / (.):
  *   dW2       = sum_v dpre[v]^T (h_in[v] (.) h_nb[v])      (summed over the given rows)
  *   dx_direct = (dpre W2) (.) h_nb        dh_nb = (dpre W2) (.) h_in
- * dW2_partials: scratch of kgat_layer_bwd_partials() * d_out * d_in floats. */
+ * dW2_partials: scratch of kgat_layer_bwd_partials() * d_out * d_in floats.
+ * dW2 may be NULL: the call then leaves one partial per CTA in dW2_partials and kgat_layer_bwd_reduce (same
+ * row count and widths) adds them in fixed order later - e.g. on a second stream, next to the following
+ * kernels, since nothing in the rest of the backward pass reads dW2. */
 KGAT_API int kgat_layer_bwd_partials(void);
+KGAT_API int kgat_layer_bwd_reduce(int64_t rows, int d_in, int d_out, const float* dW2_partials, float* dW2,
+                          kgat_stream_t stream);
 KGAT_API int kgat_layer_bwd(const kgat_graph_t* g, int64_t row_begin, int64_t row_end,
                    const float* d_concat, const int32_t* dc_row_slot, int64_t concat_stride, int64_t out_off,
                    const float* nxt_dx_direct, const float* nxt_dh_nb, const float* w_csc,
@@ -405,6 +413,11 @@ KGAT_API int kgat_peer_gather_rows_push(const float* emb, int64_t emb_stride, in
  * adds the world slots in rank order (identical bits on every rank) into out[0..n). */
 KGAT_API int kgat_peer_push_slot(const float* src, int64_t n, float* slots, const kgat_peer_group_t* pg,
                         kgat_stream_t stream);
+/* dst[0..n) = src[0..n) in the own arena and in every peer's (dst lies in the own arena, n % 4 == 0, 16-byte
+ * aligned): the all-gather push of one contiguous buffer.  Through the multicast mapping the NVSwitch writes
+ * every copy, the own one included. */
+KGAT_API int kgat_peer_push_buffer(const float* src, int64_t n, float* dst, const kgat_peer_group_t* pg,
+                          kgat_stream_t stream);
 KGAT_API int kgat_peer_sum_slots(const float* slots, int64_t n, int world, float* out, kgat_stream_t stream);
 
 /* Hardware self-test of the tcgen05 path (diagnostics; not on the hot path):

@@ -17,6 +17,6 @@ run() {  # name, env...
       > $OUT/bench_${TAG}_n${N}_$name.json 2> $OUT/bench_${TAG}_n${N}_$name.err
   echo "$name rc=$?"; tail -c 600 $OUT/bench_${TAG}_n${N}_$name.json
 }
-run mc KGAT_X=1
+run mc KGAT_PEER_MULTICAST=1
 run unicast KGAT_PEER_MULTICAST=0
 ls -la $OUT | tail -12

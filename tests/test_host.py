@@ -85,11 +85,12 @@ def test_graph_struct_layout_matches_header():
 
 def test_split_table_oracle_on_a_power_law_pointer():
     """The segment tables of kgat_graph_split_build restated in numpy (oracle/graph_ref.split_table): rows above
-    SPLIT_ROW edges ascending, ceil(deg / SPLIT_SEG) segments of equal 32-aligned length, in edge order."""
+    split_row edges ascending, ceil(deg / split_seg) segments of equal 32-aligned length, in edge order
+    (here with thresholds 2048 / 1024; the GPU tests compare the device tables at the header's thresholds)."""
     from oracle import graph_ref
     deg = np.array([0, 5, 2048, 2049, 7, 100000, 1, 4096, 3000], dtype=np.int64)
     ptr = np.concatenate([[0], np.cumsum(deg)])
-    t = graph_ref.split_table(ptr, _lib.SPLIT_ROW, _lib.SPLIT_SEG)
+    t = graph_ref.split_table(ptr, 2048, 1024)
     assert t["long_row"].tolist() == [3, 5, 7, 8]
     assert t["long_nseg"].tolist() == [3, 98, 4, 3]
     assert t["long_seg0"].tolist() == [0, 3, 101, 105]
@@ -98,7 +99,7 @@ def test_split_table_oracle_on_a_power_law_pointer():
         segs = [(t["seg_beg"][s], t["seg_end"][s]) for s in range(s0, s0 + n)]
         assert segs[0][0] == ptr[row] and segs[-1][1] == ptr[row + 1]
         assert all(a[1] == b[0] for a, b in zip(segs, segs[1:]))                # contiguous, in edge order
-        assert all(0 < e - b <= _lib.SPLIT_SEG for b, e in segs)
+        assert all(0 < e - b <= 1024 for b, e in segs)
         assert all((b - ptr[row]) % 32 == 0 for b, _ in segs)
         assert (t["seg_row"][s0:s0 + n] == row).all() and (t["seg_long"][s0:s0 + n] == li).all()
 
