@@ -33,9 +33,27 @@ from . import _lib, ops
 from .graph import CKGraph
 
 
-def _L2_loss_mean(x):
-    # mean(sum(x ** 2) / 2), models.py:9-11
-    return th.mean(th.sum(th.pow(x, 2), dim=1, keepdim=False) / 2.)
+def _half_sq_norm_mean(*rows):
+    """sum over the given (B, d) tensors of mean_b(|row_b|^2 / 2): the L2 term of both losses (models.py:9-11)."""
+    return sum(0.5 * v.square().sum(dim=1).mean() for v in rows)
+
+
+def _bpr_loss_host(embedding, src_ids, pos_ids, neg_ids, reg_lambda):
+    """Host statement of models.py:170-178 for CPU tensors (API / oracle tests); the GPU path is ops.BprLoss."""
+    s, p, n = (embedding.index_select(0, i.reshape(-1)) for i in (src_ids, pos_ids, neg_ids))
+    margin = (s * p).sum(dim=1) - (s * n).sum(dim=1)
+    return -F.logsigmoid(margin).mean() + reg_lambda * _half_sq_norm_mean(s, p, n)
+
+
+def _transr_loss_host(entity, rel_emb, W_R, h, r, pos_t, neg_t, reg_lambda):
+    """Host statement of models.py:114-133 for CPU tensors (API / oracle tests); the GPU path is ops.TransRLoss."""
+    W = W_R.index_select(0, r)                                               # (B, d, rd), models.py:46-47
+    project = lambda ids: F.normalize(th.bmm(entity.index_select(0, ids).unsqueeze(1), W).squeeze(1), p=2, dim=1)
+    hv, pv, nv = project(h), project(pos_t), project(neg_t)
+    rv = F.normalize(rel_emb.index_select(0, r), p=2, dim=1)
+    d_pos = (hv + rv - pv).square().sum(dim=1)
+    d_neg = (hv + rv - nv).square().sum(dim=1)
+    return -F.logsigmoid(d_neg - d_pos).mean() + reg_lambda * _half_sq_norm_mean(hv, rv, pv, nv)
 
 
 def bmm_maybe_select(A, B, index):
@@ -115,29 +133,18 @@ class Model(nn.Module):
 
     # ------------------------------------------------------------------ KG-embedding mode
     def transR(self, h, r, pos_t, neg_t):
-        """TransR pairwise ranking loss on L2-normalised projections (models.py:114-133).  On the GPU,
-        for 64-wide embeddings, loss and gradients come from one relation-grouped library call
-        (``ops.TransRLoss``); the plain formula below is the same arithmetic for every other shape."""
-        if h.dim() == 1 and ops.transr_supported(self.entity_embed.weight, self.relation_embed.weight, self.W_R,
-                                                 h.numel()):
-            return ops.transr_loss(self.entity_embed.weight, self.relation_embed.weight, self.W_R, h, r, pos_t,
-                                   neg_t, self._reg_lambda_kg)
-        h_embed = self.entity_embed(h)
-        r_embed = self.relation_embed(r)
-        pos_t_embed = self.entity_embed(pos_t)
-        neg_t_embed = self.entity_embed(neg_t)
-
-        h_vec = F.normalize(bmm_maybe_select(h_embed, self.W_R, r), p=2, dim=1)
-        r_vec = F.normalize(r_embed, p=2, dim=1)
-        pos_t_vec = F.normalize(bmm_maybe_select(pos_t_embed, self.W_R, r), p=2, dim=1)
-        neg_t_vec = F.normalize(bmm_maybe_select(neg_t_embed, self.W_R, r), p=2, dim=1)
-
-        pos_score = th.sum(th.pow(h_vec + r_vec - pos_t_vec, 2), dim=1, keepdim=True)
-        neg_score = th.sum(th.pow(h_vec + r_vec - neg_t_vec, 2), dim=1, keepdim=True)
-        l = th.mean((-1.0) * F.logsigmoid(neg_score - pos_score))
-        reg_loss = _L2_loss_mean(h_vec) + _L2_loss_mean(r_vec) + \
-                   _L2_loss_mean(pos_t_vec) + _L2_loss_mean(neg_t_vec)
-        return l + self._reg_lambda_kg * reg_loss
+        """TransR pairwise ranking loss on L2-normalised projections (models.py:114-133).  On the GPU loss and
+        gradients come from the relation-grouped library kernels (``ops.TransRLoss``, 64-wide embeddings; any
+        other width is refused - no silent slow path).  CPU tensors get the host statement of the same formula
+        (``_transr_loss_host``): the API tests run without a GPU."""
+        ent, rel, W = self.entity_embed.weight, self.relation_embed.weight, self.W_R
+        if ent.is_cuda:
+            if h.dim() != 1 or not ops.transr_supported(ent, rel, W, h.numel()):
+                raise _lib.KgatError("transR on the GPU needs fp32 parameters with entity_embed_dim = relation_dim = 64, "
+                                     "at most 1024 relations and 1-D index tensors (KGAT_ERR_UNSUPPORTED_DIM); got "
+                                     "entity %s, relation %s" % (tuple(ent.shape), tuple(rel.shape)))
+            return ops.transr_loss(ent, rel, W, h, r, pos_t, neg_t, self._reg_lambda_kg)
+        return _transr_loss_host(ent, rel, W, h, r, pos_t, neg_t, self._reg_lambda_kg)
 
     # ------------------------------------------------------------------ attention-update mode
     def compute_attention(self, g):
@@ -175,17 +182,14 @@ class Model(nn.Module):
         return ops.propagate(ops.PropagatePlan(dg, w_csr, w_csc), list(drop_masks), False, h, *weights)
 
     def get_loss(self, embedding, src_ids, pos_dst_ids, neg_dst_ids):
-        """BPR loss + L2 regulariser on the gathered rows (models.py:170-178).  On the GPU this is
-        one fused kernel whose backward hands ``gnn`` a compact row gradient; the plain formula below
-        is the same arithmetic and serves tensors the kernel does not cover (CPU, widths > 256)."""
-        if (embedding.is_cuda and embedding.dtype == th.float32 and embedding.dim() == 2
-                and embedding.shape[1] % 4 == 0 and embedding.shape[1] <= 256 and src_ids.dim() == 1):
+        """BPR loss + L2 regulariser on the gathered rows (models.py:170-178).  On the GPU this is one fused kernel
+        whose backward hands ``gnn`` a compact row gradient (widths that are multiples of 4 up to 256; anything
+        else is refused).  CPU tensors get the host statement of the formula (``_bpr_loss_host``)."""
+        if embedding.is_cuda:
+            if not (embedding.dtype == th.float32 and embedding.dim() == 2 and embedding.shape[1] % 4 == 0
+                    and embedding.shape[1] <= 256 and src_ids.dim() == 1):
+                raise _lib.KgatError("get_loss on the GPU needs an fp32 (N, d) embedding with d % 4 == 0, d <= 256 "
+                                     "and 1-D id tensors (KGAT_ERR_UNSUPPORTED_DIM); got %s %s"
+                                     % (tuple(embedding.shape), embedding.dtype))
             return ops.bpr_loss(embedding, src_ids, pos_dst_ids, neg_dst_ids, self._reg_lambda_gnn)
-        src_vec = embedding[src_ids]
-        pos_dst_vec = embedding[pos_dst_ids]
-        neg_dst_vec = embedding[neg_dst_ids]
-        pos_score = th.bmm(src_vec.unsqueeze(1), pos_dst_vec.unsqueeze(2)).squeeze()
-        neg_score = th.bmm(src_vec.unsqueeze(1), neg_dst_vec.unsqueeze(2)).squeeze()
-        cf_loss = th.mean(F.logsigmoid(pos_score - neg_score)) * (-1.0)
-        reg_loss = _L2_loss_mean(src_vec) + _L2_loss_mean(pos_dst_vec) + _L2_loss_mean(neg_dst_vec)
-        return cf_loss + self._reg_lambda_gnn * reg_loss
+        return _bpr_loss_host(embedding, src_ids, pos_dst_ids, neg_dst_ids, self._reg_lambda_gnn)

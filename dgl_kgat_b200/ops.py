@@ -495,9 +495,9 @@ def score_topk(emb: th.Tensor, user_ids: th.Tensor, item_ids: th.Tensor, mask_pt
 
 # --------------------------------------------------------------------------- TransR step
 def transr_supported(entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Tensor, batch: int) -> bool:
-    """Shapes ``kgat_transr_fwd_bwd`` covers (anything else goes through the plain torch formula)."""
+    """Shapes the TransR kernels cover (Model.transR refuses anything else on the GPU)."""
     return (entity.is_cuda and entity.dtype == th.float32 and entity.shape[1] == 64 and rel_emb.shape[1] == 64
-            and W_R.shape[0] <= 1024 and 0 < 3 * batch <= 16384)
+            and W_R.shape[0] <= 1024 and batch > 0)
 
 
 class TransRLoss(th.autograd.Function):
@@ -544,5 +544,19 @@ class TransRLoss(th.autograd.Function):
         return d_ent, d_rel, d_W, None, None, None, None, None
 
 
+TRANSR_MAX_BATCH = 16384 // 3          # (node, row) keys one plan kernel sorts
+
+
 def transr_loss(entity, rel_emb, W_R, h, r, pos_t, neg_t, reg_lambda):
-    return TransRLoss.apply(entity, rel_emb, W_R, h, r, pos_t, neg_t, reg_lambda)
+    """Every term of the loss is a mean over the batch, so a batch above the plan kernel's capacity is the
+    size-weighted sum of its chunks (``--batch_size_kg`` beyond 5461)."""
+    B = h.numel()
+    if B <= TRANSR_MAX_BATCH:
+        return TransRLoss.apply(entity, rel_emb, W_R, h, r, pos_t, neg_t, reg_lambda)
+    total = None
+    for b0 in range(0, B, TRANSR_MAX_BATCH):
+        b1 = min(B, b0 + TRANSR_MAX_BATCH)
+        part = TransRLoss.apply(entity, rel_emb, W_R, h[b0:b1], r[b0:b1], pos_t[b0:b1], neg_t[b0:b1], reg_lambda)
+        part = part * ((b1 - b0) / B)
+        total = part if total is None else total + part
+    return total

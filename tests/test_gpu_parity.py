@@ -827,21 +827,44 @@ def test_transr_fused_is_deterministic_and_scales_with_upstream_gradient(dev):
         assert th.allclose(c, 3.0 * a, rtol=1e-6, atol=0)
 
 
-def test_transr_unsupported_shapes_use_the_plain_formula(dev):
+def test_transr_and_get_loss_refuse_unsupported_shapes_on_the_gpu(dev):
+    """No silent slow path: widths the kernels do not cover raise (the library returns KGAT_ERR_UNSUPPORTED_DIM)."""
     ck = synth_ckg("tiny")
     N, R = ck.cfg.n_nodes, ck.cfg.n_relations
     m = make_model(N, R, dev, d=32, hidden=32, layers=1, rd=32)
     ids = [th.zeros(8, dtype=th.long, device=dev)] * 4
     assert not ops.transr_supported(m.entity_embed.weight, m.relation_embed.weight, m.W_R, 8)
-    m.transR(*ids).backward()
-    assert m.W_R.grad is not None
-    # and the library itself refuses rather than guessing
+    with pytest.raises(_lib.KgatError):
+        m.transR(*ids)
+    with pytest.raises(_lib.KgatError):
+        m.get_loss(th.zeros(16, 6, device=dev), *ids[:3])            # width not a multiple of 4
     lib = _lib.load()
     z = th.zeros(64, device=dev)
     rc = lib.kgat_transr_fwd(z.data_ptr(), 1, z.data_ptr(), z.data_ptr(), 1, 32, 32, ids[0].data_ptr(),
                              ids[0].data_ptr(), ids[0].data_ptr(), ids[0].data_ptr(), 8, 0.0, z.data_ptr(),
                              z.data_ptr(), 1 << 20, _lib.stream_ptr())
     assert rc == -2
+
+
+def test_transr_batch_above_the_plan_capacity_is_chunked(dev):
+    """--batch_size_kg above 5461 samples: size-weighted sum of chunk losses == the loss of the whole batch."""
+    ck = synth_ckg("tiny")
+    N, R = ck.cfg.n_nodes, ck.cfg.n_relations
+    m = make_model(N, R, dev)
+    rng = np.random.default_rng(3)
+    B = ops.TRANSR_MAX_BATCH + 1500
+    h, pt, nt = (th.as_tensor(rng.integers(0, N, B), device=dev) for _ in range(3))
+    r = th.as_tensor(rng.integers(0, R, B), device=dev)
+    loss = m.transR(h, r, pt, nt)
+    loss.backward()
+    ids = [t.cpu() for t in (h, r, pt, nt)]
+    loss64, g64 = _transr_oracle(m, ids, m._reg_lambda_kg, th.float64)
+    _, g32 = _transr_oracle(m, ids, m._reg_lambda_kg, th.float32)
+    assert abs(loss.item() - loss64.item()) < 1e-5 * abs(loss64.item())
+    for k, g in (("entity_embed.weight", m.entity_embed.weight.grad), ("relation_embed.weight", m.relation_embed.weight.grad),
+                 ("W_R", m.W_R.grad)):
+        bound = max(RTOL, 2.0 * max_rel(g32[k].numpy(), g64[k].numpy()))
+        assert max_rel(g.cpu().numpy(), g64[k].numpy()) < bound, k
 
 
 # --------------------------------------------------------------------------- Adam step (SURVEY 8f-3)
