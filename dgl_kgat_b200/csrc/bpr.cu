@@ -92,6 +92,7 @@ __global__ void bpr_link_kernel(const int64_t* __restrict__ src, const int64_t* 
 // contributions of all members in ascending slot order - a fixed order, so the gradient is bit-identical
 // from run to run without a sort and without floating-point atomics - into rows[leader slot];
 // row_slot[node] then points there (the chain head it held is no longer needed: only this warp read it).
+template <int NG>       // float4 column groups per lane: dim <= 128 * NG
 __global__ void __launch_bounds__(BPR_THREADS)
 bpr_bwd_kernel(const float* __restrict__ emb, int64_t stride, int dim, const int64_t* __restrict__ src,
                const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
@@ -132,9 +133,11 @@ bpr_bwd_kernel(const float* __restrict__ emb, int64_t stride, int dim, const int
     }
     const bool in_regs = len <= 32 * PER;
     const float scale = grad_loss[0] / static_cast<float>(B);
-    // dim <= 256: each lane owns up to two float4 column groups
-    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-    const int c0 = lane * 4, c1 = c0 + 128;
+    // each lane owns up to NG float4 column groups: columns lane * 4 + 128 k
+    float4 acc[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c0 = lane * 4;
     int done = -1;                                   // largest slot already accumulated
     for (int t = 0; t < len; ++t) {
         // next member in ascending order: the smallest slot above `done`
@@ -177,12 +180,13 @@ bpr_bwd_kernel(const float* __restrict__ emb, int64_t stride, int dim, const int
             acc.x = fmaf(scale, g.x, acc.x); acc.y = fmaf(scale, g.y, acc.y);
             acc.z = fmaf(scale, g.z, acc.z); acc.w = fmaf(scale, g.w, acc.w);
         };
-        contrib(c0, acc0);
-        contrib(c1, acc1);
+#pragma unroll
+        for (int k = 0; k < NG; ++k) contrib(c0 + 128 * k, acc[k]);
     }
     float* out = rows + static_cast<int64_t>(i) * rows_stride;
-    if (c0 < dim) *reinterpret_cast<float4*>(out + c0) = acc0;
-    if (c1 < dim) *reinterpret_cast<float4*>(out + c1) = acc1;
+#pragma unroll
+    for (int k = 0; k < NG; ++k)
+        if (c0 + 128 * k < dim) *reinterpret_cast<float4*>(out + c0 + 128 * k) = acc[k];
     __syncwarp();                                    // every lane has finished reading the chain head
     if (lane == 0) {
         row_slot[node] = i;
@@ -210,7 +214,7 @@ extern "C" int kgat_bpr_loss_fwd(const float* emb, int64_t emb_stride, int dim, 
                                  kgat_stream_t stream) {
     KGAT_REQUIRE(emb && src && pos && neg && loss && sig && workspace);
     KGAT_REQUIRE(batch > 0 && batch < (int64_t(1) << 28) && aligned16(emb) && emb_stride % 4 == 0);
-    if (dim <= 0 || dim % 4 != 0 || dim > 256) return KGAT_ERR_UNSUPPORTED_DIM;
+    if (dim <= 0 || dim % 4 != 0 || dim > 512) return KGAT_ERR_UNSUPPORTED_DIM;
     if (workspace_bytes < kgat_bpr_workspace_bytes(batch)) return KGAT_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
     const int B = static_cast<int>(batch);
@@ -235,7 +239,7 @@ extern "C" int kgat_bpr_loss_bwd(const float* emb, int64_t emb_stride, int dim, 
     KGAT_REQUIRE(emb && src && pos && neg && sig && grad_loss && rows && rows_node && row_slot && workspace);
     KGAT_REQUIRE(batch > 0 && batch < (int64_t(1) << 28) && n_nodes > 0 && aligned16(emb) && aligned16(rows) &&
                  emb_stride % 4 == 0);
-    if (dim <= 0 || dim % 4 != 0 || dim > 256) return KGAT_ERR_UNSUPPORTED_DIM;
+    if (dim <= 0 || dim % 4 != 0 || dim > 512) return KGAT_ERR_UNSUPPORTED_DIM;
     if (workspace_bytes < kgat_bpr_workspace_bytes(batch)) return KGAT_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
     const int B = static_cast<int>(batch);
@@ -246,9 +250,13 @@ extern "C" int kgat_bpr_loss_bwd(const float* emb, int64_t emb_stride, int dim, 
     KGAT_CUDA(cudaMemsetAsync(row_slot, 0xff, sizeof(int32_t) * n_nodes, st));          // -1 everywhere: empty chains
     bpr_link_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(ns, np_, nn, B, own_begin, own_end, row_slot, next);
     KGAT_LAUNCH_CHECK();
-    bpr_bwd_kernel<<<(3 * B + BPR_WARPS - 1) / BPR_WARPS, BPR_THREADS, 0, st>>>(
-        emb, emb_stride, dim, src, pos, neg, ns, np_, nn, B, reg_lambda, sig, grad_loss, next, rows, dim, row_slot,
-        rows_node);
+    const unsigned grid = (3 * B + BPR_WARPS - 1) / BPR_WARPS;
+    if (dim <= 256)
+        bpr_bwd_kernel<2><<<grid, BPR_THREADS, 0, st>>>(emb, emb_stride, dim, src, pos, neg, ns, np_, nn, B, reg_lambda, sig,
+                                                      grad_loss, next, rows, dim, row_slot, rows_node);
+    else        // 128-wide models: the concat of three layers is 352 floats
+        bpr_bwd_kernel<4><<<grid, BPR_THREADS, 0, st>>>(emb, emb_stride, dim, src, pos, neg, ns, np_, nn, B, reg_lambda, sig,
+                                                      grad_loss, next, rows, dim, row_slot, rows_node);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }

@@ -183,13 +183,13 @@ class Model(nn.Module):
 
     def get_loss(self, embedding, src_ids, pos_dst_ids, neg_dst_ids):
         """BPR loss + L2 regulariser on the gathered rows (models.py:170-178).  On the GPU this is one fused kernel
-        whose backward hands ``gnn`` a compact row gradient (widths that are multiples of 4 up to 256; anything
+        whose backward hands ``gnn`` a compact row gradient (widths that are multiples of 4 up to 512; anything
         else is refused).  CPU tensors get the host statement of the formula (``_bpr_loss_host``)."""
         if embedding.is_cuda:
             if not (embedding.dtype == th.float32 and embedding.dim() == 2 and embedding.shape[1] % 4 == 0
-                    and embedding.shape[1] <= 256 and src_ids.dim() == 1):
-                raise _lib.KgatError("get_loss on the GPU needs an fp32 (N, d) embedding with d % 4 == 0, d <= 256 "
-                                     "and 1-D id tensors (KGAT_ERR_UNSUPPORTED_DIM); got %s %s"
+                    and embedding.shape[1] <= 512 and src_ids.dim() == 1):
+                raise _lib.KgatError("get_loss on the GPU needs an fp32 (N, d) embedding with d a multiple of 4, at most "
+                                     "512, and 1-D id tensors (KGAT_ERR_UNSUPPORTED_DIM); got %s %s"
                                      % (tuple(embedding.shape), embedding.dtype))
             return ops.bpr_loss(embedding, src_ids, pos_dst_ids, neg_dst_ids, self._reg_lambda_gnn)
         return _bpr_loss_host(embedding, src_ids, pos_dst_ids, neg_dst_ids, self._reg_lambda_gnn)
