@@ -33,7 +33,7 @@ SPLIT_ROW, SPLIT_SEG, SPLIT_SCRATCH_WIDTH = 256, 512, 128     # KGAT_SPLIT_* of 
 
 class KgatRuns(C.Structure):
     """Mirror of ``kgat_runs_t``."""
-    _fields_ = [(name, C.c_void_p) for name in ("bk_run", "run_ptr", "run_head", "rel_run_ptr", "n_runs")]
+    _fields_ = [(name, C.c_void_p) for name in ("bk_run", "run_ptr", "run_head", "rel_run_ptr", "n_runs", "rel_mode")]
 
 
 RUN_ARRAYS = [name for name, _ in KgatRuns._fields_]
@@ -68,6 +68,8 @@ SIGNATURES = {
     "kgat_runs_build": (C.c_int, [_GP, _RP, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kgat_attention_logits_runs": (C.c_int, [_GP, _RP, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p,
                                              C.c_void_p]),
+    "kgat_attention_logits_hybrid": (C.c_int, [_GP, _RP, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p,
+                                               C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "kgat_segment_softmax": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "kgat_edge_weights_from_eid": (C.c_int, [_GP, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "kgat_layer_fwd": (C.c_int, [_GP, C.c_int64, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int,

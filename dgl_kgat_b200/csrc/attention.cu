@@ -9,6 +9,8 @@
 //
 // Softmax: exp(x - max) / sum over the in-edges of a destination row like DGL's edge_softmax (reference
 // models.py:153), with the parallelism matched to the row length (see segment_softmax_kernel).
+#include <cstdint>
+
 #include "peer.cuh"
 #include "split.cuh"
 
@@ -369,11 +371,13 @@ using namespace kgat;
 int kgat_launch_att_logits_umma(const kgat_graph_t* g, const float* entity, const float* rel_emb, const float* W_R,
                                 float* logits_csr, int* only_if, cudaStream_t st);
 int kgat_launch_att_logits_umma16(const kgat_graph_t* g, const float* entity, const float* rel_emb,
-                                  const float* W_R, float* logits_csr, int* fallback, cudaStream_t st);
+                                  const float* W_R, float* logits_csr, int* fallback, const int32_t* rel_skip,
+                                  cudaStream_t st);
 int kgat_launch_att_range(const float* W_R, int64_t n, int* word, cudaStream_t st);
 int kgat_launch_att_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
-                                const float* rel_emb, const float* W_R, float* logits_csr, float* v_rows, int* fallback,
-                                cudaStream_t st);
+                                const float* rel_emb, const float* W_R, float* logits_csr, float* v_rows,
+                                int64_t v_base, int64_t v_count, int64_t p_begin, int64_t p_end,
+                                const int32_t* rel_mode, int* fallback, cudaStream_t st);
 int* kgat_att_fallback_word();
 
 // KGAT_ATT_IMPL selects the kernel for d = rd = 64 (A/B runs): "f16" (default) tcgen05 split-fp16,
@@ -404,7 +408,7 @@ extern "C" int kgat_attention_logits(const kgat_graph_t* g, const float* entity,
         if (!word) return KGAT_ERR_CUDA;
         int rc = kgat_launch_att_range(W_R, g->n_rel * static_cast<int64_t>(d) * rd, word, st);
         if (rc != KGAT_OK) return rc;
-        rc = kgat_launch_att_logits_umma16(g, entity, rel_emb, W_R, logits_csr, word, st);
+        rc = kgat_launch_att_logits_umma16(g, entity, rel_emb, W_R, logits_csr, word, nullptr, st);
         if (rc != KGAT_OK) return rc;
         return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, word, st);
     } else if (d == 64 && rd == 64 && g->n_rel <= 1024 && impl == 1) {
@@ -446,8 +450,35 @@ extern "C" int kgat_attention_logits_runs(const kgat_graph_t* g, const kgat_runs
     int rc = kgat_launch_att_range(W_R, g->n_rel * static_cast<int64_t>(d) * rd, word, st);
     if (rc != KGAT_OK) return rc;
     KGAT_REQUIRE(!v_rows || aligned16(v_rows));
-    rc = kgat_launch_att_logits_runs(g, runs, entity, rel_emb, W_R, logits_csr, v_rows, word, st);
+    rc = kgat_launch_att_logits_runs(g, runs, entity, rel_emb, W_R, logits_csr, v_rows, 0, INT64_MAX, 0, g->n_edges,
+                                     nullptr, word, st);
     if (rc != KGAT_OK) return rc;
+    return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, word, st);
+}
+
+extern "C" int kgat_attention_logits_hybrid(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
+                                            const float* rel_emb, const float* W_R, int d, int rd, float* logits_csr,
+                                            float* v_rows, int64_t v_base, int64_t v_count, int64_t p_begin,
+                                            int64_t p_end, kgat_stream_t stream) {
+    KGAT_REQUIRE(g && runs && entity && rel_emb && W_R && logits_csr);
+    KGAT_REQUIRE(runs->bk_run && runs->run_ptr && runs->run_head && runs->rel_run_ptr && runs->n_runs && runs->rel_mode);
+    KGAT_REQUIRE(aligned16(entity) && aligned16(rel_emb) && aligned16(W_R) && (!v_rows || aligned16(v_rows)));
+    KGAT_REQUIRE(v_base >= 0 && v_count >= 0 && 0 <= p_begin && p_begin <= p_end && p_end <= g->n_edges);
+    if (d != 64 || rd != 64 || g->n_rel > 1024) return KGAT_ERR_UNSUPPORTED_DIM;
+    if (g->n_edges == 0) return KGAT_OK;
+    cudaStream_t st = as_stream(stream);
+    int* word = kgat_att_fallback_word();
+    if (!word) return KGAT_ERR_CUDA;
+    int rc = kgat_launch_att_range(W_R, g->n_rel * static_cast<int64_t>(d) * rd, word, st);
+    if (rc != KGAT_OK) return rc;
+    // relations marked 0: two projections per edge; relations marked 1: two per (head, relation) run + a dot per edge
+    rc = kgat_launch_att_logits_umma16(g, entity, rel_emb, W_R, logits_csr, word, runs->rel_mode, st);
+    if (rc != KGAT_OK) return rc;
+    if (p_end > p_begin) {
+        rc = kgat_launch_att_logits_runs(g, runs, entity, rel_emb, W_R, logits_csr, v_rows, v_base, v_count, p_begin,
+                                         p_end, runs->rel_mode, word, st);
+        if (rc != KGAT_OK) return rc;
+    }
     return kgat_launch_att_logits_umma(g, entity, rel_emb, W_R, logits_csr, word, st);
 }
 

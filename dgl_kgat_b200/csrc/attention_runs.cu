@@ -126,7 +126,8 @@ att_logits_runs_kernel(const int32_t* __restrict__ rel_run_ptr, int n_rel, const
                        const int32_t* __restrict__ bk_tail, const int32_t* __restrict__ bk_pos,
                        const float* __restrict__ ent, const float* __restrict__ rel_emb,
                        const float* __restrict__ W_R, float* __restrict__ logits_csr,
-                       float* __restrict__ v_out, int* __restrict__ err, int* __restrict__ fallback) {
+                       float* __restrict__ v_out, int64_t v_base, const int32_t* __restrict__ rel_mode,
+                       int* __restrict__ err, int* __restrict__ fallback) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -141,7 +142,9 @@ att_logits_runs_kernel(const int32_t* __restrict__ rel_run_ptr, int n_rel, const
         for (int r0 = 0; r0 < n_rel; r0 += 32) {
             const int r = r0 + lane;
             const int lo = r < n_rel ? rel_run_ptr[r] : 0, hi = r < n_rel ? rel_run_ptr[r + 1] : 0;
-            const int nt = (hi - lo + TILE - 1) / TILE;
+            // hybrid calls: only the relations marked 1 are ours, the per-edge kernel has the others
+            const bool mine = !rel_mode || (r < n_rel && rel_mode[r] == 1);
+            const int nt = mine ? (hi - lo + TILE - 1) / TILE : 0;
             int incl = nt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -184,21 +187,30 @@ att_logits_runs_kernel(const int32_t* __restrict__ rel_run_ptr, int n_rel, const
     // row of the interaction relation vs a KG relation) - with equal counts the two CTAs that got the item
     // relation ran 13 x longer than the rest (measured: 4.5 ms instead of 0.35).  cost(boundary k) = RUN_COST *
     // runs before tile k + edges before tile k, monotone in k: two binary searches per CTA.
+    // cost of everything before relation rel (relations without tiles - empty, or the per-edge kernel's in a hybrid
+    // call - cost nothing); the table borrows A2[0], which no role touches before the ranges are known
+    long long* const cbase = reinterpret_cast<long long*>(s.A2[0]);
+    const long long RUN_COST = v_out ? 1000 : 3;           // split mode: no edge walk in this kernel
     if (tid == 0) {
+        long long c = 0;
+        for (int r = 0; r < n_rel; ++r) {
+            cbase[r] = c;
+            if (s.prefix[r + 1] > s.prefix[r])
+                c += RUN_COST * (s.rstart[r + 1] - s.rstart[r]) +
+                     static_cast<long long>(__ldg(run_ptr + s.rstart[r + 1]) - __ldg(run_ptr + s.rstart[r]));
+        }
+        cbase[n_rel] = c;
         const int n_tiles = s.prefix[n_rel];
-        const long long RUN_COST = v_out ? 1000 : 3;       // split mode: no edge walk in this kernel
-        auto runs_before = [&](int k) {                    // global index of the first run of tile k
-            if (k >= n_tiles) return s.rstart[n_rel];
-            int lo = 0, hi = n_rel - 1;                    // last relation with prefix[rel] <= k
+        auto cost_at = [&](int k) {                        // cost of the tiles before tile k
+            if (k >= n_tiles) return cbase[n_rel];
+            int lo = 0, hi = n_rel - 1;                    // last relation with prefix[rel] <= k: the one that owns tile k
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
                 if (s.prefix[mid] <= k) lo = mid; else hi = mid - 1;
             }
-            return s.rstart[lo] + (k - s.prefix[lo]) * TILE;
-        };
-        auto cost_at = [&](int k) {
-            const int r = runs_before(k);
-            return RUN_COST * r + static_cast<long long>(__ldg(run_ptr + r));
+            const int r = s.rstart[lo] + (k - s.prefix[lo]) * TILE;
+            return cbase[lo] + RUN_COST * (r - s.rstart[lo]) +
+                   static_cast<long long>(__ldg(run_ptr + r) - __ldg(run_ptr + s.rstart[lo]));
         };
         const long long total = cost_at(n_tiles);
         for (int side = 0; side < 2; ++side) {
@@ -439,7 +451,7 @@ att_logits_runs_kernel(const int32_t* __restrict__ rel_run_ptr, int n_rel, const
                 for (int r = w_first + half; r < w_last; r += 2) {
                     const int rl = r - ti.r0;
                     const float4 vv = *reinterpret_cast<const float4*>(V + rl * D + ((l16 ^ (rl & 15)) << 2));
-                    *reinterpret_cast<float4*>(v_out + static_cast<size_t>(r) * D + l16 * 4) = vv;
+                    *reinterpret_cast<float4*>(v_out + static_cast<size_t>(r - v_base) * D + l16 * 4) = vv;
                 }
             } else if (w_first < w_last) {
                 // ---- step 3 (fused mode): the edges of this warp's 32 runs; 16 lanes per edge
@@ -495,39 +507,50 @@ att_logits_runs_kernel(const int32_t* __restrict__ rel_run_ptr, int n_rel, const
     if (warp == MMA_WARP) umma::tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// logit[bk_pos[p]] = e_tail(p) . v[bk_run[p]]  for every bucket position p: 16 lanes per edge (128-bit coalesced row
-// reads), 4 edges per lane group in flight, 16-lane shuffle reduction.  The v rows of consecutive edges are the same
-// row for a whole run, so their reads are L1 / L2 hits.
+// logit[bk_pos[p]] = e_tail(p) . v[bk_run[p]]  for the bucket positions [p_begin, p_end): 16 lanes per edge (128-bit
+// coalesced row reads), 4 edges per lane group with all eight row loads in flight, 16-lane shuffle reduction.  The v
+// rows of consecutive edges are the same row for a whole run, so their reads are L1 hits: taking the row from the
+// previous edge's registers instead (tried, with 4 and with 8 edges per group) made the kernel SLOWER - 0.38 / 0.55
+// against 0.33 ms at the Last-FM shape - the random tail rows out of L2 bound it, not the v rows.
+// `rel_mode` (hybrid calls, else null): only edges whose relation is marked 1 belong to this kernel, and only their
+// runs have a row in v (rows [v_base, v_base + v_count)).
+constexpr int EDGES_PER_GROUP = 4;
+
 __global__ void __launch_bounds__(256)
 edge_dot_kernel(const int32_t* __restrict__ bk_run, const int32_t* __restrict__ bk_tail,
-                const int32_t* __restrict__ bk_pos, int64_t E, const float* __restrict__ ent,
-                const float* __restrict__ v, float* __restrict__ logits_csr, int* __restrict__ fallback) {
+                const int32_t* __restrict__ bk_pos, int64_t p_begin, int64_t p_end, const float* __restrict__ ent,
+                const float* __restrict__ v, int64_t v_base, int64_t v_count, const int32_t* __restrict__ rel_mode,
+                const int32_t* __restrict__ csr_rel, float* __restrict__ logits_csr, int* __restrict__ fallback) {
     const int l16 = threadIdx.x & 15;
     const int64_t grp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 4;
-    const int64_t p0 = grp * 4;
-    if (p0 >= E) return;                                  // whole 16-lane groups leave together
-    int tail[4], run[4];
+    const int64_t p0 = p_begin + grp * EDGES_PER_GROUP;
+    if (p0 >= p_end) return;                              // whole 16-lane groups leave together
+    int tail[EDGES_PER_GROUP];
+    int64_t vr[EDGES_PER_GROUP];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const bool ok = p0 + j < E;
+    for (int j = 0; j < EDGES_PER_GROUP; ++j) {
+        const bool ok = p0 + j < p_end;
         tail[j] = ok ? __ldg(bk_tail + p0 + j) : 0;
-        run[j] = ok ? __ldg(bk_run + p0 + j) : 0;
+        vr[j] = ok ? static_cast<int64_t>(__ldg(bk_run + p0 + j)) - v_base : -1;
+        if (vr[j] >= v_count) vr[j] = -1;                 // hybrid: a run of the other kernel's relation
     }
-    float4 a[4], b[4];
+    float4 a[EDGES_PER_GROUP], b[EDGES_PER_GROUP];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < EDGES_PER_GROUP; ++j) {
         a[j] = ldg4(ent + static_cast<size_t>(tail[j]) * D + l16 * 4);
-        b[j] = ldg4(v + static_cast<size_t>(run[j]) * D + l16 * 4);
+        b[j] = ldg4(v + static_cast<size_t>(vr[j] < 0 ? 0 : vr[j]) * D + l16 * 4);
     }
     const unsigned gmask = 0xffffu << (threadIdx.x & 16);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < EDGES_PER_GROUP; ++j) {
         float p = a[j].x * b[j].x;
         p = fmaf(a[j].y, b[j].y, p); p = fmaf(a[j].z, b[j].z, p); p = fmaf(a[j].w, b[j].w, p);
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) p += __shfl_xor_sync(gmask, p, o);
-        if (l16 == j && p0 + j < E) {
-            logits_csr[__ldg(bk_pos + p0 + j)] = p;
+        if (l16 == j && vr[j] >= 0) {
+            const int pos = __ldg(bk_pos + p0 + j);
+            if (rel_mode && __ldg(rel_mode + __ldg(csr_rel + pos)) != 1) continue;      // the per-edge kernel's edge
+            logits_csr[pos] = p;
             if (!(fabsf(p) < INFINITY)) *reinterpret_cast<volatile int*>(fallback) = 1;
         }
     }
@@ -652,6 +675,15 @@ __global__ void run_finish_kernel(const int32_t* __restrict__ rel_ptr, int n_rel
     if (r == 0) run_ptr[nr] = static_cast<int32_t>(E);
 }
 
+// rel_mode[r] = 1 when relation r is worth the run shortcut: at most a third as many runs as edges
+__global__ void rel_mode_kernel(const int32_t* __restrict__ rel_ptr, const int32_t* __restrict__ rel_run_ptr, int n_rel,
+                                int32_t* __restrict__ rel_mode) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rel) return;
+    const int64_t edges = rel_ptr[r + 1] - rel_ptr[r], runs = rel_run_ptr[r + 1] - rel_run_ptr[r];
+    rel_mode[r] = (edges > 0 && 3 * runs <= edges) ? 1 : 0;
+}
+
 }  // namespace
 }  // namespace kgat
 
@@ -673,6 +705,7 @@ extern "C" int kgat_runs_build(const kgat_graph_t* g, const kgat_runs_t* runs, v
         KGAT_CUDA(cudaMemsetAsync(runs->rel_run_ptr, 0, sizeof(int32_t) * (R + 1), st));
         KGAT_CUDA(cudaMemsetAsync(runs->n_runs, 0, sizeof(int32_t), st));
         KGAT_CUDA(cudaMemsetAsync(runs->run_ptr, 0, sizeof(int32_t), st));
+        if (runs->rel_mode) KGAT_CUDA(cudaMemsetAsync(runs->rel_mode, 0, sizeof(int32_t) * R, st));
         return KGAT_OK;
     }
     KGAT_REQUIRE(workspace && workspace_bytes >= kgat_runs_build_workspace_bytes(E));
@@ -690,15 +723,22 @@ extern "C" int kgat_runs_build(const kgat_graph_t* g, const kgat_runs_t* runs, v
     run_finish_kernel<<<(R + 1 + 255) / 256, 256, 0, st>>>(g->rel_ptr, R, E, runs->bk_run, runs->n_runs, runs->run_ptr,
                                                            runs->rel_run_ptr);
     KGAT_LAUNCH_CHECK();
+    if (runs->rel_mode) {
+        rel_mode_kernel<<<(R + 255) / 256, 256, 0, st>>>(g->rel_ptr, runs->rel_run_ptr, R, runs->rel_mode);
+        KGAT_LAUNCH_CHECK();
+    }
     return KGAT_OK;
 }
 
 int* kgat_umma_error_word();      // attention_umma.cu
 
-// Launcher used by kgat_attention_logits_runs (attention.cu) for d = rd = 64.
+// Launcher used by kgat_attention_logits_runs / _hybrid (attention.cu) for d = rd = 64.
+// hybrid (rel_mode non-null): only the relations marked 1; v_rows then holds the runs [v_base, v_base + v_count)
+// and the edge dots cover the bucket positions [p_begin, p_end) that span those relations.
 int kgat_launch_att_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
-                                const float* rel_emb, const float* W_R, float* logits_csr, float* v_rows, int* fallback,
-                                cudaStream_t st) {
+                                const float* rel_emb, const float* W_R, float* logits_csr, float* v_rows,
+                                int64_t v_base, int64_t v_count, int64_t p_begin, int64_t p_end,
+                                const int32_t* rel_mode, int* fallback, cudaStream_t st) {
     static PerDeviceOnce configured;
     int* err_flag = kgat_umma_error_word();
     if (!err_flag) return KGAT_ERR_CUDA;
@@ -708,16 +748,17 @@ int kgat_launch_att_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, 
         configured.set();
     }
     // the run count lives on the device; the grid is sized for the worst case (n_runs <= E) and capped at the SMs
-    const int64_t max_tiles = g->n_edges / TILE + g->n_rel;
+    const int64_t max_tiles = (rel_mode ? p_end - p_begin : g->n_edges) / TILE + g->n_rel;
     const int grid = static_cast<int>(max_tiles < num_sms() ? max_tiles : num_sms());
     att_logits_runs_kernel<<<grid, THREADS, sizeof(Smem), st>>>(
         runs->rel_run_ptr, static_cast<int>(g->n_rel), runs->run_ptr, runs->run_head, runs->bk_run, g->bk_tail, g->bk_pos,
-        entity, rel_emb, W_R, logits_csr, v_rows, err_flag, fallback);
+        entity, rel_emb, W_R, logits_csr, v_rows, v_base, rel_mode, err_flag, fallback);
     KGAT_LAUNCH_CHECK();
-    if (v_rows) {
-        const int64_t groups = (g->n_edges + 3) / 4;
+    if (v_rows && p_end > p_begin) {
+        const int64_t groups = (p_end - p_begin + EDGES_PER_GROUP - 1) / EDGES_PER_GROUP;
         edge_dot_kernel<<<static_cast<unsigned>((groups * 16 + 255) / 256), 256, 0, st>>>(
-            runs->bk_run, g->bk_tail, g->bk_pos, g->n_edges, entity, v_rows, logits_csr, fallback);
+            runs->bk_run, g->bk_tail, g->bk_pos, p_begin, p_end, entity, v_rows, v_base, v_count, rel_mode, g->csr_rel,
+            logits_csr, fallback);
         KGAT_LAUNCH_CHECK();
     }
     return KGAT_OK;

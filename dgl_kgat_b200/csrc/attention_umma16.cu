@@ -146,7 +146,7 @@ att_logits_umma16_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const i
                          const int32_t* __restrict__ bk_tail, const int32_t* __restrict__ bk_pos,
                          const float* __restrict__ ent, const float* __restrict__ rel_emb,
                          const float* __restrict__ W_R, float* __restrict__ logits_csr,
-                         int* __restrict__ err, int* __restrict__ fallback) {
+                         int* __restrict__ err, int* __restrict__ fallback, const int32_t* __restrict__ rel_skip) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -164,7 +164,9 @@ att_logits_umma16_kernel(const int32_t* __restrict__ rel_ptr, int n_rel, const i
         for (int r0 = 0; r0 < n_rel; r0 += 32) {
             const int r = r0 + lane;
             const int lo = r < n_rel ? rel_ptr[r] : 0, hi = r < n_rel ? rel_ptr[r + 1] : 0;
-            const int nt = (hi - lo + TILE - 1) / TILE;
+            // hybrid calls: relations marked 1 belong to the run kernel and get no tiles here
+            const bool skip = rel_skip && r < n_rel && rel_skip[r] == 1;
+            const int nt = skip ? 0 : (hi - lo + TILE - 1) / TILE;
             int incl = nt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -468,7 +470,8 @@ int* kgat_umma_error_word();      // attention_umma.cu
 
 // Launcher used by kgat_attention_logits for d = rd = 64 (declared in attention.cu).
 int kgat_launch_att_logits_umma16(const kgat_graph_t* g, const float* entity, const float* rel_emb,
-                                  const float* W_R, float* logits_csr, int* fallback, cudaStream_t st) {
+                                  const float* W_R, float* logits_csr, int* fallback, const int32_t* rel_skip,
+                                  cudaStream_t st) {
     static PerDeviceOnce configured;
     int* err_flag = kgat_umma_error_word();
     if (!err_flag) return KGAT_ERR_CUDA;
@@ -481,7 +484,7 @@ int kgat_launch_att_logits_umma16(const kgat_graph_t* g, const float* entity, co
     const int grid = static_cast<int>(max_tiles < num_sms() ? max_tiles : num_sms());
     att_logits_umma16_kernel<<<grid, THREADS, sizeof(Smem), st>>>(
         g->rel_ptr, static_cast<int>(g->n_rel), g->bk_head, g->bk_tail, g->bk_pos, entity, rel_emb, W_R, logits_csr,
-        err_flag, fallback);
+        err_flag, fallback, rel_skip);
     KGAT_LAUNCH_CHECK();
     return KGAT_OK;
 }

@@ -432,9 +432,11 @@ class DistKGAT:
         if d0 == 64 and model.relation_embed.weight.shape[1] == 64 and self.part.n_edges > 0 and n_rel <= 1024 \
                 and self.device.type == "cuda":
             self.dg_in.runs()
-            n_runs = th.tensor([self.dg_in.n_runs], dtype=th.int64, device=self.device)
-            tdist.all_reduce(n_runs, group=group)
-            self.att_impl = ops.attention_impl_for(int(n_runs.item()), self.part.n_edges)
+            counts = th.from_numpy(np.stack([self.dg_in.rel_edges, self.dg_in.rel_runs])).to(self.device)
+            tdist.all_reduce(counts, group=group)
+            counts = counts.cpu().numpy()
+            self.att_impl, mode = ops.attention_plan_for(counts[0], counts[1])
+            self.dg_in.set_rel_mode(mode)         # per-relation marks of the whole graph, not of this rank's slice
         self.w_full = None
         self._plan = None
         self._dw_views = None

@@ -71,7 +71,8 @@ class DeviceGraph:
             lib = _lib.load()
             E, R = self.n_edges, self.n_rel
             with th.cuda.device(self.device):
-                sizes = {"bk_run": max(E, 1), "run_ptr": E + 1, "run_head": max(E, 1), "rel_run_ptr": R + 1, "n_runs": 1}
+                sizes = {"bk_run": max(E, 1), "run_ptr": E + 1, "run_head": max(E, 1), "rel_run_ptr": R + 1, "n_runs": 1,
+                         "rel_mode": R}
                 self.run_arrays = {n: th.zeros(sizes[n], dtype=th.int32, device=self.device) for n in _lib.RUN_ARRAYS}
                 self._runs = _lib.KgatRuns(*[self.run_arrays[n].data_ptr() for n in _lib.RUN_ARRAYS])
                 ws_bytes = lib.kgat_runs_build_workspace_bytes(E)
@@ -80,7 +81,35 @@ class DeviceGraph:
                                                _lib.stream_ptr()), "kgat_runs_build")
                 th.cuda.current_stream().synchronize()      # ws must outlive the build
                 self.n_runs = int(self.run_arrays["n_runs"].item())
+                # per relation: edges, runs, and the mark the library derived from them (1 = run shortcut pays)
+                rel_ptr = self.arrays["rel_ptr"].cpu().numpy().astype(np.int64)
+                rel_run_ptr = self.run_arrays["rel_run_ptr"].cpu().numpy().astype(np.int64)
+                self.rel_edges, self.rel_runs = np.diff(rel_ptr), np.diff(rel_run_ptr)
+                self._rel_ptr, self._rel_run_ptr = rel_ptr, rel_run_ptr
+                self.rel_mode = self.run_arrays["rel_mode"].cpu().numpy().copy()
         return ctypes.byref(self._runs)
+
+    def set_rel_mode(self, mode):
+        """Override the per-relation marks (dist.DistKGAT: decided from the GLOBAL counts so that every rank and the
+        single-GPU step run the same arithmetic on every edge)."""
+        self.runs()
+        mode = np.ascontiguousarray(mode, dtype=np.int32)
+        if mode.shape != (self.n_rel,):
+            raise ValueError("rel_mode must have one entry per relation")
+        self.run_arrays["rel_mode"].copy_(th.from_numpy(mode))
+        self.rel_mode = mode.copy()
+
+    def hybrid_spans(self):
+        """What kgat_attention_logits_hybrid needs about the marked relations of THIS graph: the run range and the
+        bucket-position range from the first to the last marked relation that has edges here, or None."""
+        self.runs()
+        marked = np.flatnonzero((self.rel_mode == 1) & (self.rel_edges > 0))
+        if len(marked) == 0:
+            return None
+        lo, hi = int(marked[0]), int(marked[-1])
+        return {"v_base": int(self._rel_run_ptr[lo]), "v_count": int(self._rel_run_ptr[hi + 1] - self._rel_run_ptr[lo]),
+                "p_begin": int(self._rel_ptr[lo]), "p_end": int(self._rel_ptr[hi + 1]),
+                "marked_edges": int(self.rel_edges[marked].sum()), "marked_runs": int(self.rel_runs[marked].sum())}
 
     def edge_weights(self, w_eid: th.Tensor):
         """(w_csr, w_csc) for an (E,) or (E,1) weight tensor given in edge-id order."""

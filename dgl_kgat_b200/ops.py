@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import os
 
+import numpy as np
 import torch as th
 
 from . import _lib
@@ -43,6 +44,23 @@ def attention_impl_for(n_runs: int, n_edges: int) -> str:
     return "runs" if 3 * n_runs <= n_edges else "f16"
 
 
+def attention_plan_for(rel_edges, rel_runs):
+    """(impl, rel_mode) from the per-relation edge and (head, relation)-run counts of the WHOLE graph.
+    impl: "runs" (the run shortcut) when runs are at most a third of the edges, the per-edge kernel "f16" otherwise.
+    rel_mode[r] = 1 where relation r alone passes that test (kgat_runs_build applies the same rule on the device):
+    the marks of the per-RELATION choice, KGAT_ATT_IMPL=hybrid.  That one is opt-in: on the synthetic Amazon-book
+    graph (random KG heads next to the two interaction relations, whose rows are one run each) it measured
+    0.377 ms against 0.344 ms for the per-edge kernel alone - a second tensor-core kernel with its own set-up, W_r
+    staging and tail costs more than the 30 % of the projections it saves.
+    KGAT_ATT_IMPL = runs / runs_fused / hybrid / f16 / tf32 / ffma forces a kernel (A/B runs)."""
+    rel_edges, rel_runs = np.asarray(rel_edges, dtype=np.int64), np.asarray(rel_runs, dtype=np.int64)
+    mode = ((rel_edges > 0) & (3 * rel_runs <= rel_edges)).astype(np.int32)
+    impl = os.environ.get("KGAT_ATT_IMPL", "auto")
+    if impl == "auto":
+        impl = "runs" if 3 * int(rel_runs.sum()) <= int(rel_edges.sum()) else "f16"
+    return impl, mode
+
+
 def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Tensor, rows=None, want_eid=True,
               w_csr_out=None, peer=None, impl=None):
     """Logits + per-destination softmax (reference models.py:146-154).
@@ -77,19 +95,27 @@ def attention(dg: DeviceGraph, entity: th.Tensor, rel_emb: th.Tensor, W_R: th.Te
         # relation) RUN, not per edge (kgat_attention_logits_runs).  It pays when runs are much fewer than edges -
         # always on a real CKG (every user row is one run), 12.7 x on the Last-FM shape - and not on a KG with
         # uniformly random heads (Amazon-book synthetic: 0.52 runs per edge), where the per-edge kernel stays the
-        # default.  KGAT_ATT_IMPL = runs / runs_fused / f16 / tf32 / ffma forces a kernel (A/B runs).
+        # only kernel for the KG relations, while its two interaction relations take the shortcut ("hybrid":
+        # attention_plan_for).  KGAT_ATT_IMPL = runs / runs_fused / hybrid / f16 / tf32 / ffma forces a kernel.
         # ``impl``: the caller's choice (dist.DistKGAT decides from the GLOBAL run count so that every rank - and the
         # single-GPU step - runs the same arithmetic); None: decide from this graph
         can_runs = d == 64 and rd == 64 and dg.n_rel <= 1024 and dg.n_edges > 0
         if impl is None:
             impl = os.environ.get("KGAT_ATT_IMPL", "auto")
-            if impl == "auto" and can_runs:
+            if impl in ("auto", "hybrid") and can_runs:
                 dg.runs()
-                impl = attention_impl_for(dg.n_runs, dg.n_edges)
+                impl, _ = attention_plan_for(dg.rel_edges, dg.rel_runs)
+        spans = dg.hybrid_spans() if (can_runs and impl == "hybrid") else None     # None: no marked edge on this rank
         use_runs = can_runs and impl in ("runs", "runs_fused")
-        runs = dg.runs() if use_runs else None           # built (and synchronised) once per graph, outside any capture
-        with _lib.record("attention_logits", 4 if use_runs else 3):
-            if use_runs:
+        runs = dg.runs() if (use_runs or spans is not None) else None     # built once per graph, outside any capture
+        with _lib.record("attention_logits", 5 if spans is not None else (4 if use_runs else 3)):
+            if spans is not None:
+                v_rows = th.empty(max(spans["v_count"], 1), d, dtype=th.float32, device=dev)
+                _lib.check(lib.kgat_attention_logits_hybrid(dg.ref, runs, entity.data_ptr(), rel_emb.data_ptr(),
+                                                            W_R.data_ptr(), d, rd, logits.data_ptr(), v_rows.data_ptr(),
+                                                            spans["v_base"], spans["v_count"], spans["p_begin"],
+                                                            spans["p_end"], st), "kgat_attention_logits_hybrid")
+            elif use_runs:
                 v_rows = None if impl == "runs_fused" else th.empty(max(dg.n_runs, 1), d, dtype=th.float32, device=dev)
                 _lib.check(lib.kgat_attention_logits_runs(dg.ref, runs, entity.data_ptr(), rel_emb.data_ptr(),
                                                           W_R.data_ptr(), d, rd, logits.data_ptr(), _lib.ptr(v_rows), st),

@@ -157,6 +157,7 @@ typedef struct kgat_runs_t {
     int32_t *run_head;      /* [E] */
     int32_t *rel_run_ptr;   /* [n_rel+1] */
     int32_t *n_runs;        /* [1] */
+    int32_t *rel_mode;      /* [n_rel] or NULL: 1 = the relation has at most a third as many runs as edges */
 } kgat_runs_t;
 KGAT_API size_t kgat_runs_build_workspace_bytes(int64_t n_edges);
 KGAT_API int kgat_runs_build(const kgat_graph_t* g, const kgat_runs_t* runs, void* workspace, size_t workspace_bytes,
@@ -164,6 +165,16 @@ KGAT_API int kgat_runs_build(const kgat_graph_t* g, const kgat_runs_t* runs, voi
 KGAT_API int kgat_attention_logits_runs(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
                                const float* rel_emb, const float* W_R, int d, int rd, float* logits_csr,
                                float* v_rows, kgat_stream_t stream);
+/* (2h) the choice per RELATION: relations with runs->rel_mode[r] == 1 go through the run shortcut, the others
+ *      through the per-edge kernel of kgat_attention_logits (a synthetic KG with random heads next to the two
+ *      interaction relations, whose rows are one run each).  The caller reads rel_mode / rel_ptr / rel_run_ptr
+ *      once per graph and passes the spans of the marked relations: v_rows holds the runs
+ *      [v_base, v_base + v_count) (64 floats each; NULL = fused edge walk), [p_begin, p_end) are the bucket
+ *      positions from the first to the last marked relation. */
+KGAT_API int kgat_attention_logits_hybrid(const kgat_graph_t* g, const kgat_runs_t* runs, const float* entity,
+                                 const float* rel_emb, const float* W_R, int d, int rd, float* logits_csr,
+                                 float* v_rows, int64_t v_base, int64_t v_count, int64_t p_begin, int64_t p_end,
+                                 kgat_stream_t stream);
 
 /* (3a) softmax over the in-edges of every destination row -- replaces
  *      edge_softmax (models.py:153).  Rows [row_begin,row_end).  Writes the weights

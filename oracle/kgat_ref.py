@@ -101,23 +101,46 @@ def aggregate(h, w, trip, n_nodes):
     return th.zeros(n_nodes, h.shape[1], dtype=h.dtype).index_add(0, dst, h[src] * w)
 
 
-def kgat_conv(h, w, trip, n_nodes, W2, drop_mask=None):
-    """KGATConv.forward, models.py:60-70 (only the h (.) h_N branch exists, :66)."""
+def kgat_conv(h, w, trip, n_nodes, W2, drop_mask=None, branch=None, info=None):
+    """KGATConv.forward, models.py:60-70 (only the h (.) h_N branch exists, :66).
+
+    ``branch`` = (signs, tol), test-only: LeakyReLU's derivative jumps at 0, so a gradient comparison between two
+    arithmetics is only meaningful when both took the same branch.  Where a pre-activation lies within the
+    forward error band of zero, |pre| <= tol * (|z| |W2|^T) - the rounding of the dot product that produced it,
+    relative to the magnitude of its terms - the branch is taken from ``signs`` (the signs of the other
+    implementation's layer output) instead of from this evaluation.  ``info`` collects how many elements the two
+    implementations decided differently and how many of those lay outside the band."""
     h_n = aggregate(h, w, trip, n_nodes)
-    out = F.leaky_relu(F.linear(th.mul(h, h_n), W2))
+    z = th.mul(h, h_n)
+    pre = F.linear(z, W2)
+    if branch is None:
+        out = F.leaky_relu(pre)
+    else:
+        signs, tol = branch
+        with th.no_grad():
+            band = tol * F.linear(z.abs(), W2.abs())
+            near = pre.abs() <= band
+            other_pos = signs > 0
+            pos = th.where(near, other_pos, pre > 0)
+            if info is not None:
+                differ = (other_pos != (pre > 0)) & (signs != 0)
+                info.append({"differ": int(differ.sum()), "outside_band": int((differ & ~near).sum()),
+                             "in_band": int(near.sum())})
+        out = th.where(pos, pre, 0.01 * pre)              # F.leaky_relu's default slope (models.py:66)
     if drop_mask is not None:
         out = out * drop_mask
     return out
 
 
-def gnn(params, trip, w, n_nodes, drop_masks=None):
+def gnn(params, trip, w, n_nodes, drop_masks=None, branch_signs=None, branch_tol=1e-5, info=None):
     """Model.gnn, models.py:156-168: cache [e, norm(h1), norm(h2), ...], un-normalised h
-    feeds the next layer, concat along dim 1."""
+    feeds the next layer, concat along dim 1.  ``branch_signs``: one sign tensor per layer (see kgat_conv)."""
     h = params["entity_embed.weight"]
     cache = [h]
     for i in range(n_layers_of(params)):
         m = None if drop_masks is None else drop_masks[i]
-        h = kgat_conv(h, w, trip, n_nodes, params["layers.%d.res_fc_2.weight" % i], m)
+        b = None if branch_signs is None else (branch_signs[i], branch_tol)
+        h = kgat_conv(h, w, trip, n_nodes, params["layers.%d.res_fc_2.weight" % i], m, branch=b, info=info)
         cache.append(F.normalize(h, p=2, dim=1))
     return th.cat(cache, 1)
 
@@ -148,12 +171,24 @@ def transr_loss(params, h, r, pos_t, neg_t, reg_lambda):
     return l + reg_lambda * reg
 
 
-def cf_step(params, trip, w, n_nodes, src_ids, pos_ids, neg_ids, reg_lambda):
+def layer_signs(embedding, params):
+    """Signs of the layer outputs as they appear in an (N, sum d) embedding (normalisation keeps them)."""
+    d0 = params["entity_embed.weight"].shape[1]
+    out, off = [], d0
+    for i in range(n_layers_of(params)):
+        d = params["layers.%d.res_fc_2.weight" % i].shape[0]
+        out.append(th.sign(embedding[:, off:off + d]).to(params["entity_embed.weight"].dtype))
+        off += d
+    return out
+
+
+def cf_step(params, trip, w, n_nodes, src_ids, pos_ids, neg_ids, reg_lambda, branch_signs=None, branch_tol=1e-5,
+            info=None):
     """One CF iteration of kgat.py:159-161: gnn forward, BPR loss, backward.
-    Returns (loss, embedding, grads) with grads keyed like ``params``."""
+    Returns (loss, embedding, grads) with grads keyed like ``params``.  ``branch_signs``: see kgat_conv."""
     leaves = {k: v.detach().clone().requires_grad_(k == "entity_embed.weight" or k.startswith("layers."))
               for k, v in params.items()}
-    emb = gnn(leaves, trip, w, n_nodes)
+    emb = gnn(leaves, trip, w, n_nodes, branch_signs=branch_signs, branch_tol=branch_tol, info=info)
     loss = get_loss(emb, src_ids, pos_ids, neg_ids, reg_lambda)
     loss.backward()
     grads = {k: v.grad for k, v in leaves.items() if v.grad is not None}

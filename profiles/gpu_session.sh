@@ -6,7 +6,8 @@ TAG=${1:-r2}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu_$TAG.txt
-( time timeout 900 python -m pytest tests -x -q -m gpu ) > $OUT/pytest_gpu_$TAG.log 2>&1
+rm -f $OUT/parity_fullsize_$TAG.jsonl
+( time KGAT_PARITY_LOG=$OUT/parity_fullsize_$TAG.jsonl timeout 900 python -m pytest tests -x -q -m gpu ) > $OUT/pytest_gpu_$TAG.log 2>&1
 tail -3 $OUT/pytest_gpu_$TAG.log
 timeout 600 python bench.py > $OUT/bench_${TAG}_n1.json 2> $OUT/bench_${TAG}_n1.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_${TAG}_reference.json 2> $OUT/bench_${TAG}_reference.err

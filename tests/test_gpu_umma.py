@@ -105,12 +105,21 @@ def test_attention_logits_precision_by_magnitude(dev, scale):
     dg = g.device_graph(dev)
     eid = dg.arrays["csr_eid"].cpu().numpy().astype(np.int64)
     out = {}
-    for impl in ("ffma", "tf32", "f16", "runs", "runs_fused"):
+    for impl in ("ffma", "tf32", "f16", "runs", "runs_fused", "hybrid"):
         os.environ["KGAT_ATT_IMPL"] = impl
         try:
             lib = _lib.load()
             logits = th.empty(len(trip), device=dev)
-            if impl.startswith("runs"):
+            if impl == "hybrid":
+                runs, sp = dg.runs(), dg.hybrid_spans()
+                assert sp is not None and 0 < sp["marked_edges"] < len(trip)      # the tiny CKG has both kinds
+                vr = th.empty(max(sp["v_count"], 1), 64, device=dev)
+                _lib.check(lib.kgat_attention_logits_hybrid(dg.ref, runs, m.entity_embed.weight.data_ptr(),
+                                                            m.relation_embed.weight.data_ptr(), m.W_R.data_ptr(), 64, 64,
+                                                            logits.data_ptr(), vr.data_ptr(), sp["v_base"], sp["v_count"],
+                                                            sp["p_begin"], sp["p_end"], _lib.stream_ptr()),
+                           "kgat_attention_logits_hybrid")
+            elif impl.startswith("runs"):
                 runs = dg.runs()
                 vr = th.empty(max(dg.n_runs, 1), 64, device=dev) if impl == "runs" else None
                 _lib.check(lib.kgat_attention_logits_runs(dg.ref, runs, m.entity_embed.weight.data_ptr(),
@@ -365,4 +374,27 @@ def test_runs_structure_bit_exact_and_logits(dev, case):
         th.cuda.synchronize()
         got = logits.cpu().numpy().astype(np.float64)
         assert float(np.abs(got - ref[eid]).max() / np.abs(ref).max()) < 1e-5, fused
+    # per-relation choice with ARBITRARY marks (every other relation, none, all): every edge is written exactly by
+    # the kernel that owns its relation - the NaN prefill shows an edge nobody wrote
+    own_mode = dg.rel_mode.copy()
+    for pattern in ("alternate", "none", "all", "library"):
+        mode = {"alternate": (np.arange(R) % 2).astype(np.int32), "none": np.zeros(R, np.int32),
+                "all": np.ones(R, np.int32), "library": own_mode}[pattern]
+        dg.set_rel_mode(mode)
+        sp = dg.hybrid_spans()
+        logits = th.full((E,), float("nan"), device=dev)
+        if sp is None:
+            _lib.check(lib.kgat_attention_logits(dg.ref, m.entity_embed.weight.data_ptr(), m.relation_embed.weight.data_ptr(),
+                                                 m.W_R.data_ptr(), 64, 64, logits.data_ptr(), _lib.stream_ptr()), "logits")
+        else:
+            vr = th.empty(max(sp["v_count"], 1), 64, device=dev)
+            _lib.check(lib.kgat_attention_logits_hybrid(dg.ref, dg.runs(), m.entity_embed.weight.data_ptr(),
+                                                        m.relation_embed.weight.data_ptr(), m.W_R.data_ptr(), 64, 64,
+                                                        logits.data_ptr(), vr.data_ptr(), sp["v_base"], sp["v_count"],
+                                                        sp["p_begin"], sp["p_end"], _lib.stream_ptr()), "hybrid")
+        th.cuda.synchronize()
+        got = logits.cpu().numpy().astype(np.float64)
+        assert np.isfinite(got).all(), pattern
+        assert float(np.abs(got - ref[eid]).max() / np.abs(ref).max()) < 1e-5, pattern
+    dg.set_rel_mode(own_mode)
     assert lib.kgat_umma_error_flag() == 0 and lib.kgat_attention_fallbacks() == 0

@@ -388,3 +388,21 @@ def test_tensor_core_tile_decomposition_of_the_layer_gemms(d_in, d_out):
         scatter(dz, acc, 16 * mt, 8 * nt)
     assert np.allclose(dz, dp @ w2)
 
+
+
+def test_attention_plan_rule(monkeypatch):
+    """Which logits kernel a graph gets (ops.attention_plan_for): the run shortcut or the per-edge kernel - decided
+    from integer counts, so every rank of a partitioned graph (which all-reduces the counts) reaches the decision of
+    the single-GPU step; the per-relation marks serve the opt-in hybrid call."""
+    from dgl_kgat_b200 import ops
+    monkeypatch.delenv("KGAT_ATT_IMPL", raising=False)
+    impl, mode = ops.attention_plan_for([100, 90, 0], [10, 80, 0])
+    assert impl == "f16" and mode.tolist() == [1, 0, 0]           # per-relation marks; the hybrid kernel is opt-in
+    impl, mode = ops.attention_plan_for([100, 90], [10, 30])
+    assert impl == "runs" and mode.tolist() == [1, 1]
+    impl, mode = ops.attention_plan_for([0, 0], [0, 0])
+    assert impl == "runs" and mode.tolist() == [0, 0]
+    monkeypatch.setenv("KGAT_ATT_IMPL", "hybrid")
+    assert ops.attention_plan_for([100, 90, 0], [10, 80, 0])[0] == "hybrid"
+    monkeypatch.setenv("KGAT_ATT_IMPL", "tf32")
+    assert ops.attention_plan_for([100, 90, 0], [10, 80, 0])[0] == "tf32"
