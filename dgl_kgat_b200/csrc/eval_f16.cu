@@ -517,32 +517,52 @@ score_topk_f16_kernel(const unsigned char* __restrict__ u_blob, const unsigned c
 
 // L sorted lists per user (one per item range and read-out group) -> the user's top-K: highest score first,
 // equal scores by lower item index - exactly what one list over the whole item axis would hold.
-__global__ void __launch_bounds__(128)
+// Sixteen lanes per user, lane s owns list s: the lists are staged in shared memory with coalesced loads, then K
+// rounds of a 16-lane arg-max over the list heads (shuffles), the winner's lane advances.  (One thread per user
+// walking L list heads in global memory per round took 93 us for the 10 lists of an 8-way user shard.)
+constexpr int MERGE_USERS = 8;                    // users per CTA (128 threads)
+constexpr int MERGE_K_MAX = 32;
+
+__global__ void __launch_bounds__(16 * MERGE_USERS)
 topk_merge_kernel(const int32_t* __restrict__ part_idx, const float* __restrict__ part_score, int n_users, int L,
                   int K, int32_t* __restrict__ out_idx, float* __restrict__ out_score,
                   const unsigned int* __restrict__ word) {
+    __shared__ int32_t s_idx[MERGE_USERS][L_MAX * MERGE_K_MAX];
+    __shared__ float s_sc[MERGE_USERS][L_MAX * MERGE_K_MAX];
     if (*reinterpret_cast<const volatile unsigned int*>(word + 1)) return;
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_users) return;
-    const float inv = 1.0f / operand_scale(word[0]);          // scores back to the caller's units: / s, twice
-    unsigned char ptr[L_MAX];
-#pragma unroll
-    for (int s = 0; s < L_MAX; ++s) ptr[s] = 0;
+    const int lu = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+    const int u = blockIdx.x * MERGE_USERS + lu;
+    if (u >= n_users) return;                             // whole 16-lane groups leave together
+    const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+    const float inv = 1.0f / operand_scale(word[0]);      // scores back to the caller's units: / s, twice
     const size_t base = static_cast<size_t>(u) * L * K;
+    for (int i = l16; i < L * K; i += 16) {
+        s_idx[lu][i] = part_idx[base + i];
+        s_sc[lu][i] = part_score[base + i];
+    }
+    __syncwarp(gmask);
+    int pos = 0;                                          // head of this lane's list
     for (int k = 0; k < K; ++k) {
-        int best = -1, best_idx = -1;
-        float best_sc = -INFINITY;
-        for (int s = 0; s < L; ++s) {
-            if (ptr[s] >= K) continue;
-            const size_t o = base + static_cast<size_t>(s) * K + ptr[s];
-            const int idx = part_idx[o];
-            if (idx < 0) continue;
-            const float sc = part_score[o];
-            if (best < 0 || sc > best_sc || (sc == best_sc && idx < best_idx)) { best = s; best_sc = sc; best_idx = idx; }
+        int idx = -1;
+        float sc = -INFINITY;
+        if (l16 < L && pos < K) {
+            idx = s_idx[lu][l16 * K + pos];
+            sc = idx >= 0 ? s_sc[lu][l16 * K + pos] : -INFINITY;
         }
-        out_idx[static_cast<size_t>(u) * K + k] = best_idx;
-        if (out_score) out_score[static_cast<size_t>(u) * K + k] = best >= 0 ? best_sc * inv * inv : -INFINITY;
-        if (best >= 0) ++ptr[best];
+        int b_idx = idx, b_lane = idx >= 0 ? l16 : -1;
+        float b_sc = sc;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const int o_idx = __shfl_xor_sync(gmask, b_idx, o), o_lane = __shfl_xor_sync(gmask, b_lane, o);
+            const float o_sc = __shfl_xor_sync(gmask, b_sc, o);
+            const bool take = o_lane >= 0 && (b_lane < 0 || o_sc > b_sc || (o_sc == b_sc && o_idx < b_idx));
+            if (take) { b_idx = o_idx; b_lane = o_lane; b_sc = o_sc; }
+        }
+        if (l16 == 0) {
+            out_idx[static_cast<size_t>(u) * K + k] = b_lane >= 0 ? b_idx : -1;
+            if (out_score) out_score[static_cast<size_t>(u) * K + k] = b_lane >= 0 ? b_sc * inv * inv : -INFINITY;
+        }
+        if (b_lane == l16) ++pos;
     }
 }
 
@@ -553,14 +573,18 @@ __device__ unsigned int g_eval_word[4] = {0, 0, 0, 0x7f800000u};
 
 inline size_t align1k(size_t x) { return (x + 1023) / 1024 * 1024; }
 
-// item ranges per user tile: fill the SMs at any user count without paying the user-tile load and the
-// pipeline ramp (~3 item tiles) more often than it helps
+// item ranges per user tile: fill the SMs at any user count without paying a unit's fixed cost more often than it
+// helps.  That cost is not the user-tile load but the cold top-K lists: until a row has seen K good scores every
+// score is a candidate and goes through the insertion path.  Measured on B200 (profiles/eval_shards.py): 3.65 us
+// per item tile in steady state, ~95 us per unit on top = 26 tiles (the first version assumed 3 and cut an
+// eighth of the users into 5-7 ranges: 1.18 ms for a 4-way shard where S = 1 takes 0.8).
+constexpr int UNIT_OVERHEAD_TILES = 26;
 inline int pick_splits(int u_tiles, int n_it, int sms) {
     int best_s = 1;
     long long best_cost = -1;
     for (int s = 1; s <= S_MAX && s <= n_it; ++s) {
         const long long waves = (static_cast<long long>(u_tiles) * s + sms - 1) / sms;
-        const long long cost = waves * ((n_it + s - 1) / s + 3);
+        const long long cost = waves * ((n_it + s - 1) / s + UNIT_OVERHEAD_TILES);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s; }
     }
     return best_s;
@@ -656,7 +680,7 @@ int kgat_launch_score_topk_f16(const float* emb, int64_t emb_stride, int dim, co
         ws + p.u_blob, ws + p.i_blob, n_users, n_items, p.nkb, p.n_ks, p.S, mask_ptr, mask_items, K, pidx, pscore,
         err_word, word);
     KGAT_LAUNCH_CHECK();
-    topk_merge_kernel<<<(n_users + 127) / 128, 128, 0, st>>>(pidx, pscore, n_users, p.S * N_GRP, K, topk_idx, topk_score,
+    topk_merge_kernel<<<(n_users + MERGE_USERS - 1) / MERGE_USERS, 16 * MERGE_USERS, 0, st>>>(pidx, pscore, n_users, p.S * N_GRP, K, topk_idx, topk_score,
                                                              word);
     KGAT_LAUNCH_CHECK();
     return kgat_launch_score_topk_umma(emb, emb_stride, dim, user_ids, n_users, item_ids, n_items, mask_ptr, mask_items, K,
