@@ -521,24 +521,26 @@ score_topk_f16_kernel(const unsigned char* __restrict__ u_blob, const unsigned c
 // rounds of a 16-lane arg-max over the list heads (shuffles), the winner's lane advances.  (One thread per user
 // walking L list heads in global memory per round took 93 us for the 10 lists of an 8-way user shard.)
 constexpr int MERGE_USERS = 8;                    // users per CTA (128 threads)
-constexpr int MERGE_K_MAX = 32;
 
 __global__ void __launch_bounds__(16 * MERGE_USERS)
 topk_merge_kernel(const int32_t* __restrict__ part_idx, const float* __restrict__ part_score, int n_users, int L,
                   int K, int32_t* __restrict__ out_idx, float* __restrict__ out_score,
                   const unsigned int* __restrict__ word) {
-    __shared__ int32_t s_idx[MERGE_USERS][L_MAX * MERGE_K_MAX];
-    __shared__ float s_sc[MERGE_USERS][L_MAX * MERGE_K_MAX];
+    // dynamic shared memory, MERGE_USERS * L * K (index, score) pairs: sized for the call, not for L_MAX lists -
+    // a static 32 KB array left 7 CTAs per SM and made the 2-list merge of an unsharded evaluation 3x slower
+    extern __shared__ __align__(16) unsigned char merge_smem[];
     if (*reinterpret_cast<const volatile unsigned int*>(word + 1)) return;
     const int lu = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+    int32_t* const my_idx = reinterpret_cast<int32_t*>(merge_smem) + lu * L * K;
+    float* const my_sc = reinterpret_cast<float*>(merge_smem) + (MERGE_USERS + lu) * L * K;
     const int u = blockIdx.x * MERGE_USERS + lu;
     if (u >= n_users) return;                             // whole 16-lane groups leave together
     const unsigned gmask = 0xffffu << (threadIdx.x & 16);
     const float inv = 1.0f / operand_scale(word[0]);      // scores back to the caller's units: / s, twice
     const size_t base = static_cast<size_t>(u) * L * K;
     for (int i = l16; i < L * K; i += 16) {
-        s_idx[lu][i] = part_idx[base + i];
-        s_sc[lu][i] = part_score[base + i];
+        my_idx[i] = part_idx[base + i];
+        my_sc[i] = part_score[base + i];
     }
     __syncwarp(gmask);
     int pos = 0;                                          // head of this lane's list
@@ -546,8 +548,8 @@ topk_merge_kernel(const int32_t* __restrict__ part_idx, const float* __restrict_
         int idx = -1;
         float sc = -INFINITY;
         if (l16 < L && pos < K) {
-            idx = s_idx[lu][l16 * K + pos];
-            sc = idx >= 0 ? s_sc[lu][l16 * K + pos] : -INFINITY;
+            idx = my_idx[l16 * K + pos];
+            sc = idx >= 0 ? my_sc[l16 * K + pos] : -INFINITY;
         }
         int b_idx = idx, b_lane = idx >= 0 ? l16 : -1;
         float b_sc = sc;
@@ -563,6 +565,39 @@ topk_merge_kernel(const int32_t* __restrict__ part_idx, const float* __restrict_
             if (out_score) out_score[static_cast<size_t>(u) * K + k] = b_lane >= 0 ? b_sc * inv * inv : -INFINITY;
         }
         if (b_lane == l16) ++pos;
+    }
+}
+
+// The same merge with one thread per user walking the list heads in global memory: the cheaper one for up to
+// four lists (28 us against 81 us for the two lists per user of an unsharded evaluation), the slower one beyond
+// (93 us for ten lists) - the launcher picks by L.
+__global__ void __launch_bounds__(128)
+topk_merge_serial_kernel(const int32_t* __restrict__ part_idx, const float* __restrict__ part_score, int n_users, int L,
+                         int K, int32_t* __restrict__ out_idx, float* __restrict__ out_score,
+                         const unsigned int* __restrict__ word) {
+    if (*reinterpret_cast<const volatile unsigned int*>(word + 1)) return;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_users) return;
+    const float inv = 1.0f / operand_scale(word[0]);
+    int pos[4] = {0, 0, 0, 0};
+    const size_t base = static_cast<size_t>(u) * L * K;
+    for (int k = 0; k < K; ++k) {
+        int best = -1, best_idx = -1;
+        float best_sc = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (s >= L || pos[s] >= K) continue;
+            const size_t o = base + static_cast<size_t>(s) * K + pos[s];
+            const int idx = part_idx[o];
+            if (idx < 0) continue;
+            const float sc = part_score[o];
+            if (best < 0 || sc > best_sc || (sc == best_sc && idx < best_idx)) { best = s; best_sc = sc; best_idx = idx; }
+        }
+        out_idx[static_cast<size_t>(u) * K + k] = best_idx;
+        if (out_score) out_score[static_cast<size_t>(u) * K + k] = best >= 0 ? best_sc * inv * inv : -INFINITY;
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (s == best) ++pos[s];
     }
 }
 
@@ -680,8 +715,15 @@ int kgat_launch_score_topk_f16(const float* emb, int64_t emb_stride, int dim, co
         ws + p.u_blob, ws + p.i_blob, n_users, n_items, p.nkb, p.n_ks, p.S, mask_ptr, mask_items, K, pidx, pscore,
         err_word, word);
     KGAT_LAUNCH_CHECK();
-    topk_merge_kernel<<<(n_users + MERGE_USERS - 1) / MERGE_USERS, 16 * MERGE_USERS, 0, st>>>(pidx, pscore, n_users, p.S * N_GRP, K, topk_idx, topk_score,
-                                                             word);
+    const int n_lists = p.S * N_GRP;
+    if (n_lists <= 4) {
+        topk_merge_serial_kernel<<<(n_users + 127) / 128, 128, 0, st>>>(pidx, pscore, n_users, n_lists, K, topk_idx,
+                                                                      topk_score, word);
+    } else {
+        const size_t merge_bytes = static_cast<size_t>(2 * MERGE_USERS) * n_lists * K * sizeof(float);      // <= 32 KB
+        topk_merge_kernel<<<(n_users + MERGE_USERS - 1) / MERGE_USERS, 16 * MERGE_USERS, merge_bytes, st>>>(
+            pidx, pscore, n_users, n_lists, K, topk_idx, topk_score, word);
+    }
     KGAT_LAUNCH_CHECK();
     return kgat_launch_score_topk_umma(emb, emb_stride, dim, user_ids, n_users, item_ids, n_items, mask_ptr, mask_items, K,
                                        topk_idx, topk_score, reinterpret_cast<int*>(word + 1), st);

@@ -289,7 +289,8 @@ class Propagate(th.autograd.Function):
             st = _lib.stream_ptr()
             # peer exchange: every layer's dW2 is a view of one flat buffer that travels as one slot
             dw_flat = th.empty(w_off[-1], dtype=th.float32, device=dev) if peer is not None else None
-            side = _side_stream(dev) if (not plan.distributed and REDUCE_OVERLAP) else None
+            # (single GPU and the peer exchange; the NCCL exchange keeps everything on one stream)
+            side = _side_stream(dev) if (REDUCE_OVERLAP and (peer is not None or not plan.distributed)) else None
             keep = []            # partial buffers stay alive until the side stream has been joined
             for l in reversed(range(L)):
                 d_in, d_out = dims[l], dims[l + 1]
@@ -346,6 +347,8 @@ class Propagate(th.autograd.Function):
             if peer is not None:
                 # last phase: the dW2 of all layers (one slot per rank) and the entity gradient share a barrier
                 slots = peer.buf(("dW2",), (peer.world, w_off[-1]))
+                if side is not None:
+                    th.cuda.current_stream().wait_stream(side)      # the dW2 of every layer is complete
                 with _lib.record("peer_push_slot"):
                     _lib.check(lib.kgat_peer_push_slot(dw_flat.data_ptr(), w_off[-1], slots.data_ptr(), peer.ref, st),
                                "kgat_peer_push_slot")
