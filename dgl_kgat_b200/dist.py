@@ -396,6 +396,7 @@ class DistKGAT:
             floats = E + N * sum(dims[1:L]) + N * sum(dims[:L]) + N * dims[0] \
                 + self.world * sum(dims[l] * dims[l + 1] for l in range(L)) + 3 * int(max_batch) * sum(dims)
             self.peer = PeerArena(4 * floats + 256 * (2 * L + 8), self.device, group)
+            self.peer.max_batch = int(max_batch)          # rows of the loss-row table (ops.DistBprLoss)
         # cost model of the partition, per step (measured on B200s, Amazon-book shape, profiles/README.md): a rank's
         # kernel time is ~3 ns per owned row of dense work + ~3 ns per row and DESTINATION of its exchanged rows
         # (1.3 KB per row: one destination with the NVSwitch multicast, world - 1 with unicast pushes) + 0.29 ns per
@@ -527,8 +528,13 @@ class DistKGAT:
         self.poll_peers()
         m = self.model
         weights = [l.res_fc_2.weight for l in m.layers]
-        masks = list(drop_masks) if drop_masks is not None else [None] * len(weights)
-        return ops.propagate(self._plan, masks, False, m.entity_embed.weight, *weights)
+        if drop_masks is None:
+            # the full-size masks Model.gnn would draw (models.py:70): every rank draws the same ones from the same
+            # generator state, so the partitioned step drops the elements the single-GPU step drops
+            from .models import _dropout_mask
+            drop_masks = [_dropout_mask(l.mess_drop, self.part.n_nodes, l.res_fc_2.out_features, self.device)
+                          for l in m.layers]
+        return ops.propagate(self._plan, list(drop_masks), False, m.entity_embed.weight, *weights)
 
     def get_loss(self, embedding, src_ids, pos_dst_ids, neg_dst_ids):
         """BPR loss of models.py:170-178 on rows gathered from their owners; replicated value.  The

@@ -110,10 +110,31 @@ class GraphedDistCFStep(GraphedCFStep):
     that variant is EXPERIMENTAL (gain ~3 %, process-group teardown after capturing NCCL work was
     unreliable) and bench.py uses it only when KGAT_BENCH_GRAPH_DIST=1."""
 
-    def __init__(self, dk, batch_size, warmup=3):
-        self.dk, self.model = dk, dk.model
-        self._cap_w = self._seen_w = None           # the partitioned step refreshes the attention inside the graph
+    def __init__(self, dk, batch_size, warmup=3, refresh_attention=True):
+        """``refresh_attention=False``: the training loop of kgat.py, which refreshes the attention once per EPOCH
+        (:139-145) and runs every CF iteration of the epoch on those weights.  The graph then holds propagation,
+        loss and backward only; the weights of the own in-edges live in the arena (same address after every
+        refresh), the CSC layout of the out-edge weights is a buffer this object owns and re-fills after a
+        refresh (``_sync_weights``)."""
+        self.dk, self.model, self.refresh_attention = dk, dk.model, refresh_attention
+        self._cap_w = self._seen_w = None
+        self._cap_wcsc = self._seen_wcsc = None
+        if not refresh_attention:
+            dk.attention_weights()                  # barrier + CSC layout of the weights that are current now
+            self._cap_wcsc = self._seen_wcsc = dk._plan.w_csc
         self._capture(dk.model, batch_size, warmup)
+
+    def _sync_weights(self):
+        if self.refresh_attention:
+            return
+        dk = self.dk
+        dk.attention_weights()                      # no-op unless compute_attention() ran since the last call
+        cur = dk._plan.w_csc
+        if cur is not self._seen_wcsc:
+            if cur is not self._cap_wcsc:
+                self._cap_wcsc.copy_(cur)
+            self._seen_wcsc = cur
+        dk._plan.w_csc = self._cap_wcsc
 
     def __call__(self, src_ids, pos_ids, neg_ids):
         self.dk.poll_peers()                # a lost peer must surface as an error, not as corrupted gradients
@@ -123,7 +144,8 @@ class GraphedDistCFStep(GraphedCFStep):
         dk = self.dk
         for p in self.model.parameters():
             p.grad = None
-        dk.compute_attention()
+        if self.refresh_attention:
+            dk.compute_attention()
         emb = dk.gnn()
         loss = dk.get_loss(emb, *self.ids)
         loss.backward()

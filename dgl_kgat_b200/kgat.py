@@ -14,6 +14,11 @@ cap the phases for smoke runs; batches come from the device-resident sampler unl
 ``--host_sampler`` is given; the KG and CF iterations run as CUDA graphs (``graphed.py``) unless
 ``--eager``; Adam is one library launch per step (``optim.FusedAdam``); ``--save_every`` / ``--resume`` write and read
 checkpoints (the reference has none, kgat.py:190).
+
+Multi-GPU (the reference is single-GPU): launched as
+``python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P -m dgl_kgat_b200.kgat ...``
+the same loop runs with the attention refresh, the CF phase and the evaluation on the destination-partitioned graph
+(``dist.DistKGAT``); parameters stay bit-identical across ranks, rank 0 writes the logs and checkpoints.
 """
 from __future__ import annotations
 
@@ -70,6 +75,12 @@ def parse_args(argv=None):
         name, args.entity_embed_dim, args.gnn_num_layer, args.dropout_rate, args.lr,
         args.batch_size, args.batch_size_kg, int(args.use_attention), args.seed)
     args.save_dir = os.path.join(args.log_root, save_dir)
+    # under torchrun (one process per GPU) every rank but the first logs into its own sub-folder
+    args.rank, args.world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if args.world > 1:
+        args.gpu = int(os.environ.get("LOCAL_RANK", args.rank))
+        if args.rank > 0:
+            args.save_dir = os.path.join(args.save_dir, "rank%d" % args.rank)
     os.makedirs(args.save_dir, exist_ok=True)
     args.save_id = creat_log_id(args.save_dir)
     return args
@@ -86,14 +97,34 @@ def eval(model, g, train_user_dict, eval_user_dict, item_id_range, use_cuda, use
                                        K=20, use_cuda=use_cuda)
 
 
+def eval_dist(dk, train_user_dict, eval_user_dict, item_id_range, use_attention):
+    """eval() on the destination-partitioned graph: attention and propagation partitioned, the embedding rows
+    all-gathered, the eval users sharded over the ranks, three scalars all-reduced."""
+    with th.no_grad():
+        if use_attention:
+            dk.compute_attention()
+        emb = dk.full_embedding(dk.gnn())        # dropout follows model.training, as in the reference's eval()
+        return dk.calc_recall_ndcg(emb, train_user_dict, eval_user_dict, item_id_range, 20)
+
+
 def train_eval(args):
-    logging_config(folder=args.save_dir, name='log{:d}'.format(args.save_id), no_console=False)
+    rank, world = getattr(args, "rank", 0), getattr(args, "world", 1)
+    logging_config(folder=args.save_dir, name='log{:d}'.format(args.save_id), no_console=rank > 0)
     logging.info(args)
     if not (args.gpu >= 0 and th.cuda.is_available()):
         raise RuntimeError("the KGAT hot path needs a B200 GPU; there is no CPU fallback")
     th.cuda.set_device(args.gpu)
     dev = th.device("cuda", args.gpu)
     th.manual_seed(args.seed)
+    if world > 1:
+        # Multi-GPU (python -m torch.distributed.run ... -m dgl_kgat_b200.kgat ...): the CF phase, the attention refresh
+        # and the evaluation run on the destination-partitioned graph (dist.DistKGAT: one process per GPU, exchange
+        # over NVLink peer memory); parameters and optimizer state are replicated and stay bit-identical because
+        # every rank draws the same batches and masks from the same seed and every gradient is complete and
+        # identical on every rank.  The TransR phase is replicated.
+        import torch.distributed as tdist
+        if not tdist.is_initialized():
+            tdist.init_process_group("nccl", device_id=dev)
 
     if args.synthetic is not None:
         dataset = DataLoader.from_synthetic(args.synthetic, seed=args.seed)
@@ -136,6 +167,15 @@ def train_eval(args):
     item_id_range = th.as_tensor(dataset.item_id_range, dtype=th.long, device=dev)
     as_ids = lambda a: th.as_tensor(a, dtype=th.long).to(dev, non_blocking=True)
 
+    dk_train = dk_test = None
+    if world > 1:
+        from .dist import DistKGAT
+        N, R = dataset.n_KG_entity, dataset.n_KG_relation
+        dk_train = DistKGAT(model, N, train_g.triplets, R, dev, max_batch=args.batch_size)
+        dk_test = DistKGAT(model, N, test_g.triplets, R, dev, max_batch=args.batch_size)
+        logging.info("rank %d of %d owns rows [%d, %d) of the train graph (%s exchange)", rank, world,
+                     dk_train.part.r0, dk_train.part.r1, dk_train.exchange)
+
     kg_graph = cf_graph = None
     for epoch in range(start_epoch, args.max_epoch + 1):
         # phase 1: TransR on the KG (kgat.py:116-136)
@@ -167,9 +207,12 @@ def train_eval(args):
         # phase 2: attention refresh (kgat.py:139-145)
         if args.use_attention:
             t0 = time()
-            with th.no_grad():
-                A_w = model.compute_attention(train_g)
-            train_g.edata['w'] = A_w
+            if dk_train is not None:
+                dk_train.compute_attention()
+            else:
+                with th.no_grad():
+                    A_w = model.compute_attention(train_g)
+                train_g.edata['w'] = A_w
             th.cuda.synchronize()
             logging.info("Time for attention: {:.3f}s".format(time() - t0))
 
@@ -181,9 +224,15 @@ def train_eval(args):
             it += 1
             if not args.eager and len(user_ids) == args.batch_size:
                 if cf_graph is None:
-                    from .graphed import GraphedCFStep
-                    cf_graph = GraphedCFStep(model, train_g, args.batch_size, refresh_attention=False)
+                    from .graphed import GraphedCFStep, GraphedDistCFStep
+                    cf_graph = GraphedCFStep(model, train_g, args.batch_size, refresh_attention=False) \
+                        if dk_train is None else GraphedDistCFStep(dk_train, args.batch_size, refresh_attention=False)
                 loss = cf_graph(user_ids, item_pos_ids, item_neg_ids)
+            elif dk_train is not None:
+                embedding = dk_train.gnn()
+                loss = dk_train.get_loss(embedding, as_ids(user_ids), as_ids(item_pos_ids), as_ids(item_neg_ids))
+                loss.backward()
+                loss, embedding = loss.detach(), None
             else:
                 embedding = model.gnn(train_g, train_g.ndata['id'])
                 loss = model.get_loss(embedding, as_ids(user_ids), as_ids(item_pos_ids), as_ids(item_neg_ids))
@@ -198,23 +247,31 @@ def train_eval(args):
 
         if epoch % args.evaluate_every == 0:                 # kgat.py:171-196
             t0 = time()
-            val_recall, val_ndcg = eval(model, train_g, dataset.train_user_dict, dataset.valid_user_dict,
-                                        item_id_range, True, args.use_attention)
+            if dk_train is not None:
+                val_recall, val_ndcg = eval_dist(dk_train, dataset.train_user_dict, dataset.valid_user_dict,
+                                                 dataset.item_id_range, args.use_attention)
+            else:
+                val_recall, val_ndcg = eval(model, train_g, dataset.train_user_dict, dataset.valid_user_dict,
+                                            item_id_range, True, args.use_attention)
             info = "Epoch{}, [{:.1f}s] val recall:{:.5f}, val ndcg:{:.5f}".format(epoch, time() - t0, val_recall, val_ndcg)
             is_best = val_recall > best_recall
             valid_log.log(epoch=epoch, recall=val_recall, ndcg=val_ndcg, is_best=int(is_best))
             t0 = time()
             # the reference evaluates the test users in both branches (kgat.py:185,193) but keeps the numbers it
             # reports at the end only when the validation recall improved (kgat.py:181-187)
-            cur_recall, cur_ndcg = eval(model, test_g, dataset.train_valid_user_dict, dataset.test_user_dict,
-                                        item_id_range, True, args.use_attention)
+            if dk_test is not None:
+                cur_recall, cur_ndcg = eval_dist(dk_test, dataset.train_valid_user_dict, dataset.test_user_dict,
+                                                 dataset.item_id_range, args.use_attention)
+            else:
+                cur_recall, cur_ndcg = eval(model, test_g, dataset.train_valid_user_dict, dataset.test_user_dict,
+                                            item_id_range, True, args.use_attention)
             if is_best:
                 best_recall, best_epoch = val_recall, epoch
                 test_recall, test_ndcg = cur_recall, cur_ndcg
                 test_log.log(epoch=epoch, recall=test_recall, ndcg=test_ndcg)
             info += "\t[{:.1f}s] test recall:{:.5f}, test ndcg:{:.5f}".format(time() - t0, cur_recall, cur_ndcg)
             logging.info(info)
-        if args.save_every > 0 and epoch % args.save_every == 0:
+        if args.save_every > 0 and epoch % args.save_every == 0 and rank == 0:
             path = os.path.join(args.save_dir, 'ckpt{:d}.pt'.format(args.save_id))
             th.save({'state_dict': model.state_dict(), 'optimizer': optimizer.state_dict(), 'epoch': epoch,
                      'best_epoch': best_epoch, 'best_recall': best_recall, 'test_recall': test_recall,
@@ -224,6 +281,10 @@ def train_eval(args):
 
     logging.info("Final test recall:{:.5f}, test ndcg:{:.5f}, best epoch:{}".format(test_recall, test_ndcg, best_epoch))
     train_eval.last_model = model            # for callers (and tests) that want the trained parameters
+    if dk_train is not None:
+        cf_graph = None
+        dk_train.close()
+        dk_test.close()
     return test_recall, test_ndcg, best_epoch
 
 

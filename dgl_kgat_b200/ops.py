@@ -467,7 +467,14 @@ class DistBprLoss(th.autograd.Function):
         cat = th.cat(node_ids)
         if peer is not None:
             # every owner stores its rows into the table of every rank (NVLink stores), then one barrier
-            table = peer.buf(("loss_rows", B, emb.shape[1]), (3 * B, emb.shape[1]))
+            # ONE table sized for the largest batch (DistKGAT(max_batch=...)): the partial last batch of an epoch
+            # takes a prefix of it instead of a second arena buffer
+            full = peer._bufs.get(("loss_rows", emb.shape[1]))
+            cap = full.shape[0] // 3 if full is not None else max(int(getattr(peer, "max_batch", 0)), B)
+            if B > cap:
+                raise _lib.KgatError("batch of %d rows exceeds the %d the peer arena was sized for (DistKGAT max_batch)"
+                                     % (B, cap))
+            table = peer.buf(("loss_rows", emb.shape[1]), (3 * cap, emb.shape[1]))[: 3 * B]
             with th.cuda.device(dev):
                 with _lib.record("peer_gather_rows_push"):
                     _lib.check(_lib.load().kgat_peer_gather_rows_push(

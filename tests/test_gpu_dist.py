@@ -122,3 +122,60 @@ def test_multi_gpu_step_matches_single_gpu(world):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert dict(ret) == {k: "ok" for k in range(world)}
+
+
+# ------------------------------------------------------------------------------- the CLI under torchrun semantics
+def _cli_worker(rank, world, port, log_root, ret):
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank),
+                       "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank)})
+    try:
+        from dgl_kgat_b200 import kgat
+        args = kgat.parse_args(_CLI_ARGS + ["--log_root", log_root])
+        assert (args.rank, args.world, args.gpu) == (rank, world, rank)
+        res = kgat.train_eval(args)
+        sd = {k: v.detach().cpu() for k, v in kgat.train_eval.last_model.state_dict().items()}
+        csv = open(os.path.join(args.save_dir, "valid%d.csv" % args.save_id)).read()
+        ret[rank] = (res, sd, csv)
+    except Exception as e:
+        ret[rank] = "FAIL: %r" % (e,)
+        raise
+    finally:
+        if tdist.is_initialized():
+            tdist.destroy_process_group()
+
+
+_CLI_ARGS = ["--synthetic", "tiny", "--max_epoch", "2", "--batch_size", "4096", "--batch_size_kg", "1024",
+             "--print_every", "1000"]          # dropout 0.1 (default): every rank must draw the same masks
+
+
+def test_cli_on_two_gpus_follows_the_single_gpu_run(tmp_path):
+    """python -m torch.distributed.run ... -m dgl_kgat_b200.kgat: two full epochs of the reference loop (kgat.py:114-196)
+    with the CF phase, the attention refresh and the evaluation on the destination-partitioned graph.  Parameters
+    stay bit-identical ACROSS ranks (same batches, same masks, complete identical gradients on every rank) and
+    follow the single-GPU run to re-association noise: same validation metrics to 1e-3, parameters to 1e-4."""
+    if th.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs, the box has %d" % th.cuda.device_count())
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cli_worker, args=(2, _free_port(), str(tmp_path / "dist"), ret), nprocs=2, join=True)
+    assert all(not isinstance(ret[k], str) for k in range(2)), dict(ret)
+    (res0, sd0, csv0), (res1, sd1, _) = ret[0], ret[1]
+    for k in sd0:
+        assert th.equal(sd0[k], sd1[k]), "ranks diverged: " + k
+    assert res0 == res1
+    # the single-GPU run of the same command
+    from dgl_kgat_b200 import kgat
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        os.environ.pop(k, None)
+    th.cuda.set_device(0)
+    args = kgat.parse_args(_CLI_ARGS + ["--log_root", str(tmp_path / "single")])
+    res = kgat.train_eval(args)
+    sd = {k: v.detach().cpu() for k, v in kgat.train_eval.last_model.state_dict().items()}
+    rows = lambda txt: [[float(x) for x in line.split(",")] for line in txt.strip().splitlines()[1:]]
+    csv = open(os.path.join(args.save_dir, "valid%d.csv" % args.save_id)).read()
+    for a, b in zip(rows(csv0), rows(csv)):
+        assert a[0] == b[0] and abs(a[1] - b[1]) < 1e-3 and abs(a[2] - b[2]) < 1e-3, (a, b)
+    for k in sd:
+        err = (sd0[k] - sd[k]).abs().max().item() / sd[k].abs().max().item()
+        assert err < 1e-4, (k, err)
+    assert abs(res0[0] - res[0]) < 1e-3 and abs(res0[1] - res[1]) < 1e-3
