@@ -202,7 +202,8 @@ def train_eval(args):
             total.add_(loss.detach())               # summed on the device: no host sync per iteration
             if it % args.print_every == 0 or it == 1:
                 logging.info("Epoch {:04d} Iter {:04d} | Loss {:.4f} ".format(epoch, it, total.item() / it))
-        logging.info('Time for KGE: {:.1f}s, loss {:.4f}'.format(time() - t0, total.item() / max(it, 1)))
+        mean_loss = total.item() / max(it, 1)            # the read-back waits for the phase: the time below is real
+        logging.info('Time for KGE: {:.1f}s, loss {:.4f}'.format(time() - t0, mean_loss))
 
         # phase 2: attention refresh (kgat.py:139-145)
         if args.use_attention:
@@ -243,7 +244,8 @@ def train_eval(args):
             total.add_(loss.detach())               # summed on the device: no host sync per iteration
             if it % args.print_every == 0 or it == 1:
                 logging.info("Epoch {:04d} Iter {:04d} | Loss {:.4f} ".format(epoch, it, total.item() / it))
-        logging.info('Time for GNN: {:.1f}s, loss {:.4f}'.format(time() - t0, total.item() / max(it, 1)))
+        mean_loss = total.item() / max(it, 1)
+        logging.info('Time for GNN: {:.2f}s, loss {:.4f}'.format(time() - t0, mean_loss))
 
         if epoch % args.evaluate_every == 0:                 # kgat.py:171-196
             t0 = time()
