@@ -41,14 +41,12 @@ def _single_gpu_reference(m, ck, ids, dev):
     return w, emb.detach(), loss.detach(), grads
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, skew=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["KGAT_PEER_TIMEOUT_MS"] = "15000"
-    # The partitioned (PUSH) backward kernels still use the fp32 FFMA tile GEMMs while the single-GPU path
-    # defaults to the tensor-core ones; this test is about the exchange, so both sides are pinned to the same
-    # arithmetic (the tensor-core GEMMs are held against the fp64 oracle in test_gpu_parity.py).
-    os.environ["KGAT_BWD_EPILOGUE"] = "ffma"
+    # default arithmetic on both sides: the partitioned (PUSH) kernels run the same tensor-core tile GEMMs as the
+    # single-GPU ones
     th.cuda.set_device(0)                       # every rank on the same GPU
     dev = th.device("cuda", 0)
     tdist.init_process_group("gloo", rank=rank, world_size=world)
@@ -57,7 +55,7 @@ def _worker(rank, world, port, ret):
         from dgl_kgat_b200.dist import DistKGAT
         from dgl_kgat_b200.graphed import GraphedDistCFStep
         from dgl_kgat_b200.synth import synth_ckg
-        ck = synth_ckg("tiny")
+        ck = synth_ckg("tiny", skew=skew)       # skew: rows above KGAT_SPLIT_ROW edges inside the partitioned kernels
         N, R, trip = ck.cfg.n_nodes, ck.cfg.n_relations, ck.triplets
         th.manual_seed(1234)
         m = models.Model(True, 64, "kgat", 3, 64, 0.0, n_entities=N, n_relations=R, relation_dim=64,
@@ -111,6 +109,35 @@ def _worker(rank, world, port, ret):
                 assert th.equal(p.grad, eager[k]), "graphed step differs from the eager step: " + k
         assert dk.peer.error() == 0, "a peer barrier timed out"
         step = None
+
+        # the training-loop variant (kgat.py:139-165): attention refreshed per EPOCH outside the graph, the graph
+        # holds propagation + loss + backward and must follow every refresh
+        m.zero_grad(set_to_none=True)
+        dk.compute_attention()
+        step2 = GraphedDistCFStep(dk, B, refresh_attention=False)
+        step2(*ids)
+        th.cuda.synchronize()
+        for k, p in m.named_parameters():
+            if k in eager:
+                assert th.equal(p.grad, eager[k]), "graphed step without refresh differs: " + k
+        with th.no_grad():
+            m.W_R.mul_(1.05)                    # the next epoch's attention is different
+        dk.compute_attention()
+        loss5 = step2(*ids)
+        th.cuda.synchronize()
+        graphed = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        loss5_val = loss5.item()
+        m.zero_grad(set_to_none=True)
+        emb6 = dk.gnn()
+        loss6 = dk.get_loss(emb6, *ids)
+        loss6.backward()
+        assert loss6.item() == loss5_val and loss5_val != loss2_val
+        for k, p in m.named_parameters():
+            if k in graphed:
+                assert th.equal(p.grad, graphed[k]), "graphed step did not follow the attention refresh: " + k
+        assert dk.peer.error() == 0, "a peer barrier timed out"
+        del emb6, loss6
+        step2 = None
         dk.close()
         ret[rank] = "ok"
     except Exception as e:
@@ -120,11 +147,11 @@ def _worker(rank, world, port, ret):
         tdist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [1, 2])
-def test_peer_exchange_on_one_gpu(world):
+@pytest.mark.parametrize("world,skew", [(1, False), (2, False), (2, True)])
+def test_peer_exchange_on_one_gpu(world, skew):
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), ret, skew), nprocs=world, join=True)
     assert dict(ret) == {r: "ok" for r in range(world)}
 
 
