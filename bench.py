@@ -641,6 +641,14 @@ def run_ours(args):
         roofline["frac_of_nominal_8TBps"] = ach / 8000.0
         roofline["step_frac_of_nominal_8TBps"] = roofline["step_frac"] * peak / 8000.0
         roofline["step_c_model_GB"] = (E * (12 + 6 * 8) + N * (256 + 2 * 2 * 640)) / 1e9
+        # The physical bound of the aggregation kernels at shapes whose tables fit the 126 MB L2 is the L2 -> SM
+        # path, not HBM: ~6300 B/clk chip-wide (B300_MICROARCH.md, LTS throughput cap; not re-measured on B200) =
+        # 12.4 TB/s at 1965 MHz.  E-model bytes of each gather kernel against that cap:
+        l2_cap = 6300.0 * 1965e6 / 1e9
+        roofline["l2_gather"] = {
+            "cap_GBps": l2_cap, "cap_source": "6300 B/clk LTS cap of the micro-architecture notes x 1965 MHz (not re-measured)",
+            "frac": {k: round(alg[k] / (ms * 1e-3) / 1e9 / l2_cap, 3) for k, ms in kernel_ms.items()
+                     if alg.get(k) is not None and k.split("_")[0] in ("layer", "csc", "input") and not k.startswith("layer_bwd")}}
         if distributed:
             roofline["scope"] = "rank 0 (%d of %d rows, %d of %d in-edges); step_frac is whole-job" % (n_loc, N, e_loc, E)
 
