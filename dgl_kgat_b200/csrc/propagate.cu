@@ -262,7 +262,9 @@ layer_fwd_kernel(const int32_t* __restrict__ csr_ptr, const int32_t* __restrict_
         bool is_long = false;
         if (row < row_end) {
             const int beg = __ldg(csr_ptr + row), end = __ldg(csr_ptr + row + 1);
-            if (end - beg > LONG_ROW) is_long = true;
+            // with the pre-pass every row above SPLIT_ROW edges is already gathered; without it rows above LONG_ROW
+            // go to the whole CTA
+            if (end - beg > (split_done ? SPLIT_ROW : LONG_ROW)) is_long = true;
             else finish_row(row, rl, gather_row<DIN>(csr_src, w_csr, beg, end, h_in, lane));
         } else if (lane < LPI) {
             *reinterpret_cast<float4*>(sZ + rl * LDZ + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -760,14 +762,15 @@ __device__ __forceinline__ float4 gather_block_rows(const int32_t* __restrict__ 
     const int row = first + warp;
     int beg = 0, end = 0;
     if (row < row_end) { beg = __ldg(csc_ptr + row); end = __ldg(csc_ptr + row + 1); }
-    const bool is_long = end - beg > LONG_ROW;
+    const int long_row = pre ? SPLIT_ROW : LONG_ROW;           // with the pre-pass every row above SPLIT_ROW is done
+    const bool is_long = end - beg > long_row;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (__syncthreads_or(is_long ? 1 : 0)) {
         for (int w = 0; w < WARPS; ++w) {                       // CTA-uniform: every thread re-reads the bounds
             const int r = first + w;
             if (r >= row_end) break;
             const int b = __ldg(csc_ptr + r), e = __ldg(csc_ptr + r + 1);
-            if (e - b <= LONG_ROW) continue;
+            if (e - b <= long_row) continue;
             if (pre && e - b > SPLIT_ROW) {      // gathered by the pre-pass (split_prepass) into row r of `pre`
                 if (w == warp) g = *reinterpret_cast<const float4*>(pre + static_cast<size_t>(r) * D + (lane % (D / 4)) * 4);
                 continue;
