@@ -789,7 +789,7 @@ __device__ __forceinline__ float4 gather_block_rows(const int32_t* __restrict__ 
 // persistent dW2 accumulators) in lockstep with the tile GEMMs - 0.235 ms for the 64 x 64 layer where this
 // kernel plus the dense remainder take less (measured, profiles/README.md).
 template <int D>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 8)      // 32 registers: 8 CTAs per SM (at 40 the kernel ran 10 % slower)
 csc_gather_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
                   const float* __restrict__ w_csc, int row_begin, int row_end, const float* __restrict__ add,
                   const float* __restrict__ feat, float* __restrict__ out, int split_done) {
@@ -811,7 +811,7 @@ csc_gather_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict
 
 // d_entity[v] = d_concat[v, in_off:+D] + dx_direct[v] + sum_{k in CSC row v} w[k] * dh_nb[dst[k]]
 template <int D, bool PUSH>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 8)
 input_bwd_kernel(const int32_t* __restrict__ csc_ptr, const int32_t* __restrict__ csc_dst,
                  const float* __restrict__ w_csc, int row_begin, int row_end,
                  const float* __restrict__ d_concat, const int32_t* __restrict__ dc_slot, int64_t cstride,
