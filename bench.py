@@ -20,8 +20,16 @@ Prints ONE JSON line (rank 0).
             region, against the measured HBM copy bandwidth of MEASURED_PEAKS.json.
  cpu_baseline  the oracle port (oracle/kgat_ref.py = the reference's models.py op sequence on
             pure-torch message passing) on the host cores, bounded sample.
- --impl reference   times that CPU port alone, same metric/config, and prints the same line.
+ --impl reference   times that CPU port alone, same metric/config, and prints the same line (the steps it timed).
 Multi-GPU (torchrun): destination-partitioned graph, strong scaling (fixed graph).
+Further keys of the line: `roofline.l2_gather` (E-model bytes of the gather kernels against the L2 -> SM
+throughput cap - the physical bound while the tables fit L2), `roofline.measured_dram_frac`, `roofline_eval`
+(tensor-pipe fraction of the scoring GEMM), `kernels` / `halves` (per-kernel CUDA events of the eager pass),
+`skew` (N = 1: the same step on the Zipf-skewed graph of the same size), and at N > 1 `ranks` (rows, edges,
+kernel time and barrier wait of every rank), `dist_parity` (the partitioned step against the single-GPU step on
+rank 0, outside the timed region), `scale_10x` (BASELINE configs[4]: the 10x graph, step and user-sharded
+evaluation), `nvlink` (byte counters when nvidia-smi has them, else the derived bytes of the pushed buffers).
+`--skew` runs the whole bench on the skewed graph (diagnostic, not the headline config).
 """
 from __future__ import annotations
 

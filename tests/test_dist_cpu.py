@@ -150,3 +150,21 @@ def test_distributed_algorithm_world2_gloo():
     port = _free_port()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_partition_rows_blended_minimises_the_largest_rank_cost():
+    """dist.partition_rows_blended: contiguous ranges whose LARGEST cost is minimal (bisection + greedy packing) -
+    valid boundaries, never worse than equal-row or equal-edge cuts, exact on a case with a known optimum."""
+    from dgl_kgat_b200.dist import partition_rows_blended
+    rng = np.random.default_rng(0)
+    cost = np.concatenate([np.full(700, 4.0), rng.integers(20, 60, 300).astype(np.float64)])   # cheap user rows, heavy entity rows
+    for parts in (2, 4, 8):
+        b = partition_rows_blended(cost, parts)
+        assert b[0] == 0 and b[-1] == len(cost) and np.all(np.diff(b) >= 0) and len(b) == parts + 1
+        worst = max(cost[b[k]: b[k + 1]].sum() for k in range(parts))
+        equal_rows = np.linspace(0, len(cost), parts + 1).astype(int)
+        assert worst <= max(cost[equal_rows[k]: equal_rows[k + 1]].sum() for k in range(parts)) + 1e-9
+        assert worst >= cost.sum() / parts - 1e-9                      # cannot beat the average
+        assert worst <= cost.sum() / parts + cost.max() + 1e-9         # greedy packing overshoots by at most one row
+    assert partition_rows_blended(np.array([5.0, 1.0, 1.0, 1.0, 1.0, 1.0]), 2).tolist() == [0, 1, 6]
+    assert partition_rows_blended(np.ones(5), 1).tolist() == [0, 5]
