@@ -99,8 +99,9 @@ __device__ __forceinline__ float4 gather_row_cta(const int32_t* __restrict__ idx
     return t;
 }
 
-// Rows with more than SPLIT_ROW edges (split.cuh; the hottest entities of a power-law graph: 10^5..10^6 edges)
-// are gathered by a PRE-PASS in front of the kernel that owns the row: one CTA per segment of <= SPLIT_SEG
+// Rows with more than SPLIT_ROW edges (split.cuh: a few hundred edges already - hot rows come in clusters of
+// neighbouring ids and would keep one CTA busy long after the grid has drained - up to the 10^6 of the hottest
+// entity of a power-law graph) are gathered by a PRE-PASS in front of the kernel that owns the row: one CTA per segment of <= SPLIT_SEG
 // edges writes a partial sum, one warp per split row adds the partials in segment order into the row of `out`
 // where the main kernel picks the total up instead of walking the row (fixed order: deterministic).
 template <int W>
