@@ -122,6 +122,9 @@ SIGNATURES = {
                                      C.c_void_p]),
     "kgat_score_topk": (C.c_int, [c_f32p, C.c_int64, C.c_int, c_i32p, C.c_int64, c_i32p, C.c_int64, c_i32p, c_i32p,
                                   C.c_int, c_i32p, c_f32p, C.c_void_p]),
+    "kgat_recall_ndcg_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "kgat_recall_ndcg": (C.c_int, [c_i32p, C.c_int64, C.c_int, c_i32p, c_i32p, c_i32p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                   C.c_void_p]),
     "kgat_score_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "kgat_score_topk_ws": (C.c_int, [c_f32p, C.c_int64, C.c_int, c_i32p, C.c_int64, c_i32p, C.c_int64, c_i32p, c_i32p,
                                      C.c_int, c_i32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -160,6 +160,102 @@ static int eval_impl() {
 }
 static bool eval_use_umma() { return eval_impl() != 0; }
 
+// ------------------------------------------------------------------------------------------------
+// Recall@K / NDCG@K from the top-K lists (reference metric.py:5-31, 56-63), fp64 like the numpy helpers.
+//   hits[k]  = topk[u, k] is one of the user's held-out items       (binary search in the sorted positives)
+//   recall_u = sum(hits) / len(pos)            (len(pos) counts duplicates, as len(test_user_dict[u]) does)
+//   ndcg_u   = DCG(hits) / DCG(sorted hits),   DCG(r) = sum_k r[k] / log2(k + 2)             (method 1)
+// One thread per user, block sums in a fixed tree order, block partials added in order by the last launch:
+// bit-identical from run to run.
+// ------------------------------------------------------------------------------------------------
+namespace kgat {
+namespace {
+
+constexpr int METRIC_THREADS = 256;
+
+__global__ void __launch_bounds__(METRIC_THREADS)
+recall_ndcg_kernel(const int32_t* __restrict__ topk, int64_t n_users, int K, const int32_t* __restrict__ pos_ptr,
+                   const int32_t* __restrict__ pos_items, const int32_t* __restrict__ pos_len,
+                   double* __restrict__ partial) {
+    __shared__ double s_r[METRIC_THREADS], s_n[METRIC_THREADS];
+    const int64_t u = blockIdx.x * static_cast<int64_t>(METRIC_THREADS) + threadIdx.x;
+    double rec = 0.0, ndcg = 0.0;
+    if (u < n_users) {
+        const int beg = pos_ptr[u], end = pos_ptr[u + 1];
+        int n_hit = 0;
+        double dcg = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const int item = topk[u * K + k];
+            int lo = beg, hi = end;                     // first position with pos_items[p] >= item
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (pos_items[mid] < item) lo = mid + 1; else hi = mid;
+            }
+            if (item >= 0 && lo < end && pos_items[lo] == item) {
+                ++n_hit;
+                dcg += 1.0 / log2(static_cast<double>(k + 2));
+            }
+        }
+        double ideal = 0.0;
+        for (int k = 0; k < n_hit; ++k) ideal += 1.0 / log2(static_cast<double>(k + 2));
+        const int len = pos_len[u];
+        rec = len > 0 ? static_cast<double>(n_hit) / static_cast<double>(len) : 0.0;
+        ndcg = ideal > 0.0 ? dcg / ideal : 0.0;
+    }
+    s_r[threadIdx.x] = rec;
+    s_n[threadIdx.x] = ndcg;
+    __syncthreads();
+    for (int o = METRIC_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            s_r[threadIdx.x] += s_r[threadIdx.x + o];
+            s_n[threadIdx.x] += s_n[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = s_r[0];
+        partial[2 * blockIdx.x + 1] = s_n[0];
+    }
+}
+
+__global__ void recall_ndcg_finish_kernel(const double* __restrict__ partial, int n_blocks, int64_t n_users,
+                                          double* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double r = 0.0, n = 0.0;
+    for (int b = 0; b < n_blocks; ++b) { r += partial[2 * b]; n += partial[2 * b + 1]; }
+    out[0] = n_users > 0 ? r / static_cast<double>(n_users) : 0.0;
+    out[1] = n_users > 0 ? n / static_cast<double>(n_users) : 0.0;
+}
+
+}  // namespace
+}  // namespace kgat
+
+extern "C" size_t kgat_recall_ndcg_workspace_bytes(int64_t n_users) {
+    if (n_users <= 0) return 16;
+    return static_cast<size_t>((n_users + kgat::METRIC_THREADS - 1) / kgat::METRIC_THREADS) * 2 * sizeof(double);
+}
+
+extern "C" int kgat_recall_ndcg(const int32_t* topk_idx, int64_t n_users, int K, const int32_t* pos_ptr,
+                                const int32_t* pos_items, const int32_t* pos_len, double* out_recall_ndcg,
+                                void* workspace, size_t workspace_bytes, kgat_stream_t stream) {
+    KGAT_REQUIRE(out_recall_ndcg && n_users >= 0 && n_users < (int64_t(1) << 31) && K > 0);
+    cudaStream_t st = as_stream(stream);
+    if (n_users == 0) {
+        KGAT_CUDA(cudaMemsetAsync(out_recall_ndcg, 0, 2 * sizeof(double), st));
+        return KGAT_OK;
+    }
+    KGAT_REQUIRE(topk_idx && pos_ptr && pos_len && workspace);
+    if (workspace_bytes < kgat_recall_ndcg_workspace_bytes(n_users)) return KGAT_ERR_WORKSPACE;
+    const int blocks = static_cast<int>((n_users + kgat::METRIC_THREADS - 1) / kgat::METRIC_THREADS);
+    double* partial = static_cast<double*>(workspace);
+    kgat::recall_ndcg_kernel<<<blocks, kgat::METRIC_THREADS, 0, st>>>(topk_idx, n_users, K, pos_ptr, pos_items, pos_len,
+                                                                    partial);
+    KGAT_LAUNCH_CHECK();
+    kgat::recall_ndcg_finish_kernel<<<1, 32, 0, st>>>(partial, blocks, n_users, out_recall_ndcg);
+    KGAT_LAUNCH_CHECK();
+    return KGAT_OK;
+}
+
 extern "C" size_t kgat_score_topk_workspace_bytes(int64_t n_users, int64_t n_items, int dim, int K) {
     if (n_users <= 0 || n_items <= 0 || !kgat_score_topk_f16_supported(dim, K)) return 0;
     return kgat_score_topk_f16_workspace(n_users, n_items, dim, K);

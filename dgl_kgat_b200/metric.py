@@ -81,11 +81,16 @@ class EvalPlan:
         return self._dev[key]
 
     def device_positives(self, device):
-        """(sorted positive keys int64, positives per user float64) on the device."""
+        """(pos_ptr, pos_items, pos_len) int32 on the device: per eval user the held-out items as ascending unique
+        positions into the item range, and len(test_user_dict[u]) (duplicates counted, metric.py:60)."""
         key = "pos:" + str(device)
         if key not in self._dev:
-            self._dev[key] = (th.from_numpy(self.pos_keys).to(device),
-                              th.from_numpy(self.pos_len.astype(np.float64)).to(device))
+            rows = self.pos_keys // max(self.n_items, 1)
+            ptr = np.zeros(self.n_users + 1, dtype=np.int64)
+            np.cumsum(np.bincount(rows, minlength=self.n_users), out=ptr[1:])
+            items = (self.pos_keys % max(self.n_items, 1)).astype(np.int32)      # keys are sorted: ascending per user
+            self._dev[key] = tuple(th.from_numpy(np.ascontiguousarray(a)).to(device)
+                                   for a in (ptr.astype(np.int32), items, self.pos_len.astype(np.int32)))
         return self._dev[key]
 
 
@@ -120,24 +125,23 @@ def metrics_from_topk(topk: np.ndarray, plan: EvalPlan, K: int):
 
 
 def metrics_from_topk_device(topk: th.Tensor, plan: EvalPlan, K: int):
-    """Same arithmetic as :func:`metrics_from_topk`, on the device in float64 (hit matching by binary
-    search in the sorted positive keys); only the two scalars travel to the host."""
+    """Same arithmetic as :func:`metrics_from_topk` in one library call on the device (``kgat_recall_ndcg``: hit
+    matching by binary search in the user's sorted positives, fp64, fixed-order sums); only the two scalars travel
+    to the host."""
+    from . import _lib
     dev = topk.device
-    pos_keys, pos_len = plan.device_positives(dev)
+    pos_ptr, pos_items, pos_len = plan.device_positives(dev)
     n = plan.n_users
-    keys = th.arange(n, dtype=th.int64, device=dev).unsqueeze(1) * plan.n_items + topk.to(th.int64)
-    if pos_keys.numel():
-        idx = th.searchsorted(pos_keys, keys.reshape(-1)).clamp_(max=pos_keys.numel() - 1)
-        hits = (pos_keys[idx] == keys.reshape(-1)).reshape(n, K).to(th.float64)          # metric.py:56-59
-    else:
-        hits = th.zeros(n, K, dtype=th.float64, device=dev)
-    n_hit = hits.sum(1)
-    recall_u = th.where(pos_len > 0, n_hit / pos_len.clamp(min=1.0), th.zeros_like(n_hit))  # metric.py:60-61
-    disc = 1.0 / th.log2(th.arange(2, K + 2, dtype=th.float64, device=dev))
-    dcg = (hits * disc).sum(1)
-    ideal = th.cat([th.zeros(1, dtype=th.float64, device=dev), th.cumsum(disc, 0)])[n_hit.to(th.int64)]
-    ndcg_u = th.where(ideal > 0, dcg / th.where(ideal > 0, ideal, th.ones_like(ideal)), th.zeros_like(dcg))
-    out = th.stack([recall_u.sum(), ndcg_u.sum()]) / n
+    lib = _lib.load()
+    topk = topk.to(th.int32).contiguous()
+    out = th.empty(2, dtype=th.float64, device=dev)
+    ws_bytes = lib.kgat_recall_ndcg_workspace_bytes(n)
+    ws = th.empty(max(ws_bytes, 16), dtype=th.uint8, device=dev)
+    with th.cuda.device(dev):
+        with _lib.record("recall_ndcg", 2):
+            _lib.check(lib.kgat_recall_ndcg(topk.data_ptr(), n, K, pos_ptr.data_ptr(), pos_items.data_ptr(),
+                                            pos_len.data_ptr(), out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                            _lib.stream_ptr()), "kgat_recall_ndcg")
     rec, ndcg = out.tolist()
     return rec, ndcg
 

@@ -321,6 +321,17 @@ KGAT_API int kgat_score_topk(const float* emb, int64_t emb_stride, int dim,
                     const int32_t* mask_ptr, const int32_t* mask_items,
                     int K, int32_t* topk_idx, float* topk_score, kgat_stream_t stream);
 
+/* (5m) Recall@K / NDCG@K of the top-K lists -- replaces the per-user hit matching and the helpers of
+ *      metric.py:5-31, :56-63 (recall = hits / len(pos); NDCG method 1 with the IDCG of the HIT vector), fp64:
+ *        pos_items[pos_ptr[j] .. pos_ptr[j+1])  the held-out items of eval user j as positions into item_ids,
+ *                                               ascending and unique;  pos_len[j] = len(test_user_dict[u_j])
+ *        out_recall_ndcg[0..1] = the two means over the n_users eval users (device doubles).
+ *      Deterministic (fixed-order sums).  workspace: kgat_recall_ndcg_workspace_bytes(n_users) bytes. */
+KGAT_API size_t kgat_recall_ndcg_workspace_bytes(int64_t n_users);
+KGAT_API int kgat_recall_ndcg(const int32_t* topk_idx, int64_t n_users, int K, const int32_t* pos_ptr,
+                     const int32_t* pos_items, const int32_t* pos_len, double* out_recall_ndcg,
+                     void* workspace, size_t workspace_bytes, kgat_stream_t stream);
+
 /* (5') the same contract with a caller-provided workspace: the fast path of the evaluation.  The user rows and
  *      the item rows are split ONCE into fp16 (hi, 2^11-scaled residual) operand tiles laid out for the tensor
  *      cores inside the workspace, every CTA keeps its 128-user tile resident and streams item tiles with bulk

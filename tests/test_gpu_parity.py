@@ -446,6 +446,35 @@ def test_eval_matches_reference_fixture(dev, golden_small, golden_eval):
     assert abs(rec - float(e["recall"])) < 1e-9 and abs(ndcg - float(e["ndcg"])) < 1e-9
 
 
+def test_recall_ndcg_kernel_matches_the_numpy_helpers(dev, golden_eval, golden_small):
+    """kgat_recall_ndcg (metric.py:5-31, :56-63 on the device, fp64) against metric.metrics_from_topk: the
+    reference's own top-20 lists, then random lists with duplicated positives (len(pos) counts them), users
+    without positives, and unfilled (-1) list entries."""
+    e = golden_eval
+    users = e["users"]
+    tr = {int(u): e["train_items"][e["train_ptr"][j]: e["train_ptr"][j + 1]] for j, u in enumerate(users)}
+    te = {int(u): e["test_items"][e["test_ptr"][j]: e["test_ptr"][j + 1]] for j, u in enumerate(users)}
+    plan = metric.EvalPlan(tr, te, int(golden_small["n_items"]))
+    top = np.argsort(-e["masked_scores"], axis=1, kind="stable")[:, :20]
+    rec, ndcg, _ = metric.metrics_from_topk(top, plan, 20)
+    rec_d, ndcg_d = metric.metrics_from_topk_device(th.from_numpy(top.astype(np.int32)).to(dev), plan, 20)
+    assert abs(rec_d - float(e["recall"])) < 1e-12 and abs(ndcg_d - float(e["ndcg"])) < 1e-12
+    assert abs(rec_d - rec) < 1e-12 and abs(ndcg_d - ndcg) < 1e-12
+    rng = np.random.default_rng(4)
+    n_items, U, K = 500, 700, 20
+    tr2 = {u: np.array([0]) for u in range(U)}
+    te2 = {u: (rng.integers(0, n_items, rng.integers(0, 30)) if u % 7 else np.zeros(0, np.int64)) for u in range(U)}
+    te2[3] = np.array([5, 5, 5, 9])                                  # duplicates: recall divides by 4
+    plan2 = metric.EvalPlan(tr2, te2, n_items)
+    top2 = np.stack([rng.permutation(n_items)[:K] for _ in range(U)]).astype(np.int32)
+    top2[11, 15:] = -1
+    top2[3, :3] = (5, 9, 7)
+    rec2, ndcg2, _ = metric.metrics_from_topk(top2, plan2, K)
+    a = metric.metrics_from_topk_device(th.from_numpy(top2).to(dev), plan2, K)
+    b = metric.metrics_from_topk_device(th.from_numpy(top2).to(dev), plan2, K)
+    assert abs(a[0] - rec2) < 1e-12 and abs(a[1] - ndcg2) < 1e-12 and a == b
+
+
 def test_eval_toy_mask_to_zero_quirk(dev, golden_g3):
     """masked train items score 0.0 and still rank (u1: [.1,.9,.5,0,0] -> [1,2,0])."""
     emb = th.nn.functional.pad(th.from_numpy(golden_g3["toy_emb"]), [0, 2]).to(dev)      # width 2 -> 4

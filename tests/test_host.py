@@ -315,9 +315,7 @@ def test_metric_helpers_and_plan(golden_g3, golden_eval, golden_small):
     rec, ndcg, _ = metric.metrics_from_topk(top, plan, 20)
     assert abs(rec - float(e["recall"])) < 1e-12 and abs(ndcg - float(e["ndcg"])) < 1e-12
     assert plan.mask_ptr[-1] == plan.mask_items.size and np.all(np.diff(plan.mask_ptr) >= 0)
-    # the on-device reduction (torch, float64) is the same arithmetic
-    rec_d, ndcg_d = metric.metrics_from_topk_device(th.from_numpy(top.astype(np.int32)), plan, 20)
-    assert abs(rec_d - rec) < 1e-12 and abs(ndcg_d - ndcg) < 1e-12
+    # (the on-device reduction, kgat_recall_ndcg, is held against this one in tests/test_gpu_parity.py)
 
 
 def test_synth_shapes():
