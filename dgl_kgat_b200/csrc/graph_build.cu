@@ -2,10 +2,8 @@
 // relation buckets, all on the device.  Replaces DGLGraph()/add_edges/readonly
 // (reference dataset.py:112-130) and the per-relation filter_edges scans
 // (reference models.py:150).  Bit-exact against oracle/graph_ref.py: every order is a
-// stable LSD radix sort (cub::DeviceRadixSort is stable) of an explicit key, so the
-// result does not depend on scheduling.
-#include <cub/device/device_radix_sort.cuh>
-
+// stable LSD radix sort (radix_sort_pairs below) of an explicit key, so the result does not
+// depend on scheduling.
 #include "common.cuh"
 #include "split.cuh"
 
@@ -86,18 +84,145 @@ __global__ void gather2(const int32_t* __restrict__ pos, int64_t n, const int32_
     }
 }
 
-struct Workspace {
-    size_t keys_a, keys_b, vals_a, cub_temp, cub_bytes, total;
-};
+// ------------------------------------------------------------------------------------------------
+// Stable LSD radix sort of (key, value) pairs, 8 bits per pass.
+//   pass:  radix_hist   block b counts the digits of its tile of TILE consecutive elements -> hist[digit][b]
+//          radix_scan   exclusive scan of hist in (digit, block) order: where block b's run of a digit starts
+//          radix_scatter  block b walks its tile in element order, 256 elements per round; the rank of an
+//                       element among the equal digits of its round comes from __match_any_sync inside the warp
+//                       plus the counts of the lower warps, rounds and blocks before it come from running bases
+//                       - so equal keys keep their input order (stable), whatever the scheduling.
+// One-off per graph; three passes for the (head, relation) key of the Amazon-book shape.
+// ------------------------------------------------------------------------------------------------
+constexpr int RADIX_BITS = 8, RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256, SORT_ROUNDS = 16, SORT_TILE = SORT_THREADS * SORT_ROUNDS;
 
 template <typename KeyT>
-size_t cub_temp_bytes(int64_t n) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const KeyT*>(nullptr),
-                                    static_cast<KeyT*>(nullptr), static_cast<const int32_t*>(nullptr),
-                                    static_cast<int32_t*>(nullptr), static_cast<int>(n), 0,
-                                    static_cast<int>(sizeof(KeyT) * 8));
-    return bytes;
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_hist_kernel(const KeyT* __restrict__ keys, int64_t n, int shift, int n_blocks, int32_t* __restrict__ hist) {
+    __shared__ int s_h[RADIX];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * SORT_TILE;
+    for (int r = 0; r < SORT_ROUNDS; ++r) {
+        const int64_t i = base + r * SORT_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&s_h[static_cast<int>((keys[i] >> shift) & (RADIX - 1))], 1);      // integer counts
+    }
+    __syncthreads();
+    hist[static_cast<size_t>(threadIdx.x) * n_blocks + blockIdx.x] = s_h[threadIdx.x];
+}
+
+// one CTA: in-place exclusive scan of the RADIX * n_blocks counters (digit-major)
+__global__ void __launch_bounds__(1024) radix_scan_kernel(int32_t* __restrict__ hist, int64_t n) {
+    __shared__ int s_w[32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t c0 = 0; c0 < n; c0 += 1024) {
+        const int64_t c = c0 + threadIdx.x;
+        const int v = c < n ? hist[c] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = s_w[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(FULL_MASK, wi, o);
+                if (lane >= o) wi += u;
+            }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        const int excl = s_base + s_w[warp] + incl - v;
+        if (c < n) hist[c] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_base = excl + v;
+        __syncthreads();
+    }
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_scatter_kernel(const KeyT* __restrict__ keys_in, const int32_t* __restrict__ vals_in, int64_t n, int shift,
+                     int n_blocks, const int32_t* __restrict__ offsets, KeyT* __restrict__ keys_out,
+                     int32_t* __restrict__ vals_out) {
+    constexpr int WARPS_ = SORT_THREADS / 32;
+    __shared__ int s_base[RADIX];                 // where this block's next element of a digit goes
+    __shared__ int s_cnt[WARPS_][RADIX];          // per-warp digit counts of the current round
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s_base[threadIdx.x] = offsets[static_cast<size_t>(threadIdx.x) * n_blocks + blockIdx.x];
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * SORT_TILE;
+    for (int r = 0; r < SORT_ROUNDS; ++r) {
+#pragma unroll
+        for (int w = 0; w < WARPS_; ++w) s_cnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t i = base + r * SORT_THREADS + threadIdx.x;
+        const bool ok = i < n;
+        KeyT k = 0;
+        int d = RADIX + lane;                     // out-of-range lanes: a group of their own, never counted
+        if (ok) { k = keys_in[i]; d = static_cast<int>((k >> shift) & (RADIX - 1)); }
+        const unsigned same = __match_any_sync(FULL_MASK, d);
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        if (ok && rank == 0) s_cnt[warp][d] = __popc(same);
+        __syncthreads();
+        if (ok) {
+            int before = 0;
+            for (int w = 0; w < warp; ++w) before += s_cnt[w][d];
+            const int dst = s_base[d] + before + rank;
+            keys_out[dst] = k;
+            vals_out[dst] = vals_in[i];
+        }
+        __syncthreads();
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS_; ++w) tot += s_cnt[w][threadIdx.x];
+        s_base[threadIdx.x] += tot;
+        __syncthreads();
+    }
+}
+
+struct Workspace {
+    size_t keys_a, keys_b, keys_c, vals_a, vals_b, hist, total;
+};
+
+inline int sort_blocks(int64_t n) { return static_cast<int>((n + SORT_TILE - 1) / SORT_TILE); }
+
+// Sorts n pairs by the low `bits` bits of the key (stable).  (ka, va) hold the input and are scratch afterwards,
+// (kb, vb) is the second pair of buffers; the result lands in (keys_out, vals_out), distinct from all four.
+template <typename KeyT>
+int radix_sort_pairs(KeyT* ka, KeyT* kb, int32_t* va, int32_t* vb, KeyT* keys_out, int32_t* vals_out, int64_t n,
+                     int bits, int32_t* hist, cudaStream_t st) {
+    const int nb = sort_blocks(n);
+    const int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
+    KeyT *kin = ka, *kout = kb;
+    int32_t *vin = va, *vout = vb;
+    for (int p = 0; p < passes; ++p) {
+        const bool last = p + 1 == passes;
+        KeyT* ko = last ? keys_out : kout;
+        int32_t* vo = last ? vals_out : vout;
+        // the last pass writes straight into the caller's arrays; they must not be the pass's own input
+        if (last && (reinterpret_cast<void*>(ko) == reinterpret_cast<void*>(kin) ||
+                     reinterpret_cast<void*>(vo) == reinterpret_cast<void*>(vin)))
+            return KGAT_ERR_INVALID_ARG;
+        radix_hist_kernel<KeyT><<<nb, SORT_THREADS, 0, st>>>(kin, n, p * RADIX_BITS, nb, hist);
+        KGAT_LAUNCH_CHECK();
+        radix_scan_kernel<<<1, 1024, 0, st>>>(hist, static_cast<int64_t>(RADIX) * nb);
+        KGAT_LAUNCH_CHECK();
+        radix_scatter_kernel<KeyT><<<nb, SORT_THREADS, 0, st>>>(kin, vin, n, p * RADIX_BITS, nb, hist, ko, vo);
+        KGAT_LAUNCH_CHECK();
+        kin = ko; vin = vo;
+        kout = (kin == ka) ? kb : ka;
+        vout = (vin == va) ? vb : va;
+    }
+    return KGAT_OK;
 }
 
 Workspace plan(int64_t n_edges) {
@@ -107,9 +232,10 @@ Workspace plan(int64_t n_edges) {
     w.keys_a = off; off += align_up(e * sizeof(uint64_t));
     w.keys_b = off; off += align_up(e * sizeof(uint64_t));
     w.vals_a = off; off += align_up(e * sizeof(int32_t));
-    size_t t64 = cub_temp_bytes<uint64_t>(n_edges), t32 = cub_temp_bytes<uint32_t>(n_edges);
-    w.cub_bytes = t64 > t32 ? t64 : t32;
-    w.cub_temp = off; off += align_up(w.cub_bytes);
+    w.vals_b = off; off += align_up(e * sizeof(int32_t));
+    w.hist = off; off += align_up(static_cast<size_t>(RADIX) * sort_blocks(static_cast<int64_t>(e)) * sizeof(int32_t));
+    // the sorted keys land in a third array: the last pass of a sort must not write into its own input
+    w.keys_c = off; off += align_up(e * sizeof(uint64_t));
     w.total = off;
     return w;
 }
@@ -123,11 +249,10 @@ int sort_edges_by_head_rel(const kgat_graph_t* g, const int32_t* head, const int
     int32_t* va = reinterpret_cast<int32_t*>(ws + w.vals_a);
     make_edge_keys<KeyT><<<blocks_for(E), TPB, 0, st>>>(head, rel, g->n_rel, E, ka, va);
     KGAT_LAUNCH_CHECK();
-    size_t bytes = w.cub_bytes;
     uint64_t max_key = static_cast<uint64_t>(g->n_nodes) * static_cast<uint64_t>(g->n_rel);
-    KGAT_CUDA(cub::DeviceRadixSort::SortPairs(ws + w.cub_temp, bytes, ka, kb, va, g->csr_eid,
-                                              static_cast<int>(E), 0, bits_for(max_key), st));
-    return KGAT_OK;
+    return radix_sort_pairs<KeyT>(ka, kb, va, reinterpret_cast<int32_t*>(ws + w.vals_b),
+                                  reinterpret_cast<KeyT*>(ws + w.keys_c), g->csr_eid, E, bits_for(max_key),
+                                  reinterpret_cast<int32_t*>(ws + w.hist), st);
 }
 
 // Segment table of one side (split.cuh): one CTA walks the row pointer in chunks of 1024 rows; a block-wide
@@ -256,14 +381,16 @@ extern "C" int kgat_graph_build(const kgat_graph_t* g, const int32_t* head, cons
     uint32_t* ka = reinterpret_cast<uint32_t*>(ws + w.keys_a);
     uint32_t* kb = reinterpret_cast<uint32_t*>(ws + w.keys_b);
     int32_t* va = reinterpret_cast<int32_t*>(ws + w.vals_a);
-    size_t bytes = w.cub_bytes;
+    int32_t* vb = reinterpret_cast<int32_t*>(ws + w.vals_b);
+    uint32_t* kc = reinterpret_cast<uint32_t*>(ws + w.keys_c);          // sorted keys
+    int32_t* hist = reinterpret_cast<int32_t*>(ws + w.hist);
 
     // CSC: stable sort of CSR positions by tail
     copy_keys_iota<<<blocks_for(E), TPB, 0, st>>>(g->csr_src, E, ka, va);
     KGAT_LAUNCH_CHECK();
-    KGAT_CUDA(cub::DeviceRadixSort::SortPairs(ws + w.cub_temp, bytes, ka, kb, va, g->csc_pos,
-                                              static_cast<int>(E), 0, bits_for(static_cast<uint64_t>(N)), st));
-    segment_offsets<uint32_t><<<blocks_for(N + 1), TPB, 0, st>>>(kb, E, N, g->csc_ptr);
+    rc = radix_sort_pairs<uint32_t>(ka, kb, va, vb, kc, g->csc_pos, E, bits_for(static_cast<uint64_t>(N)), hist, st);
+    if (rc != KGAT_OK) return rc;
+    segment_offsets<uint32_t><<<blocks_for(N + 1), TPB, 0, st>>>(kc, E, N, g->csc_ptr);
     KGAT_LAUNCH_CHECK();
     gather2<<<blocks_for(E), TPB, 0, st>>>(g->csc_pos, E, g->csr_dst, g->csr_eid, g->csc_dst, g->csc_eid);
     KGAT_LAUNCH_CHECK();
@@ -271,9 +398,9 @@ extern "C" int kgat_graph_build(const kgat_graph_t* g, const int32_t* head, cons
     // relation buckets: stable sort of CSR positions by relation
     copy_keys_iota<<<blocks_for(E), TPB, 0, st>>>(g->csr_rel, E, ka, va);
     KGAT_LAUNCH_CHECK();
-    KGAT_CUDA(cub::DeviceRadixSort::SortPairs(ws + w.cub_temp, bytes, ka, kb, va, g->bk_pos,
-                                              static_cast<int>(E), 0, bits_for(static_cast<uint64_t>(R)), st));
-    segment_offsets<uint32_t><<<blocks_for(R + 1), TPB, 0, st>>>(kb, E, R, g->rel_ptr);
+    rc = radix_sort_pairs<uint32_t>(ka, kb, va, vb, kc, g->bk_pos, E, bits_for(static_cast<uint64_t>(R)), hist, st);
+    if (rc != KGAT_OK) return rc;
+    segment_offsets<uint32_t><<<blocks_for(R + 1), TPB, 0, st>>>(kc, E, R, g->rel_ptr);
     KGAT_LAUNCH_CHECK();
     gather2<<<blocks_for(E), TPB, 0, st>>>(g->bk_pos, E, g->csr_dst, g->csr_src, g->bk_head, g->bk_tail);
     KGAT_LAUNCH_CHECK();
