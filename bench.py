@@ -156,7 +156,7 @@ def measured_tensor_peak():
     return 1650.0, "fallback (B200_PROFILING.md)"
 
 
-TRAFFIC_FILES = ("traffic_r2f.json", "traffic_r2.json", "traffic_r1.json")     # newest capture first
+TRAFFIC_FILES = ("traffic_r2k.json", "traffic_r2f.json", "traffic_r2.json", "traffic_r1.json")     # newest capture first
 
 
 def traffic_source(kernel):
