@@ -112,17 +112,21 @@ radix_hist_kernel(const KeyT* __restrict__ keys, int64_t n, int shift, int n_blo
     hist[static_cast<size_t>(threadIdx.x) * n_blocks + blockIdx.x] = s_h[threadIdx.x];
 }
 
-// one CTA: in-place exclusive scan of the RADIX * n_blocks counters (digit-major)
+// one CTA: in-place exclusive scan of the RADIX * n_blocks counters (digit-major), four consecutive counters per
+// thread and iteration (4096 per trip through the block-wide scan)
 __global__ void __launch_bounds__(1024) radix_scan_kernel(int32_t* __restrict__ hist, int64_t n) {
     __shared__ int s_w[32];
     __shared__ int s_base;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t c0 = 0; c0 < n; c0 += 1024) {
-        const int64_t c = c0 + threadIdx.x;
-        const int v = c < n ? hist[c] : 0;
-        int incl = v;
+    for (int64_t c0 = 0; c0 < n; c0 += 4096) {
+        const int64_t c = c0 + 4 * static_cast<int64_t>(threadIdx.x);
+        int v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = c + j < n ? hist[c + j] : 0;
+        const int t = v[0] + v[1] + v[2] + v[3];
+        int incl = t;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int u = __shfl_up_sync(FULL_MASK, incl, o);
@@ -141,10 +145,14 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(int32_t* __restrict__ 
             s_w[lane] = wi - w;
         }
         __syncthreads();
-        const int excl = s_base + s_w[warp] + incl - v;
-        if (c < n) hist[c] = excl;
+        int run = s_base + s_w[warp] + incl - t;             // exclusive prefix of this thread's first counter
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (c + j < n) hist[c + j] = run;
+            run += v[j];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) s_base = excl + v;
+        if (threadIdx.x == 1023) s_base = run;
         __syncthreads();
     }
 }
