@@ -85,13 +85,16 @@ class EvalPlan:
         positions into the item range, and len(test_user_dict[u]) (duplicates counted, metric.py:60)."""
         key = "pos:" + str(device)
         if key not in self._dev:
-            rows = self.pos_keys // max(self.n_items, 1)
-            ptr = np.zeros(self.n_users + 1, dtype=np.int64)
-            np.cumsum(np.bincount(rows, minlength=self.n_users), out=ptr[1:])
-            items = (self.pos_keys % max(self.n_items, 1)).astype(np.int32)      # keys are sorted: ascending per user
-            self._dev[key] = tuple(th.from_numpy(np.ascontiguousarray(a)).to(device)
-                                   for a in (ptr.astype(np.int32), items, self.pos_len.astype(np.int32)))
+            self._dev[key] = tuple(th.from_numpy(np.ascontiguousarray(a)).to(device) for a in self.positives_csr())
         return self._dev[key]
+
+    def positives_csr(self):
+        """(pos_ptr[n_users + 1], pos_items, pos_len) int32 host arrays - what kgat_recall_ndcg reads."""
+        rows = self.pos_keys // max(self.n_items, 1)
+        ptr = np.zeros(self.n_users + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=self.n_users), out=ptr[1:])
+        items = (self.pos_keys % max(self.n_items, 1)).astype(np.int32)          # keys are sorted: ascending per user
+        return ptr.astype(np.int32), items, self.pos_len.astype(np.int32)
 
 
 _PLAN_CACHE = {}

@@ -315,7 +315,12 @@ def test_metric_helpers_and_plan(golden_g3, golden_eval, golden_small):
     rec, ndcg, _ = metric.metrics_from_topk(top, plan, 20)
     assert abs(rec - float(e["recall"])) < 1e-12 and abs(ndcg - float(e["ndcg"])) < 1e-12
     assert plan.mask_ptr[-1] == plan.mask_items.size and np.all(np.diff(plan.mask_ptr) >= 0)
-    # (the on-device reduction, kgat_recall_ndcg, is held against this one in tests/test_gpu_parity.py)
+    # (the on-device reduction, kgat_recall_ndcg, is held against this one in tests/test_gpu_parity.py); its inputs:
+    ptr, items, pos_len = plan.positives_csr()
+    assert ptr[0] == 0 and ptr[-1] == len(items) and len(ptr) == plan.n_users + 1
+    for j, u in enumerate(te):
+        assert items[ptr[j]: ptr[j + 1]].tolist() == sorted(set(int(x) for x in te[u]))
+        assert pos_len[j] == len(te[u])                     # duplicates counted, as len(test_user_dict[u]) does
 
 
 def test_synth_shapes():
