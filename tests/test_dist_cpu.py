@@ -121,6 +121,25 @@ def _worker(rank, world, port, ret):
         emb_single = kgat_ref.gnn(p, trip, w_single, N)
         assert th.allclose(emb_local[own], emb_single[own], rtol=1e-12, atol=1e-14)
 
+        # --- attention plan: (head, relation) runs never straddle ranks (a rank owns whole head rows), so the
+        # per-relation edge / run counts of the local in-edge graphs add up to the global ones and every rank
+        # reaches the single-GPU decision (dist.DistKGAT all-reduces exactly these counts)
+        from oracle import graph_ref
+        from dgl_kgat_b200 import ops
+
+        def rel_counts(t):
+            st = graph_ref.build_structure(t, N, R)
+            runs = graph_ref.build_runs(st, R)
+            return np.diff(st["rel_ptr"].astype(np.int64)), np.diff(runs["rel_run_ptr"].astype(np.int64))
+        e_loc, r_loc = rel_counts(sub_in)
+        counts = th.from_numpy(np.stack([e_loc, r_loc]))
+        tdist.all_reduce(counts)
+        e_glob, r_glob = rel_counts(trip)
+        assert np.array_equal(counts[0].numpy(), e_glob) and np.array_equal(counts[1].numpy(), r_glob)
+        impl, mode = ops.attention_plan_for(counts[0].numpy(), counts[1].numpy())
+        impl1, mode1 = ops.attention_plan_for(e_glob, r_glob)
+        assert impl == impl1 and np.array_equal(mode, mode1)
+
         # --- loss rows: owner contributes, all-reduce, backward scatters locally
         emb = emb_single.clone()
         mask = th.zeros(N, 1, dtype=th.float64); mask[own] = 1
